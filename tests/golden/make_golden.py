@@ -1,0 +1,154 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the UNMODIFIED compiled reference.
+
+Run in the build container only (needs /root/reference -> oracle/_ref, see
+oracle/build.py):   python tests/golden/make_golden.py
+
+Each file holds the inputs (float64 frames, masks, positions, parameters) and
+what the reference's own UMPAModel*.match() / hooks returned for them, so the
+C oracle (CPU tests) and the CUDA path (GPU tests) can be pinned without the
+reference being present.  The reference's test-suite has no golden vectors of
+its own; these are the substitute.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref as oref          # noqa: E402
+from umpa_b200 import synth             # noqa: E402
+
+R = oref.load()
+if R is None:
+    sys.exit("compiled reference not available (oracle/build.py needs /root/reference)")
+
+CLS = {"NoDF": R.UMPAModelNoDF, "DF": R.UMPAModelDF, "DFKernel": R.UMPAModelDFKernel}
+KEYS = ("f", "T", "dx", "dy", "df", "err", "debug_Ncalls", "debug_d", "debug_a")
+
+
+def run_case(name, kind, sam, ref, mask=None, pos=None, Nw=2, max_shift=4, abc=None,
+             assign=None, subpx=None, step=None, ROI=None, dxdy=None):
+    sam_l = [np.ascontiguousarray(s) for s in sam]
+    ref_l = [np.ascontiguousarray(r) for r in ref]
+    mask_l = None if mask is None else [np.ascontiguousarray(m) for m in mask]
+    pos_l = None if pos is None else [np.array(p) for p in pos]
+    m = CLS[kind](sam_l, ref_l, mask_list=mask_l, pos_list=pos_l, window_size=Nw, max_shift=max_shift)
+    if assign is not None:
+        m.assign_coordinates = assign
+    if subpx is not None:
+        m.sub_pixel_mode = subpx
+    kw = dict(num_threads=4, quiet=True)
+    if step is not None:
+        kw["step"] = step
+    if ROI is not None:
+        kw["ROI"] = ROI
+    if dxdy is not None:
+        kw["dxdy"] = dxdy
+    if kind == "DFKernel":
+        if abc is None:
+            abc = synth.blur_abc(*m.sh)
+        kw["abc"] = abc
+    res = m.match(**kw)
+    out = {"kind": kind, "Nw": Nw, "max_shift": max_shift, "padding": m.padding,
+           "extent": np.array(m.extent), "ROI_after": np.array(m.ROI), "sh_after": np.array(m.sh),
+           "window": np.array(m.window)}
+    # frames may be ragged (sample stepping): store one entry per frame
+    out["Na"] = len(sam_l)
+    for k, (s, r) in enumerate(zip(sam_l, ref_l)):
+        out[f"sam{k}"], out[f"ref{k}"] = s, r
+        if mask_l is not None:
+            out[f"mask{k}"] = mask_l[k]
+    if pos_l is not None:
+        out["pos"] = np.array(pos_l)
+    for k_, v in (("abc", abc), ("assign", assign), ("subpx", subpx), ("step", step),
+                  ("ROI", None if ROI is None else np.array(ROI)), ("dxdy", dxdy)):
+        if v is not None:
+            out[k_] = v
+    for k_ in KEYS:
+        if k_ in res:
+            out["out_" + k_] = res[k_]
+    # a few single-pixel probes through the reference's cost()/min() hooks
+    p = m.padding
+    probes = []
+    rng = np.random.default_rng(7)
+    H0, W0 = sam_l[0].shape
+    for _ in range(6):
+        i = int(rng.integers(p, H0 - p)); j = int(rng.integers(p, W0 - p))
+        si = int(rng.integers(-max_shift + 1, max_shift)); sj = int(rng.integers(-max_shift + 1, max_shift))
+        if kind == "DFKernel":
+            c = m.cost(i, j, si, sj, .5, .1, .4)
+        else:
+            c = m.cost(i, j, si, sj)
+        probes.append([i, j, si, sj] + list(c) + [0.] * (3 - len(c)))
+    out["cost_probes"] = np.array(probes)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    ok = res["err"] == 1
+    print(f"{name:22s} {kind:9s} out {res['f'].shape} ok {ok.mean():.3f} "
+          f"calls {res['debug_Ncalls'][ok].mean() if ok.any() else 0:.2f}")
+
+
+def main():
+    clean = synth.speckle_stack(5, 40, 44, seed=11, max_shift=4, dark_field=False)
+    clean_df = synth.speckle_stack(5, 40, 44, seed=12, max_shift=4, dark_field=True)
+    noisy = synth.speckle_stack(4, 40, 44, seed=13, max_shift=4, dark_field=True, noise=.2, amplitude=2.5)
+    lowc = synth.speckle_stack(5, 40, 44, seed=14, max_shift=4, dark_field=True, contrast=.15)
+    big = synth.speckle_stack(3, 50, 54, seed=15, max_shift=4, dark_field=True)
+    wide = synth.speckle_stack(4, 44, 48, seed=16, max_shift=6, dark_field=True, amplitude=3.2)
+
+    run_case("nodf_clean", "NoDF", clean["sam"], clean["ref"])
+    run_case("df_clean", "DF", clean_df["sam"], clean_df["ref"])
+    run_case("nodf_noisy", "NoDF", noisy["sam"], noisy["ref"])
+    run_case("df_noisy", "DF", noisy["sam"], noisy["ref"])
+    run_case("df_lowcontrast", "DF", lowc["sam"], lowc["ref"])
+    run_case("df_nw3_ms6", "DF", wide["sam"], wide["ref"], Nw=3, max_shift=6)
+    run_case("nodf_nw1", "NoDF", clean["sam"], clean["ref"], Nw=1, max_shift=3)
+    run_case("dfk_clean", "DFKernel", big["sam"], big["ref"], Nw=2, max_shift=3)
+
+    # masks: smooth positive weights with a dead block and a few dead pixels
+    rng = np.random.default_rng(5)
+    mask = .5 + .5 * rng.random(clean_df["sam"].shape)
+    mask[:, 10:14, 20:26] = 0.
+    mask[rng.random(mask.shape) < .02] = 0.
+    run_case("nodf_masked", "NoDF", clean["sam"], clean["ref"], mask=mask)
+    run_case("df_masked", "DF", clean_df["sam"], clean_df["ref"], mask=mask)
+    mask_b = .5 + .5 * rng.random(big["sam"].shape)
+    run_case("dfk_masked", "DFKernel", big["sam"], big["ref"], mask=mask_b, Nw=1, max_shift=3)
+
+    # sample stepping: ragged frames at integer offsets (model.pyx:265-283)
+    pos = [(0, 0), (3, 0), (0, 5), (2, 2), (5, 4)]
+    shapes = [(40, 44), (38, 44), (40, 40), (36, 42), (35, 40)]
+    sam_p = [clean_df["sam"][k][:h, :w].copy() for k, (h, w) in enumerate(shapes)]
+    ref_p = [clean_df["ref"][k][:h, :w].copy() for k, (h, w) in enumerate(shapes)]
+    run_case("df_positions", "DF", sam_p, ref_p, pos=pos)
+    run_case("nodf_positions", "NoDF", sam_p, ref_p, pos=pos)
+
+    # options
+    run_case("df_assign_ref", "DF", clean_df["sam"], clean_df["ref"], assign="ref")
+    run_case("df_subpx0", "DF", clean_df["sam"], clean_df["ref"], subpx=0)
+    run_case("df_subpx1", "DF", clean_df["sam"], clean_df["ref"], subpx=1)
+    run_case("df_step3", "DF", clean_df["sam"], clean_df["ref"], step=3)
+    run_case("df_roi", "DF", clean_df["sam"], clean_df["ref"], ROI=((2, 20, 2), (1, 25, 3)))
+    run_case("df_dxdy", "DF", clean_df["sam"], clean_df["ref"], dxdy=(1., -1.))
+
+    # module-level hooks (model.pyx:31-114; note spm -> spmin_quad, spmq -> spmin)
+    blocks = []
+    for n in range(8):
+        g = np.random.default_rng(100 + n)
+        yy, xx = np.mgrid[-1:3, -1:3].astype(float)
+        cy, cx = g.uniform(0, 1, 2)
+        a = .3 + (yy - cy) ** 2 + .8 * (xx - cx) ** 2 + .3 * (yy - cy) * (xx - cx) + .02 * g.random((4, 4))
+        pq, vq = R.spm(np.ascontiguousarray(a))
+        ps, vs = R.spmq(np.ascontiguousarray(a))
+        blocks.append(np.concatenate([a.ravel(), pq, [vq], ps, [vs]]))
+    kern = R.test_CostArgsDFKernel(0, 0, .45, .12, .6)
+    np.savez_compressed(os.path.join(HERE, "hooks.npz"), blocks=np.array(blocks), kernel=kern,
+                        kernel_abc=np.array([.45, .12, .6]))
+    print("hooks written")
+
+
+if __name__ == "__main__":
+    main()
