@@ -1,0 +1,168 @@
+/*
+ * umpa_b200.h -- C ABI of libumpa_b200.so, the B200 (sm_100a) implementation of
+ * UMPA++'s per-pixel window-matching path.
+ *
+ * This is the drop-in boundary.  In the reference the seam is the C++ class
+ * models::ModelBase<double> and its subclasses, driven from Cython
+ * (UMPA/Model.pxd:31-69, UMPA/model.pyx:116-997).  Every entry point below names
+ * the reference interface it replaces (paths relative to the reference root).
+ * Plain pointers and sizes only; no C++/torch types.  All functions return
+ * UMPA_OK (0) or a negative error code; umpa_last_error() gives the message of
+ * the calling thread's last failure.  Nothing throws across the boundary.
+ *
+ * Conventions
+ *  - frames are row-major (rows, cols); "i"/"0" is the row axis, "j"/"1" the column axis;
+ *  - pixel coordinates (i, j) are RAW frame coordinates (padding included), exactly
+ *    what ModelBase::min / cost_interface take (UMPA/model.pyx:482-486, 780-789);
+ *  - a shift (si, sj) is valid when |si|,|sj| <= max_shift-1 (UMPA/lib/Model.cpp:372-399);
+ *  - the model works on the CUDA device that is current when umpa_create() is called;
+ *  - "stream" arguments are a cudaStream_t passed as void* (NULL = default stream).
+ */
+#ifndef UMPA_B200_H
+#define UMPA_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define UMPA_API __attribute__((visibility("default")))
+#else
+#define UMPA_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct umpa_model umpa_model;
+
+/* model kinds: ModelNoDF / ModelDF / ModelDFKernel (UMPA/lib/Model.h:126-191) */
+enum { UMPA_NODF = 0, UMPA_DF = 1, UMPA_DFKERNEL = 2 };
+
+/* return codes */
+enum {
+    UMPA_OK = 0,
+    UMPA_ERR_ARG = -1,        /* bad argument (message says which) */
+    UMPA_ERR_CUDA = -2,       /* a CUDA call or kernel failed */
+    UMPA_ERR_STATE = -3,      /* call order (e.g. match before frames were set) */
+    UMPA_ERR_UNSUPPORTED = -4 /* request outside what the selected path implements */
+};
+
+/* options for umpa_set_option() */
+enum {
+    UMPA_OPT_SUBPX_FUNC = 1,      /* -1 spline (default) | 0 none | 1 quadratic; ModelBase::subpx_func, Model.cpp:214-221 */
+    UMPA_OPT_REFERENCE_SHIFT = 2, /* 0 (default) | 1; ModelBase::reference_shift, Model.cpp:215, 408-421 */
+    UMPA_OPT_PATH = 3             /* UMPA_PATH_*: which CUDA path match() uses */
+};
+
+/* UMPA_OPT_PATH values.  Both are CUDA paths; there is no CPU path.
+ *  TABLE: FP32 exhaustive shift tables (cross-correlation summed over frames, then
+ *         Hamming-filtered) + FP64 per-pixel solve and walk.  Needs equal frame
+ *         shapes, zero positions, no masks, a separable window, NoDF/DF.
+ *  LAZY:  one thread per pixel evaluates the reference's cost() on demand in FP64,
+ *         in the reference's summation order (all models, masks, positions).
+ *  AUTO:  TABLE when eligible, else LAZY. */
+enum { UMPA_PATH_AUTO = 0, UMPA_PATH_TABLE = 1, UMPA_PATH_LAZY = 2 };
+
+/* Output maps of umpa_match*, all row-major (N0, N1); any pointer may be NULL to
+ * skip that map.  Replaces the `values`, `err`, `debug_*` arrays that
+ * UMPAModelBase._match allocates (UMPA/model.pyx:442-474) and the per-key copies
+ * of UMPAModel*.match (model.pyx:815-822, 881-889, 990-997). */
+typedef struct umpa_outputs {
+    double *f;         /* values[...,0]  cost at the (sub-pixel) minimum      */
+    double *T;         /* values[...,1]  transmission                          */
+    double *dx;        /* values[...,2]  = uv[1], column shift                 */
+    double *dy;        /* values[...,3]  = uv[0], row shift                    */
+    double *df;        /* values[...,4]  dark field (DF only)                  */
+    int32_t *err;      /* error_status.ok per pixel (1 = ok)                   */
+    int32_t *ncalls;   /* debug_Ncalls                                         */
+    double *debug_d;   /* (N0, N1, 25) minimizer_debug.d  (UMPA/lib/Optim.h:15-21) */
+    double *debug_a;   /* (N0, N1, 16) minimizer_debug.a                       */
+} umpa_outputs;
+
+/* ---- lifetime -----------------------------------------------------------
+ * umpa_create replaces `new Model{NoDF,DF,DFKernel}<double>(Na, dim, sams, refs,
+ * masks, pos, Nw, win, max_shift, padding)` (UMPA/lib/Model.cpp:193-216, 597-604,
+ * 963-968; called from UMPA/model.pyx:292, 769, 835, 911).
+ *   dim, pos : Na x 2 int32 (rows, cols) per frame   (model.pyx:226-239, 265-283)
+ *   win      : (2Nw+1)^2 doubles, row-major          (model.pyx:691-696)
+ * Frames are supplied afterwards with umpa_set_frames(). */
+UMPA_API int umpa_create(umpa_model **out, int kind, int Na, const int32_t *dim, const int32_t *pos,
+                int Nw, const double *win, int max_shift, int padding);
+
+/* replaces `del self.c_model` (UMPA/model.pyx:308-309) */
+UMPA_API void umpa_destroy(umpa_model *m);
+
+/* ---- inputs --------------------------------------------------------------
+ * The reference keeps raw double* into the caller's numpy arrays
+ * (vector<T*> sam/ref/mask, UMPA/model.pyx:235-262).  Here the frames are staged
+ * once into device memory owned by the handle: FP64 copies (LAZY path) and,
+ * when the TABLE path is eligible, mean-centred FP32 stacks.
+ *   sam, ref : Na pointers to row-major float64 frames of shape dim[k]
+ *   mask     : Na pointers or NULL (no masks)
+ *   on_device: 0 = host pointers (pageable or pinned), 1 = device pointers
+ * The caller's buffers are not referenced after the call returns. */
+UMPA_API int umpa_set_frames(umpa_model *m, const double *const *sam, const double *const *ref,
+                    const double *const *mask, int on_device, void *stream);
+
+/* replaces ModelBase::set_window (UMPA/lib/Model.cpp:239-246; Nw setter model.pyx:702-704) */
+UMPA_API int umpa_set_window(umpa_model *m, int Nw, const double *win);
+
+/* replaces direct writes to c_model.subpx_func / reference_shift (model.pyx:742, 755) */
+UMPA_API int umpa_set_option(umpa_model *m, int option, int value);
+UMPA_API int umpa_get_option(const umpa_model *m, int option, int *value);
+
+/* ---- the hot path --------------------------------------------------------
+ * umpa_match replaces the OpenMP pixel loop of UMPAModelBase._match
+ * (UMPA/model.pyx:476-492): for xi < N0, xj < N1 it runs Model*::min at raw pixel
+ * (padding + start0 + step0*xi, padding + start1 + step1*xj).
+ *   roi    : {start0, stop0, step0, start1, stop1, step1}   (model.pyx:409-415)
+ *   uv0    : start guess (row shift, col shift) applied to every pixel, or NULL
+ *            for (0,0)                                       (model.pyx:461-465)
+ *   abc    : (N0, N1, 3) float64 blur parameters, DFKernel only (model.pyx:973-984)
+ *   cover  : (N0, N1) float64 coverage map + threshold gate, or NULL = no gate
+ *            (model.pyx:427-431, 480); skipped pixels keep zeros
+ *   out    : DEVICE pointers (umpa_match) / HOST pointers (umpa_match_host)
+ *   abc/cover are DEVICE pointers for umpa_match, HOST pointers for umpa_match_host.
+ * umpa_match is asynchronous on `stream`; umpa_match_host returns after the
+ * outputs are in host memory. */
+UMPA_API int umpa_match(umpa_model *m, const int32_t roi[6], const double uv0[2], const double *abc,
+               const double *cover, double cover_threshold, const umpa_outputs *out, void *stream);
+UMPA_API int umpa_match_host(umpa_model *m, const int32_t roi[6], const double uv0[2], const double *abc,
+                    const double *cover, double cover_threshold, const umpa_outputs *out);
+
+/* ---- single-pixel entry points (debug / tests) ---------------------------
+ * umpa_cost replaces Model*::cost_interface (UMPA/lib/Model.cpp:533-542, 887-897,
+ * 1181-1192; model.pyx:780-789, 846-856, 925-940): values = {cost, t, v};
+ * *status gets the error_status bits (1 ok, 2 bound_error, 4 dimension, 8 positive).
+ * umpa_min replaces Model*::min for one pixel (Model.cpp:562-578, 923-940, 1222-1238;
+ * model.pyx:325-332, 772-778): values has Nparam entries {f, T, dx, dy, [df | a, b, c]}
+ * (a, b, c read on input for DFKernel), uv is in/out.  Both always use the LAZY path
+ * and synchronise. */
+UMPA_API int umpa_cost(umpa_model *m, int i, int j, int si, int sj, const double abc[3],
+              double values[3], int *status);
+UMPA_API int umpa_min(umpa_model *m, int i, int j, double *values, double uv[2],
+             double dbg_d[25], double dbg_a[16], int *ncalls, int *ok);
+
+/* replaces the double loop over ModelBase::coverage (UMPA/model.pyx:499-529,
+ * UMPA/lib/Model.cpp:273-314).  out: (N0, N1) float64, host (on_device=0) or device. */
+UMPA_API int umpa_coverage(umpa_model *m, const int32_t roi[6], double *out, int on_device, void *stream);
+
+/* ---- introspection --------------------------------------------------------- */
+/* which path the last umpa_match used (UMPA_PATH_TABLE / UMPA_PATH_LAZY) and how
+ * many kernels it launched */
+UMPA_API int umpa_last_match_info(const umpa_model *m, int *path, int *kernel_launches);
+/* device time of the stages of the last TABLE-path match, measured with CUDA events on the
+ * launching stream when profiling is enabled via umpa_set_profiling(m, 1):
+ * ms[0] moments, ms[1] cross table, ms[2] mean table, ms[3] walk; returns count written */
+UMPA_API int umpa_set_profiling(umpa_model *m, int enable);
+UMPA_API int umpa_last_stage_ms(umpa_model *m, float *ms, int n);
+/* bytes of device memory currently owned by the handle */
+UMPA_API int64_t umpa_device_bytes(const umpa_model *m);
+
+UMPA_API const char *umpa_last_error(void);
+UMPA_API const char *umpa_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UMPA_B200_H */

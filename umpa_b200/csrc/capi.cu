@@ -1,0 +1,459 @@
+// capi.cu -- extern "C" boundary of libumpa_b200.so (see include/umpa_b200.h for the
+// reference interface each entry point replaces).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void umpa_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int scratch_reserve(umpa_model *m, Scratch &s, size_t bytes)
+{
+    if (s.bytes >= bytes && s.p) return UMPA_OK;
+    if (s.p) { cudaFree(s.p); m->dev_bytes -= (int64_t)s.bytes; s.p = nullptr; s.bytes = 0; }
+    cudaError_t e = cudaMalloc(&s.p, bytes);
+    if (e != cudaSuccess) {
+        umpa_set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        s.p = nullptr;
+        return UMPA_ERR_CUDA;
+    }
+    s.bytes = bytes;
+    m->dev_bytes += (int64_t)bytes;
+    return UMPA_OK;
+}
+
+namespace {
+
+// 400 * (A^T A)^-1 A^T for the quadratic basis [1,i,j,i^2,ij,j^2] on the 4x4 grid {-1..2}^2
+// (i = row).  The entries are integers (UMPA/lib/Optim.cpp:169-174 lists them); they are
+// derived here rather than typed in.
+void quad_matrix(double *Q /*6x16*/)
+{
+    double A[16][6], N[6][12];
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            const double u = i - 1., v = j - 1.;
+            const double row[6] = {1., u, v, u * u, u * v, v * v};
+            memcpy(A[4 * i + j], row, sizeof(row));
+        }
+    for (int r = 0; r < 6; r++)
+        for (int c = 0; c < 6; c++) {
+            double s = 0.;
+            for (int n = 0; n < 16; n++) s += A[n][r] * A[n][c];
+            N[r][c] = s;
+            N[r][6 + c] = (r == c) ? 1. : 0.;
+        }
+    for (int p = 0; p < 6; p++) {
+        int best = p;
+        for (int r = p + 1; r < 6; r++)
+            if (fabs(N[r][p]) > fabs(N[best][p])) best = r;
+        if (best != p)
+            for (int c = 0; c < 12; c++) std::swap(N[p][c], N[best][c]);
+        const double d = N[p][p];
+        for (int c = 0; c < 12; c++) N[p][c] /= d;
+        for (int r = 0; r < 6; r++)
+            if (r != p) {
+                const double f = N[r][p];
+                for (int c = 0; c < 12; c++) N[r][c] -= f * N[p][c];
+            }
+    }
+    for (int r = 0; r < 6; r++)
+        for (int n = 0; n < 16; n++) {
+            double s = 0.;
+            for (int c = 0; c < 6; c++) s += N[r][6 + c] * A[n][c];
+            Q[16 * r + n] = std::round(400. * s);
+        }
+}
+
+int nparam(int kind) { return kind == UMPA_NODF ? 4 : (kind == UMPA_DF ? 5 : 7); }
+
+// window bookkeeping: copy, separability test (w == r c^T / total), device copies
+int install_window(umpa_model *m, int Nw, const double *win)
+{
+    if (Nw < 0) { umpa_set_error("Nw must be non-negative."); return UMPA_ERR_ARG; }   // Model.cpp:242
+    const int K = 2 * Nw + 1;
+    m->Nw = Nw; m->K = K;
+    m->win.assign(win, win + K * K);
+    std::vector<double> r(K, 0.), c(K, 0.);
+    double tot = 0., wmax = 0.;
+    for (int a = 0; a < K; a++)
+        for (int b = 0; b < K; b++) {
+            r[a] += win[a * K + b]; c[b] += win[a * K + b]; tot += win[a * K + b];
+            wmax = std::max(wmax, fabs(win[a * K + b]));
+        }
+    m->win_sum = tot;
+    bool sep = tot != 0. && K <= UMPA_MAX_K;
+    double asym = 0.;
+    if (sep)
+        for (int a = 0; a < K; a++) {
+            asym = std::max(asym, fabs(r[a] - c[a]));
+            for (int b = 0; b < K; b++)
+                if (fabs(win[a * K + b] - r[a] * c[b] / tot) > 1e-13 * wmax) sep = false;
+        }
+    if (sep && asym > 1e-13 * fabs(tot)) sep = false;      // need the same factor on both axes
+    m->separable = sep;
+    m->g.assign(K, 0.);
+    std::vector<float> gf(K, 0.f);
+    if (sep)
+        for (int a = 0; a < K; a++) { m->g[a] = r[a] / sqrt(fabs(tot)) * (tot < 0 ? -1. : 1.); gf[a] = (float)m->g[a]; }
+    // g (x) g = r r^T / tot = win.  Its float copy sums to win_sum only to FP32 accuracy; the
+    // walk divides by the FP64 sum of the *float* factor products where it matters (see table_path.cu).
+    if (m->d_win) cudaFree(m->d_win);
+    if (m->d_g) cudaFree(m->d_g);
+    m->d_win = nullptr; m->d_g = nullptr;
+    UMPA_CUDA(cudaMalloc(&m->d_win, K * K * sizeof(double)));
+    UMPA_CUDA(cudaMalloc(&m->d_g, std::max(K, 1) * sizeof(float)));
+    UMPA_CUDA(cudaMemcpy(m->d_win, win, K * K * sizeof(double), cudaMemcpyHostToDevice));
+    UMPA_CUDA(cudaMemcpy(m->d_g, gf.data(), K * sizeof(float), cudaMemcpyHostToDevice));
+    if (sep) {
+        // the table path filters with the FP32 factor: use ITS exact sum as "sum of window"
+        double gs = 0.;
+        for (int a = 0; a < K; a++) gs += (double)gf[a];
+        m->win_sum = gs * gs;
+    }
+    m->moments_valid = false;
+    return UMPA_OK;
+}
+
+int make_roi(const umpa_model *m, const int32_t roi[6], const double uv0[2], RoiView *v)
+{
+    if (!roi) { umpa_set_error("roi is NULL"); return UMPA_ERR_ARG; }
+    if (roi[2] < 1 || roi[5] < 1) { umpa_set_error("ROI steps must be >= 1"); return UMPA_ERR_ARG; }
+    v->off0 = m->padding + roi[0]; v->step0 = roi[2];
+    v->off1 = m->padding + roi[3]; v->step1 = roi[5];
+    v->N0 = 1 + (roi[1] - roi[0] - 1) / roi[2];                 // model.pyx:414-415
+    v->N1 = 1 + (roi[4] - roi[3] - 1) / roi[5];
+    if (roi[1] <= roi[0]) v->N0 = 0;
+    if (roi[4] <= roi[3]) v->N1 = 0;
+    v->uv0[0] = uv0 ? uv0[0] : 0.; v->uv0[1] = uv0 ? uv0[1] : 0.;
+    v->abc = nullptr; v->cover = nullptr; v->cover_threshold = 0.;
+    return UMPA_OK;
+}
+
+// every pixel the ROI can touch must lie inside every frame the reference would read
+int check_roi_bounds(const umpa_model *m, const RoiView &v)
+{
+    if (v.N0 <= 0 || v.N1 <= 0) return UMPA_OK;
+    if (!m->uniform) return UMPA_OK;       // ragged frames: the reach test (Model.cpp:430-433) guards per frame
+    const int reach = m->padding;          // max_shift + Nw + safe_crop
+    const int i_lo = v.off0, i_hi = v.off0 + (v.N0 - 1) * v.step0;
+    const int j_lo = v.off1, j_hi = v.off1 + (v.N1 - 1) * v.step1;
+    if (i_lo - reach < 0 || i_hi + reach > m->H || j_lo - reach < 0 || j_hi + reach > m->W) {
+        umpa_set_error("ROI rows [%d,%d] cols [%d,%d] (raw) reach outside the %dx%d frames (padding %d)",
+                       i_lo, i_hi, j_lo, j_hi, m->H, m->W, reach);
+        return UMPA_ERR_ARG;
+    }
+    return UMPA_OK;
+}
+
+void free_frames(umpa_model *m)
+{
+    for (void *p : {(void *)m->d_sam64, (void *)m->d_ref64, (void *)m->d_mask64, (void *)m->d_sam_ptrs,
+                    (void *)m->d_ref_ptrs, (void *)m->d_mask_ptrs, (void *)m->d_sam32, (void *)m->d_ref32,
+                    (void *)m->d_mean_s, (void *)m->d_mean_r, (void *)m->d_means64, (void *)m->d_partials})
+        if (p) cudaFree(p);
+    m->d_sam64 = m->d_ref64 = m->d_mask64 = nullptr;
+    m->d_sam_ptrs = m->d_ref_ptrs = m->d_mask_ptrs = nullptr;
+    m->d_sam32 = m->d_ref32 = nullptr;
+    m->d_mean_s = m->d_mean_r = nullptr;
+    m->d_means64 = m->d_partials = nullptr;
+    m->frames_set = false;
+}
+
+int zero_outputs(const umpa_outputs &o, size_t n, cudaStream_t st)
+{
+    if (o.f) UMPA_CUDA(cudaMemsetAsync(o.f, 0, n * sizeof(double), st));
+    if (o.T) UMPA_CUDA(cudaMemsetAsync(o.T, 0, n * sizeof(double), st));
+    if (o.dx) UMPA_CUDA(cudaMemsetAsync(o.dx, 0, n * sizeof(double), st));
+    if (o.dy) UMPA_CUDA(cudaMemsetAsync(o.dy, 0, n * sizeof(double), st));
+    if (o.df) UMPA_CUDA(cudaMemsetAsync(o.df, 0, n * sizeof(double), st));
+    if (o.err) UMPA_CUDA(cudaMemsetAsync(o.err, 0, n * sizeof(int32_t), st));
+    if (o.ncalls) UMPA_CUDA(cudaMemsetAsync(o.ncalls, 0, n * sizeof(int32_t), st));
+    if (o.debug_d) UMPA_CUDA(cudaMemsetAsync(o.debug_d, 0, 25 * n * sizeof(double), st));
+    if (o.debug_a) UMPA_CUDA(cudaMemsetAsync(o.debug_a, 0, 16 * n * sizeof(double), st));
+    return UMPA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *umpa_last_error(void) { return g_err; }
+const char *umpa_version(void) { return "umpa_b200 0.1 (sm_100a)"; }
+
+int umpa_create(umpa_model **out, int kind, int Na, const int32_t *dim, const int32_t *pos, int Nw,
+                const double *win, int max_shift, int padding)
+{
+    if (!out || !dim || !win) { umpa_set_error("umpa_create: NULL argument"); return UMPA_ERR_ARG; }
+    if (kind < UMPA_NODF || kind > UMPA_DFKERNEL) { umpa_set_error("umpa_create: unknown model kind %d", kind); return UMPA_ERR_ARG; }
+    if (Na < 1) { umpa_set_error("umpa_create: Na must be >= 1"); return UMPA_ERR_ARG; }
+    if (max_shift < 1 || padding < 0) { umpa_set_error("umpa_create: bad max_shift/padding"); return UMPA_ERR_ARG; }
+    umpa_model *m = new (std::nothrow) umpa_model();
+    if (!m) { umpa_set_error("out of host memory"); return UMPA_ERR_ARG; }
+    m->kind = kind; m->Na = Na; m->max_shift = max_shift; m->padding = padding;
+    cudaError_t e = cudaGetDevice(&m->device);
+    if (e != cudaSuccess) { umpa_set_error("no CUDA device: %s", cudaGetErrorString(e)); delete m; return UMPA_ERR_CUDA; }
+    m->dim.assign(dim, dim + 2 * Na);
+    if (pos) m->pos.assign(pos, pos + 2 * Na); else m->pos.assign(2 * Na, 0);
+    m->uniform = true;
+    for (int k = 0; k < Na; k++) {
+        if (m->dim[2 * k] < 1 || m->dim[2 * k + 1] < 1) { umpa_set_error("frame %d has an empty shape", k); delete m; return UMPA_ERR_ARG; }
+        if (m->pos[2 * k] < 0 || m->pos[2 * k + 1] < 0) {
+            umpa_set_error("Negative frame positions (entries in pos_list) are not allowed.");   // model.pyx:274-276
+            delete m; return UMPA_ERR_ARG;
+        }
+        if (m->dim[2 * k] != m->dim[0] || m->dim[2 * k + 1] != m->dim[1] || m->pos[2 * k] || m->pos[2 * k + 1]) m->uniform = false;
+    }
+    m->H = m->dim[0]; m->W = m->dim[1];
+    int rc = install_window(m, Nw, win);
+    if (rc) { umpa_destroy(m); return rc; }
+    double Q[96];
+    quad_matrix(Q);
+    if (cudaMalloc(&m->d_dim, 2 * Na * sizeof(int)) != cudaSuccess || cudaMalloc(&m->d_pos, 2 * Na * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&m->d_quad, sizeof(Q)) != cudaSuccess) {
+        umpa_set_error("cudaMalloc failed in umpa_create"); umpa_destroy(m); return UMPA_ERR_CUDA;
+    }
+    cudaMemcpy(m->d_dim, m->dim.data(), 2 * Na * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(m->d_pos, m->pos.data(), 2 * Na * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(m->d_quad, Q, sizeof(Q), cudaMemcpyHostToDevice);
+    *out = m;
+    return UMPA_OK;
+}
+
+void umpa_destroy(umpa_model *m)
+{
+    if (!m) return;
+    free_frames(m);
+    for (Scratch *s : {&m->filtA, &m->filtB, &m->auxS, &m->auxR, &m->tabX, &m->tabM})
+        if (s->p) cudaFree(s->p);
+    for (void *p : {(void *)m->d_dim, (void *)m->d_pos, (void *)m->d_win, (void *)m->d_quad, (void *)m->d_g})
+        if (p) cudaFree(p);
+    for (int i = 0; i < 5; i++)
+        if (m->ev[i]) cudaEventDestroy(m->ev[i]);
+    delete m;
+}
+
+int umpa_set_frames(umpa_model *m, const double *const *sam, const double *const *ref, const double *const *mask,
+                    int on_device, void *stream)
+{
+    if (!m || !sam || !ref) { umpa_set_error("umpa_set_frames: NULL argument"); return UMPA_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    free_frames(m);
+    const int Na = m->Na;
+    m->frame_off.assign(Na, 0);
+    size_t total = 0;
+    for (int k = 0; k < Na; k++) { m->frame_off[k] = total; total += (size_t)m->dim[2 * k] * m->dim[2 * k + 1]; }
+    m->stack_elems = total;
+    m->masked = mask != nullptr;
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const double *const *srcs[3] = {sam, ref, mask};
+    double **dsts[3] = {&m->d_sam64, &m->d_ref64, &m->d_mask64};
+    const double ***ptrs[3] = {&m->d_sam_ptrs, &m->d_ref_ptrs, &m->d_mask_ptrs};
+    for (int a = 0; a < 3; a++) {
+        if (!srcs[a]) continue;
+        UMPA_CUDA(cudaMalloc(dsts[a], total * sizeof(double)));
+        UMPA_CUDA(cudaMalloc((void **)ptrs[a], Na * sizeof(double *)));
+        std::vector<const double *> hp(Na);
+        for (int k = 0; k < Na; k++) {
+            if (!srcs[a][k]) { umpa_set_error("umpa_set_frames: frame %d is NULL", k); return UMPA_ERR_ARG; }
+            const size_t n = (size_t)m->dim[2 * k] * m->dim[2 * k + 1];
+            UMPA_CUDA(cudaMemcpyAsync(*dsts[a] + m->frame_off[k], srcs[a][k], n * sizeof(double), kind, st));
+            hp[k] = *dsts[a] + m->frame_off[k];
+        }
+        UMPA_CUDA(cudaMemcpyAsync((void *)*ptrs[a], hp.data(), Na * sizeof(double *), cudaMemcpyHostToDevice, st));
+        UMPA_CUDA(cudaStreamSynchronize(st));          // hp goes out of scope
+    }
+    m->dev_bytes += (int64_t)(total * sizeof(double) * (mask ? 3 : 2));
+    m->frames_set = true;
+    int rc = table_prepare_frames(m, st);
+    if (rc) return rc;
+    UMPA_CUDA(cudaStreamSynchronize(st));
+    return UMPA_OK;
+}
+
+int umpa_set_window(umpa_model *m, int Nw, const double *win)
+{
+    if (!m || !win) { umpa_set_error("umpa_set_window: NULL argument"); return UMPA_ERR_ARG; }
+    return install_window(m, Nw, win);
+}
+
+int umpa_set_option(umpa_model *m, int option, int value)
+{
+    if (!m) { umpa_set_error("NULL model"); return UMPA_ERR_ARG; }
+    switch (option) {
+        case UMPA_OPT_SUBPX_FUNC: m->subpx = value; return UMPA_OK;
+        case UMPA_OPT_REFERENCE_SHIFT: m->refshift = value ? 1 : 0; return UMPA_OK;
+        case UMPA_OPT_PATH:
+            if (value < UMPA_PATH_AUTO || value > UMPA_PATH_LAZY) { umpa_set_error("unknown path %d", value); return UMPA_ERR_ARG; }
+            m->path_opt = value; return UMPA_OK;
+    }
+    umpa_set_error("unknown option %d", option);
+    return UMPA_ERR_ARG;
+}
+
+int umpa_get_option(const umpa_model *m, int option, int *value)
+{
+    if (!m || !value) { umpa_set_error("NULL argument"); return UMPA_ERR_ARG; }
+    switch (option) {
+        case UMPA_OPT_SUBPX_FUNC: *value = m->subpx; return UMPA_OK;
+        case UMPA_OPT_REFERENCE_SHIFT: *value = m->refshift; return UMPA_OK;
+        case UMPA_OPT_PATH: *value = m->path_opt; return UMPA_OK;
+    }
+    umpa_set_error("unknown option %d", option);
+    return UMPA_ERR_ARG;
+}
+
+int umpa_match(umpa_model *m, const int32_t roi[6], const double uv0[2], const double *abc, const double *cover,
+               double cover_threshold, const umpa_outputs *out, void *stream)
+{
+    if (!m || !out) { umpa_set_error("umpa_match: NULL argument"); return UMPA_ERR_ARG; }
+    if (!m->frames_set) { umpa_set_error("umpa_match: frames were not set"); return UMPA_ERR_STATE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    RoiView v;
+    int rc = make_roi(m, roi, uv0, &v);
+    if (rc) return rc;
+    m->last_launches = 0;
+    m->ev_valid = false;
+    if (v.N0 <= 0 || v.N1 <= 0) { m->last_path = 0; return UMPA_OK; }
+    if ((rc = check_roi_bounds(m, v))) return rc;
+    v.abc = abc; v.cover = cover; v.cover_threshold = cover_threshold;
+    if (m->kind == UMPA_DFKERNEL && !abc) { umpa_set_error("abc array has to be provided"); return UMPA_ERR_ARG; }   // model.pyx:973-974
+    const size_t n = (size_t)v.N0 * v.N1;
+    if (cover) { if ((rc = zero_outputs(*out, n, st))) return rc; }
+    else if (out->df && m->kind != UMPA_DF) UMPA_CUDA(cudaMemsetAsync(out->df, 0, n * sizeof(double), st));
+
+    std::string why;
+    bool use_table = false;
+    if (m->path_opt != UMPA_PATH_LAZY) {
+        use_table = table_eligible(m, v, &why);
+        if (!use_table && m->path_opt == UMPA_PATH_TABLE) {
+            umpa_set_error("table path requested but not eligible: %s", why.c_str());
+            return UMPA_ERR_UNSUPPORTED;
+        }
+    }
+    if (use_table) { m->last_path = UMPA_PATH_TABLE; return table_match(m, v, *out, st); }
+    m->last_path = UMPA_PATH_LAZY;
+    return lazy_match(m, v, *out, st);
+}
+
+int umpa_match_host(umpa_model *m, const int32_t roi[6], const double uv0[2], const double *abc, const double *cover,
+                    double cover_threshold, const umpa_outputs *out)
+{
+    if (!m || !out) { umpa_set_error("umpa_match_host: NULL argument"); return UMPA_ERR_ARG; }
+    RoiView v;
+    int rc = make_roi(m, roi, uv0, &v);
+    if (rc) return rc;
+    if (v.N0 <= 0 || v.N1 <= 0) return UMPA_OK;
+    const size_t n = (size_t)v.N0 * v.N1;
+    // one device block: f,T,dx,dy,df | debug_d | debug_a | abc | cover | err,ncalls
+    size_t nd = 5 * n + (out->debug_d ? 25 * n : 0) + (out->debug_a ? 16 * n : 0) + (abc ? 3 * n : 0) + (cover ? n : 0);
+    void *block = nullptr;
+    UMPA_CUDA(cudaMalloc(&block, nd * sizeof(double) + 2 * n * sizeof(int32_t)));
+    double *p = (double *)block;
+    umpa_outputs d{};
+    d.f = p; p += n; d.T = p; p += n; d.dx = p; p += n; d.dy = p; p += n; d.df = p; p += n;
+    if (out->debug_d) { d.debug_d = p; p += 25 * n; }
+    if (out->debug_a) { d.debug_a = p; p += 16 * n; }
+    double *d_abc = nullptr, *d_cover = nullptr;
+    if (abc) { d_abc = p; p += 3 * n; }
+    if (cover) { d_cover = p; p += n; }
+    d.err = (int32_t *)p; d.ncalls = d.err + n;
+    cudaError_t e = cudaSuccess;
+    if (abc) e = cudaMemcpy(d_abc, abc, 3 * n * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && cover) e = cudaMemcpy(d_cover, cover, n * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(block); umpa_set_error("H2D copy failed: %s", cudaGetErrorString(e)); return UMPA_ERR_CUDA; }
+    rc = umpa_match(m, roi, uv0, d_abc, d_cover, cover_threshold, &d, nullptr);
+    if (rc == UMPA_OK) {
+        e = cudaDeviceSynchronize();
+        auto back = [&](void *dst, const void *src, size_t bytes) {
+            if (dst && e == cudaSuccess) e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+        };
+        back(out->f, d.f, n * sizeof(double)); back(out->T, d.T, n * sizeof(double));
+        back(out->dx, d.dx, n * sizeof(double)); back(out->dy, d.dy, n * sizeof(double));
+        back(out->df, d.df, n * sizeof(double));
+        back(out->debug_d, d.debug_d, 25 * n * sizeof(double)); back(out->debug_a, d.debug_a, 16 * n * sizeof(double));
+        back(out->err, d.err, n * sizeof(int32_t)); back(out->ncalls, d.ncalls, n * sizeof(int32_t));
+        if (e != cudaSuccess) { umpa_set_error("match failed on the device: %s", cudaGetErrorString(e)); rc = UMPA_ERR_CUDA; }
+    }
+    cudaFree(block);
+    return rc;
+}
+
+int umpa_cost(umpa_model *m, int i, int j, int si, int sj, const double abc[3], double values[3], int *status)
+{
+    if (!m || !values) { umpa_set_error("umpa_cost: NULL argument"); return UMPA_ERR_ARG; }
+    if (!m->frames_set) { umpa_set_error("umpa_cost: frames were not set"); return UMPA_ERR_STATE; }
+    return lazy_cost(m, i, j, si, sj, abc, values, status);
+}
+
+int umpa_min(umpa_model *m, int i, int j, double *values, double uv[2], double dbg_d[25], double dbg_a[16],
+             int *ncalls, int *ok)
+{
+    if (!m || !values || !uv) { umpa_set_error("umpa_min: NULL argument"); return UMPA_ERR_ARG; }
+    if (!m->frames_set) { umpa_set_error("umpa_min: frames were not set"); return UMPA_ERR_STATE; }
+    return lazy_min(m, i, j, values, uv, dbg_d, dbg_a, ncalls, ok);
+}
+
+int umpa_coverage(umpa_model *m, const int32_t roi[6], double *out, int on_device, void *stream)
+{
+    if (!m || !out) { umpa_set_error("umpa_coverage: NULL argument"); return UMPA_ERR_ARG; }
+    if (!m->frames_set) { umpa_set_error("umpa_coverage: frames were not set"); return UMPA_ERR_STATE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    RoiView v;
+    int rc = make_roi(m, roi, nullptr, &v);
+    if (rc) return rc;
+    if (v.N0 <= 0 || v.N1 <= 0) return UMPA_OK;
+    const size_t n = (size_t)v.N0 * v.N1;
+    if (on_device) return coverage_map(m, v, out, st);
+    double *d = nullptr;
+    UMPA_CUDA(cudaMalloc(&d, n * sizeof(double)));
+    rc = coverage_map(m, v, d, st);
+    cudaError_t e = cudaSuccess;
+    if (rc == UMPA_OK) {
+        e = cudaMemcpyAsync(out, d, n * sizeof(double), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    cudaFree(d);
+    if (e != cudaSuccess) { umpa_set_error("coverage failed: %s", cudaGetErrorString(e)); return UMPA_ERR_CUDA; }
+    return rc;
+}
+
+int umpa_last_match_info(const umpa_model *m, int *path, int *kernel_launches)
+{
+    if (!m) { umpa_set_error("NULL model"); return UMPA_ERR_ARG; }
+    if (path) *path = m->last_path;
+    if (kernel_launches) *kernel_launches = m->last_launches;
+    return UMPA_OK;
+}
+
+int umpa_set_profiling(umpa_model *m, int enable)
+{
+    if (!m) { umpa_set_error("NULL model"); return UMPA_ERR_ARG; }
+    m->profiling = enable != 0;
+    return UMPA_OK;
+}
+
+int umpa_last_stage_ms(umpa_model *m, float *ms, int n)
+{
+    if (!m || !ms) { umpa_set_error("NULL argument"); return UMPA_ERR_ARG; }
+    if (!m->ev_valid) return 0;
+    if (cudaEventSynchronize(m->ev[4]) != cudaSuccess) return 0;
+    int k = 0;
+    for (; k < 4 && k < n; k++) cudaEventElapsedTime(&ms[k], m->ev[k], m->ev[k + 1]);
+    return k;
+}
+
+int64_t umpa_device_bytes(const umpa_model *m) { return m ? m->dev_bytes : 0; }
+
+}  // extern "C"

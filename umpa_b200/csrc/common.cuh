@@ -1,0 +1,115 @@
+// common.cuh -- shared declarations of libumpa_b200 (host + device).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/umpa_b200.h"
+
+#define UMPA_KWS 8                         // KERNEL_WINDOW_SIZE, UMPA/lib/Model.h:7
+#define UMPA_KSIDE (2 * UMPA_KWS + 1)
+#define UMPA_MAX_CALLS 500                 // UMPA/lib/Optim.cpp:14
+#define UMPA_MAX_K 31                      // largest supported window side (Nw <= 15)
+
+// error_status bits (UMPA/lib/Optim.h:7-12)
+#define UMPA_ST_OK 1
+#define UMPA_ST_BOUND 2
+#define UMPA_ST_DIM 4
+#define UMPA_ST_POS 8
+
+void umpa_set_error(const char *fmt, ...);
+
+#define UMPA_CUDA(call)                                                                     \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            umpa_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return UMPA_ERR_CUDA;                                                           \
+        }                                                                                   \
+    } while (0)
+
+// ---------------------------------------------------------------- device views
+
+// What the LAZY path needs to evaluate the reference's cost() for any pixel.
+struct LazyView {
+    int kind, Na, Nw, max_shift, padding, subpx, refshift, masked;
+    const double *const *sam;    // device arrays of device pointers
+    const double *const *ref;
+    const double *const *mask;
+    const int *dim;              // Na x 2
+    const int *pos;              // Na x 2
+    const double *win;           // K*K
+    const double *quad;          // 6x16 least-squares matrix of the quadratic sub-pixel fit
+};
+
+// Geometry of one match() call.
+struct RoiView {
+    int off0, step0, N0;         // raw row of output row xi = off0 + step0*xi   (off = padding + start)
+    int off1, step1, N1;
+    double uv0[2];               // start guess (row, col)
+    const double *abc;           // (N0,N1,3) or nullptr
+    const double *cover;         // (N0,N1) or nullptr
+    double cover_threshold;
+};
+
+// ---------------------------------------------------------------- the handle
+
+struct Scratch {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+struct umpa_model {
+    int kind = 0, Na = 0, Nw = 0, K = 0, max_shift = 0, padding = 0;
+    int subpx = -1, refshift = 0, path_opt = UMPA_PATH_AUTO;
+    int device = 0;
+    std::vector<int> dim, pos;                   // host copies
+    std::vector<double> win;                     // K*K
+    bool uniform = false;                        // equal shapes and zero positions
+    int H = 0, W = 0;                            // common shape when uniform
+    bool separable = false;                      // win == g (x) g
+    std::vector<double> g;                       // 1-D factor, K
+    double win_sum = 0.;
+    bool masked = false, frames_set = false;
+
+    // device: FP64 frames (LAZY path) -- one allocation per stack
+    double *d_sam64 = nullptr, *d_ref64 = nullptr, *d_mask64 = nullptr;
+    std::vector<size_t> frame_off;               // element offset of frame k inside the stack
+    size_t stack_elems = 0;
+    const double **d_sam_ptrs = nullptr, **d_ref_ptrs = nullptr, **d_mask_ptrs = nullptr;
+    int *d_dim = nullptr, *d_pos = nullptr;
+    double *d_win = nullptr, *d_quad = nullptr;
+
+    // device: centred FP32 stacks (TABLE path); pitch in floats, multiple of 4
+    float *d_sam32 = nullptr, *d_ref32 = nullptr;
+    int pitch = 0;
+    std::vector<double> mean_s, mean_r;          // per-frame means (FP64)
+    float *d_mean_s = nullptr, *d_mean_r = nullptr, *d_g = nullptr;
+    double *d_means64 = nullptr;                 // [2*Na]: sample means then reference means
+    double *d_partials = nullptr;
+
+    // TABLE-path scratch (grow-only)
+    Scratch filtA, filtB, auxS, auxR, tabX, tabM;
+    bool moments_valid = false;
+
+    // bookkeeping
+    int last_path = 0, last_launches = 0;
+    bool profiling = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    int64_t dev_bytes = 0;
+};
+
+int scratch_reserve(umpa_model *m, Scratch &s, size_t bytes);
+
+// implemented in lazy_path.cu
+int lazy_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st);
+int lazy_cost(umpa_model *m, int i, int j, int si, int sj, const double abc[3], double values[3], int *status);
+int lazy_min(umpa_model *m, int i, int j, double *values, double uv[2], double *dd, double *da, int *ncalls, int *ok);
+int coverage_map(umpa_model *m, const RoiView &roi, double *out_dev, cudaStream_t st);
+
+// implemented in table_path.cu
+int table_prepare_frames(umpa_model *m, cudaStream_t st);      // FP64 stacks -> centred FP32 stacks
+bool table_eligible(const umpa_model *m, const RoiView &roi, std::string *why);
+int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st);

@@ -1,0 +1,237 @@
+// walk.cuh -- per-pixel integer-shift walk and sub-pixel refinement (device, FP64).
+//
+// Re-implements the behaviour of discrete_2d_minimizer (UMPA/lib/Optim.cpp:233-479),
+// spmin (Optim.cpp:41-130) and spmin_quad (Optim.cpp:155-185) for one CUDA thread per
+// pixel.  The cost function is a functor, so the same state machine runs on top of the
+// lazy FP64 evaluator (lazy_path.cu) and of the FP32 shift tables (table_path.cu).
+#pragma once
+#include "common.cuh"
+
+struct FitArgs {            // what the reference keeps in CostArgs{NoDF,DF,DFKernel}: t (and v)
+    double t, v;
+};
+
+// ---- cubic B-spline surface through a 4x4 block -----------------------------------
+// f(x,y) = sum_ij B_i(x) B_j(y) a[4i+j] / 36 with x along rows; B_* are the four uniform
+// cubic B-spline pieces on [0,1] for samples at -1,0,1,2.  BSPL[n][s]: coefficient of t^n
+// of piece s, times 6.
+__device__ __forceinline__ double bspl_coef(int n, int s)
+{
+    // {1,4,1,0}, {-3,0,3,0}, {3,-6,3,0}, {-1,3,-3,1}
+    const int tab[16] = {1, 4, 1, 0, -3, 0, 3, 0, 3, -6, 3, 0, -1, 3, -3, 1};
+    return (double)tab[4 * n + s];
+}
+
+__device__ inline double subpixel_spline(const double *a, double *pos)
+{
+    // c[4m+n] multiplies x^n y^m
+    double tmp[16], c[16];
+#pragma unroll
+    for (int n = 0; n < 4; n++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            double s = 0.;
+#pragma unroll
+            for (int i = 0; i < 4; i++) s += bspl_coef(n, i) * a[4 * i + j];
+            tmp[4 * n + j] = s;               // x-power n, column sample j
+        }
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+#pragma unroll
+        for (int n = 0; n < 4; n++) {
+            double s = 0.;
+#pragma unroll
+            for (int j = 0; j < 4; j++) s += bspl_coef(m, j) * tmp[4 * n + j];
+            c[4 * m + n] = s;
+        }
+    double x = pos[0], y = pos[1];
+    for (int it = 0; it <= 20; it++) {
+        double A[4], A1[4], A2[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const double c0 = c[4 * m], c1 = c[4 * m + 1], c2 = c[4 * m + 2], c3 = c[4 * m + 3];
+            A[m] = c0 + x * (c1 + x * (c2 + x * c3));
+            A1[m] = c1 + x * (2. * c2 + 3. * x * c3);
+            A2[m] = 2. * c2 + 6. * x * c3;
+        }
+        const double fx = A1[0] + y * (A1[1] + y * (A1[2] + y * A1[3]));
+        const double fxx = A2[0] + y * (A2[1] + y * (A2[2] + y * A2[3]));
+        const double fy = A[1] + y * (2. * A[2] + 3. * y * A[3]);
+        const double fxy = A1[1] + y * (2. * A1[2] + 3. * y * A1[3]);
+        const double fyy = 2. * A[2] + 6. * y * A[3];
+        const double det = fxx * fyy - fxy * fxy;
+        const double dx = (fxy * fy - fyy * fx) / det;
+        const double dy = (fxy * fx - fxx * fy) / det;
+        x += dx;
+        y += dy;
+        if (dx * dx + dy * dy < 1e-8) break;          // absolute stop, Optim.cpp:85,123
+    }
+    pos[0] = x;
+    pos[1] = y;
+    double f = 0., yp = 1.;
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        f += yp * (c[4 * m] + x * (c[4 * m + 1] + x * (c[4 * m + 2] + x * c[4 * m + 3])));
+        yp *= y;
+    }
+    return f / 36.;
+}
+
+// ---- least-squares quadratic through a 4x4 block ------------------------------------
+// p = 400 * pinv(A) a for the basis [1, i, j, i^2, ij, j^2] on i,j in {-1,0,1,2}
+// (i along rows).  The 6x16 integer matrix is 400*(A^T A)^-1 A^T, generated on the host
+// when a model is created (quad_matrix in capi.cu) and passed in as `quad` (device memory).
+__device__ inline double subpixel_quadratic(const double *__restrict__ c_quad, const double *a, double *pos)
+{
+    double p[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        double s = 0.;
+#pragma unroll
+        for (int n = 0; n < 16; n++) s += c_quad[16 * r + n] * a[n];
+        p[r] = s;
+    }
+    const double det = 4. * p[3] * p[5] - p[4] * p[4];
+    // reference quirk kept: pos[0] gets the column solution, pos[1] the row solution
+    pos[0] = -(2. * p[3] * p[2] - p[4] * p[1]) / det;
+    pos[1] = -(2. * p[5] * p[1] - p[4] * p[2]) / det;
+    return (p[0] + .5 * (p[2] * pos[0] + p[1] * pos[1])) / 400.;
+}
+
+// ---- the walk --------------------------------------------------------------------------
+// d: 5x5 cache of costs centred on the current integer shift (row-major, centre 12, -1 =
+// not evaluated).  axis 0 scans the column shift, axis 1 the row shift.  `keep` is the
+// reference's args_copy: the fit parameters of the best shift seen so far -- deliberately
+// NOT refreshed on a restart (Optim.cpp:364-377), which the reference's outputs depend on.
+// Eval: int operator()(int si, int sj, double &cost, FitArgs &args) -> error_status bits.
+template <class Eval>
+__device__ inline int walk_minimise(Eval &eval, int subpx, const double *quad, FitArgs &args, double &out,
+                                    double *uv, double *d, double *a, int &ncalls)
+{
+    const double tol = 1e-8;                       // absolute, Optim.cpp:243
+    int settled0 = 0, settled1 = 0, axis = 0, st;
+    FitArgs keep;
+#pragma unroll
+    for (int n = 0; n < 25; n++) d[n] = -1.;
+    ncalls = 0;
+    int c0 = (int)round(uv[0]), c1 = (int)round(uv[1]);
+
+    st = eval(c0, c1, d[12], args);
+    ncalls++;
+    if (st != UMPA_ST_OK) return st;
+    keep = args;
+
+    bool skip_limit = false;                       // a restart re-enters the loop body unconditionally
+    while (skip_limit || ncalls < UMPA_MAX_CALLS) {
+        skip_limit = false;
+        const int lo = axis ? 7 : 11, hi = axis ? 17 : 13;
+        const int dr = axis, dc = 1 - axis;
+        bool up_m, up_p;
+
+        if (d[lo] < -.5) {
+            st = eval(c0 - dr, c1 - dc, d[lo], args);
+            ncalls++;
+            if (st != UMPA_ST_OK) return st;
+            up_m = d[lo] > d[12] + tol;
+            if (!up_m) keep = args;
+        } else up_m = d[lo] > d[12] + tol;
+
+        if (d[hi] < -.5) {
+            st = eval(c0 + dr, c1 + dc, d[hi], args);
+            ncalls++;
+            if (st != UMPA_ST_OK) return st;
+            up_p = d[hi] > d[12] - tol;
+            if (!up_p) keep = args;
+        } else up_p = d[hi] > d[12] - tol;
+
+        if (up_m && up_p) {
+            const int dir = d[lo] < d[hi] ? -1 : 1;
+            if (axis) settled1 = dir; else settled0 = dir;
+            if ((axis ? settled0 : settled1) == 0) { axis = 1 - axis; continue; }
+
+            const int ip = d[17] < d[7] ? 1 : 0;
+            const int jp = d[13] < d[11] ? 1 : 0;
+            bool restarted = false;
+            for (int r = 0; r < 4 && !restarted; r++)
+                for (int q = 0; q < 4; q++) {
+                    const int n = 5 * (ip + r) + jp + q;
+                    if (d[n] < -.9) {
+                        const int e0 = c0 + ip + r - 2, e1 = c1 + jp + q - 2;
+                        double v;
+                        st = eval(e0, e1, v, args);
+                        ncalls++;
+                        if (st != UMPA_ST_OK) return st;
+                        a[4 * r + q] = v;
+                        d[n] = v;
+                        if (v < d[12]) {           // lower value off-axis: hard restart there
+                            c0 = e0; c1 = e1;
+#pragma unroll
+                            for (int t = 0; t < 25; t++) d[t] = -1.;
+                            d[12] = v;
+                            args = keep;
+                            settled0 = settled1 = 0;
+                            restarted = true;
+                            break;
+                        }
+                    } else a[4 * r + q] = d[n];
+                }
+            if (restarted) { skip_limit = true; continue; }
+
+            args = keep;
+            uv[0] = 1. - ip;
+            uv[1] = 1. - jp;
+            if (subpx == 0) out = uv[0];                           // reference quirk, Optim.cpp:399
+            else if (subpx == 1) out = subpixel_quadratic(quad, a, uv);
+            else out = subpixel_spline(a, uv);
+            uv[0] += c0 + ip - 1.;
+            uv[1] += c1 + jp - 1.;
+            return st;
+        }
+
+        uv[0] = c0; uv[1] = c1;                    // best so far, Optim.cpp:421-423
+        out = d[12];
+        if (!up_p && !up_m) up_m = d[hi] < d[lo];  // local maximum: go downhill
+
+        if (up_m) {                                // step to the plus side
+            if (axis) {
+                c0 += 1;
+                for (int n = 0; n < 20; n++) d[n] = d[n + 5];
+                for (int n = 20; n < 25; n++) d[n] = -1.;
+            } else {
+                c1 += 1;
+                for (int n = 0; n < 24; n++) d[n] = d[n + 1];
+                for (int r = 0; r < 5; r++) d[5 * r + 4] = -1.;
+            }
+        } else {                                   // step to the minus side
+            if (axis) {
+                c0 -= 1;
+                for (int n = 24; n >= 5; n--) d[n] = d[n - 5];
+                for (int n = 0; n < 5; n++) d[n] = -1.;
+            } else {
+                c1 -= 1;
+                for (int n = 24; n >= 1; n--) d[n] = d[n - 1];
+                for (int r = 0; r < 5; r++) d[5 * r] = -1.;
+            }
+        }
+        if (axis) settled0 = 0; else settled1 = 0;
+    }
+    return 0;                                      // too many calls, Optim.cpp:477
+}
+
+// Writes one pixel's results the way Model*::min packs `values` (Model.cpp:573-576, 934-938).
+__device__ __forceinline__ void store_pixel(const umpa_outputs &o, size_t n, int kind, int st, double f,
+                                            const FitArgs &args, const double *uv, const double *d,
+                                            const double *a, int ncalls, bool have_a)
+{
+    if (o.f) o.f[n] = f;
+    if (o.T) o.T[n] = args.t;
+    if (o.dx) o.dx[n] = uv[1];
+    if (o.dy) o.dy[n] = uv[0];
+    if (o.df && kind == UMPA_DF) o.df[n] = args.v;
+    if (o.err) o.err[n] = (st & UMPA_ST_OK) ? 1 : 0;
+    if (o.ncalls) o.ncalls[n] = ncalls;
+    if (o.debug_d)
+        for (int t = 0; t < 25; t++) o.debug_d[25 * n + t] = d[t];
+    if (o.debug_a)
+        for (int t = 0; t < 16; t++) o.debug_a[16 * n + t] = have_a ? a[t] : 0.;
+}
