@@ -159,6 +159,10 @@ UMPA_API int umpa_last_stage_ms(umpa_model *m, float *ms, int n);
 /* bytes of device memory currently owned by the handle */
 UMPA_API int64_t umpa_device_bytes(const umpa_model *m);
 
+/* Measured FP32-FMA peak of the current device (dependent-free FFMA chains on all SMs, CUDA
+ * events): the denominator of the FP32-FMA roofline that bench.py reports. */
+UMPA_API int umpa_fma_peak(double *tflops, int *sm_count);
+
 UMPA_API const char *umpa_last_error(void);
 UMPA_API const char *umpa_version(void);
 

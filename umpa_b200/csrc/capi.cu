@@ -1,9 +1,12 @@
 // capi.cu -- extern "C" boundary of libumpa_b200.so (see include/umpa_b200.h for the
 // reference interface each entry point replaces).
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 
 #include "common.cuh"
@@ -18,11 +21,63 @@ void umpa_set_error(const char *fmt, ...)
     va_end(ap);
 }
 
+// Device-block cache: models are typically created once per projection with identical shapes
+// (the reference's constructor is free, so callers do that).  Freed frame/scratch blocks are
+// kept and handed to the next model instead of paying cudaMalloc/cudaFree (and their implicit
+// device synchronisation) per model.  Bounded by UMPA_POOL_GB (default 64).
+namespace {
+struct PoolBlock { void *p; size_t bytes; int dev; };
+std::mutex g_pool_mu;
+std::vector<PoolBlock> g_pool;
+size_t g_pool_bytes = 0;
+size_t pool_cap()
+{
+    const char *e = getenv("UMPA_POOL_GB");
+    return (size_t)((e ? atof(e) : 64.) * (double)(1ull << 30));
+}
+}  // namespace
+
+cudaError_t pool_malloc(void **p, size_t bytes)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (size_t n = 0; n < g_pool.size(); n++)
+            if (g_pool[n].bytes == bytes && g_pool[n].dev == dev) {
+                *p = g_pool[n].p;
+                g_pool_bytes -= bytes;
+                g_pool.erase(g_pool.begin() + n);
+                return cudaSuccess;
+            }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {                 // out of memory: drop the cache and retry once
+        cudaGetLastError();
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (auto &b : g_pool) cudaFree(b.p);
+        g_pool.clear(); g_pool_bytes = 0;
+        e = cudaMalloc(p, bytes);
+    }
+    return e;
+}
+
+void pool_free(void *p, size_t bytes)
+{
+    if (!p) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (bytes == 0 || g_pool_bytes + bytes > pool_cap()) { cudaFree(p); return; }
+    g_pool.push_back({p, bytes, dev});
+    g_pool_bytes += bytes;
+}
+
 int scratch_reserve(umpa_model *m, Scratch &s, size_t bytes)
 {
     if (s.bytes >= bytes && s.p) return UMPA_OK;
-    if (s.p) { cudaFree(s.p); m->dev_bytes -= (int64_t)s.bytes; s.p = nullptr; s.bytes = 0; }
-    cudaError_t e = cudaMalloc(&s.p, bytes);
+    if (s.p) { pool_free(s.p, s.bytes); m->dev_bytes -= (int64_t)s.bytes; s.p = nullptr; s.bytes = 0; }
+    cudaError_t e = pool_malloc(&s.p, bytes);
     if (e != cudaSuccess) {
         umpa_set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
         s.p = nullptr;
@@ -159,8 +214,11 @@ int check_roi_bounds(const umpa_model *m, const RoiView &v)
 
 void free_frames(umpa_model *m)
 {
-    for (void *p : {(void *)m->d_sam64, (void *)m->d_ref64, (void *)m->d_mask64, (void *)m->d_sam_ptrs,
-                    (void *)m->d_ref_ptrs, (void *)m->d_mask_ptrs, (void *)m->d_sam32, (void *)m->d_ref32,
+    const size_t b64 = m->stack_elems * sizeof(double);
+    const size_t b32 = (size_t)m->Na * m->H * m->pitch * sizeof(float);
+    pool_free(m->d_sam64, b64); pool_free(m->d_ref64, b64); pool_free(m->d_mask64, b64);
+    pool_free(m->d_sam32, b32); pool_free(m->d_ref32, b32);
+    for (void *p : {(void *)m->d_sam_ptrs, (void *)m->d_ref_ptrs, (void *)m->d_mask_ptrs,
                     (void *)m->d_mean_s, (void *)m->d_mean_r, (void *)m->d_means64, (void *)m->d_partials})
         if (p) cudaFree(p);
     m->d_sam64 = m->d_ref64 = m->d_mask64 = nullptr;
@@ -234,9 +292,10 @@ int umpa_create(umpa_model **out, int kind, int Na, const int32_t *dim, const in
 void umpa_destroy(umpa_model *m)
 {
     if (!m) return;
+    cudaDeviceSynchronize();      // blocks go back to the cache: nothing of this model may still be running
     free_frames(m);
     for (Scratch *s : {&m->filtA, &m->filtB, &m->auxS, &m->auxR, &m->tabX, &m->tabM})
-        if (s->p) cudaFree(s->p);
+        if (s->p) pool_free(s->p, s->bytes);
     for (void *p : {(void *)m->d_dim, (void *)m->d_pos, (void *)m->d_win, (void *)m->d_quad, (void *)m->d_g})
         if (p) cudaFree(p);
     for (int i = 0; i < 5; i++)
@@ -262,7 +321,7 @@ int umpa_set_frames(umpa_model *m, const double *const *sam, const double *const
     const double ***ptrs[3] = {&m->d_sam_ptrs, &m->d_ref_ptrs, &m->d_mask_ptrs};
     for (int a = 0; a < 3; a++) {
         if (!srcs[a]) continue;
-        UMPA_CUDA(cudaMalloc(dsts[a], total * sizeof(double)));
+        UMPA_CUDA(pool_malloc((void **)dsts[a], total * sizeof(double)));
         UMPA_CUDA(cudaMalloc((void **)ptrs[a], Na * sizeof(double *)));
         std::vector<const double *> hp(Na);
         for (int k = 0; k < Na; k++) {
@@ -457,3 +516,54 @@ int umpa_last_stage_ms(umpa_model *m, float *ms, int n)
 int64_t umpa_device_bytes(const umpa_model *m) { return m ? m->dev_bytes : 0; }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// FP32 FMA peak probe: dependent-free FFMA chains on every SM, timed with CUDA events.
+// bench.py uses it as the measured denominator of the FP32-FMA roofline.
+namespace {
+__global__ void __launch_bounds__(256) ffma_probe_kernel(float *sink, int iters, float x, float y)
+{
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = threadIdx.x * 1e-3f + i;
+    for (int n = 0; n < iters; n++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int i = 0; i < 16; i++) a[i] = fmaf(a[i], x, y);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += a[i];
+    if (s == 123.456f) sink[0] = s;      // never true; keeps the chains alive
+}
+}  // namespace
+
+extern "C" UMPA_API int umpa_fma_peak(double *tflops, int *sm_count)
+{
+    if (!tflops) { umpa_set_error("NULL argument"); return UMPA_ERR_ARG; }
+    int dev = 0, sms = 0;
+    UMPA_CUDA(cudaGetDevice(&dev));
+    UMPA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float *sink = nullptr;
+    UMPA_CUDA(cudaMalloc(&sink, sizeof(float)));
+    cudaEvent_t e0, e1;
+    UMPA_CUDA(cudaEventCreate(&e0));
+    UMPA_CUDA(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = sms * 8, threads = 256;
+    double best = 0.;
+    for (int rep = 0; rep < 5; rep++) {
+        UMPA_CUDA(cudaEventRecord(e0));
+        ffma_probe_kernel<<<blocks, threads>>>(sink, iters, 0.999f, 1e-3f);
+        UMPA_CUDA(cudaEventRecord(e1));
+        UMPA_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        UMPA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flop = 2. * 16 * 8 * (double)iters * blocks * threads;
+        if (rep > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    *tflops = best;
+    if (sm_count) *sm_count = sms;
+    return UMPA_OK;
+}

@@ -102,6 +102,8 @@ struct umpa_model {
 };
 
 int scratch_reserve(umpa_model *m, Scratch &s, size_t bytes);
+cudaError_t pool_malloc(void **p, size_t bytes);   // cached cudaMalloc / cudaFree for big blocks
+void pool_free(void *p, size_t bytes);
 
 // implemented in lazy_path.cu
 int lazy_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st);

@@ -536,8 +536,8 @@ int table_prepare_frames(umpa_model *m, cudaStream_t st)
     m->pitch = 4 * ((W + 3) / 4);
     const size_t n32 = (size_t)Na * H * m->pitch;
     if (!m->d_sam32) {
-        UMPA_CUDA(cudaMalloc(&m->d_sam32, n32 * sizeof(float)));
-        UMPA_CUDA(cudaMalloc(&m->d_ref32, n32 * sizeof(float)));
+        UMPA_CUDA(pool_malloc((void **)&m->d_sam32, n32 * sizeof(float)));
+        UMPA_CUDA(pool_malloc((void **)&m->d_ref32, n32 * sizeof(float)));
         UMPA_CUDA(cudaMalloc(&m->d_mean_s, Na * sizeof(float)));
         UMPA_CUDA(cudaMalloc(&m->d_mean_r, Na * sizeof(float)));
         UMPA_CUDA(cudaMalloc(&m->d_means64, 2 * Na * sizeof(double)));
