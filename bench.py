@@ -53,13 +53,14 @@ def algorithmic_flops_per_px(cfg):
     return f
 
 
-def executed_fma_per_px_cross(cfg, tile=(16, 32)):
+def executed_fma_per_px_cross(cfg):
     """FMAs the cross-table kernel executes per output pixel: Na per (extended-tile pixel, shift)
-    plus the separable filter (row pass on the extended rows, column pass)."""
+    plus the separable filter (row pass on the extended rows, column pass).  Tile geometry of
+    table_path.cu: extended tile 16 x 32, output tile (16-2Nw) x (32-2Nw)."""
     S, K, Na, Nw = 2 * cfg["ms"] - 1, 2 * cfg["Nw"] + 1, cfg["Na"], cfg["Nw"]
-    th, tw = tile
-    ext = (th + 2 * Nw) * (4 * ((tw + 2 * Nw + 3) // 4))
-    per_tile = S * S * (Na * ext + K * (th + 2 * Nw) * tw + K * th * tw)
+    eh, ew = 16, 32
+    th, tw = eh - 2 * Nw, ew - 2 * Nw
+    per_tile = S * S * (Na * eh * ew + K * eh * tw + K * th * tw)
     return per_tile / float(th * tw)
 
 

@@ -26,16 +26,17 @@
 //   moments_kernel     a_k, b_k stacks + aux images                (HBM bound)
 //   shift_table_kernel C_s + filter -> cross table;  a_k,b_k -> mean table (FP32 FMA / smem bound)
 //   table_walk_kernel  FP64 solve + walk + spline per pixel
+#include <cuda.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 #include "walk.cuh"
 
 namespace {
 
-constexpr int TILE_W = 32;         // output tile width of shift_table_kernel (floats: one 128 B line)
-constexpr int MAX_NT = 384;        // thread-block size cap of shift_table_kernel
 constexpr int SMEM_CAP = 227 * 1024;
 
 // ------------------------------------------------------------------ frame conversion
@@ -197,97 +198,132 @@ __global__ void __launch_bounds__(MO_NT) moments_kernel(MomentsParams p)
 }
 
 // ------------------------------------------------------------------ shift tables
+//
+// table[s][p] = sum_k A_k(p+s) * B_k(p)   (FILTER: then window-filtered over p)
+//
+// One CTA owns an output tile TH x TW and produces ALL S*S shifts for it.  Work split:
+//   * the extended tile (TH + 2*halo rows, 32 columns = TW + 2*halo) is cut into strips of
+//     4 consecutive pixels; a thread owns one strip -> 8 strips per row, so every quarter
+//     warp reads one contiguous 128 B shared-memory line (conflict-free LDS.128);
+//   * G warp groups work on the same frame at the same time, group g accumulating shift rows
+//     [ (pass*G+g)*SH, +SH ): SH*S*4 FP32 accumulators per thread live in registers across all
+//     frames, so each frame tile is streamed through shared memory exactly once per pass;
+//   * frames arrive by TMA (cp.async.bulk.tensor, 3-D map over [Na][H][pitch], zero fill out
+//     of bounds) into a ring of NST stages guarded by full/empty mbarriers; thread 0 is the
+//     producer, nobody executes a per-frame __syncthreads();
+//   * epilogue (per shift row): accumulators -> shared, separable window filter (row pass in
+//     registers, column pass with 4-row register blocking), float4 stores to the table.
 
 struct TableParams {
-    const float *A, *B;          // stacks [Na][H][pitch]: A is read at q+s, B at q
     float *table;                // [S*S][rows_p][cols_p]
     const float *g;              // window factor (FILTER only)
-    int Na, Nw, H, W, pitch;
+    int Na, Nw;
     int oy, ox;                  // raw coordinates of table element (0,0)
-    int rows_p, cols_p;          // padded table plane (multiples of the tile)
-    int TH;                      // tile height
-    int EH, EWs;                 // extended tile (B tile): rows, cols (multiple of 4)
-    int AH, AP;                  // A tile rows, pitch
-    int nslot, resident;         // frame slots in smem; 1 = whole stack stays resident
-    int nt;                      // threads per block
+    int rows_p, cols_p;          // padded table plane
+    int TH, TW;                  // output tile
+    int EH;                      // extended tile rows (ext cols are EXT_W)
+    int AH, AP;                  // A tile rows, pitch (= TMA box width)
+    int G, npass, nstage;
+    int a_stage_floats, stage_floats;   // per-stage layout: A tile then B tile (128 B aligned)
 };
 
-__device__ __forceinline__ void cp_async4(float *dst, const float *src, bool valid)
+constexpr int EXT_W = 32;          // extended tile width: one 128 B line per row
+constexpr int MAX_NT = 384;        // threads per CTA (3 groups x 16 rows x 8 strips)
+constexpr int MAX_STAGES = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-    const int sz = valid ? 4 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(src), "r"(sz));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-constexpr int PF_DEPTH = 2;       // frames in flight
-
-// S: shifts per axis (2*max_shift-1); SH: shift rows accumulated per pass;
-// FILTER: apply the separable window to the accumulated correlation before storing.
-template <int S, int SH, bool FILTER>
-__global__ void __launch_bounds__(MAX_NT) shift_table_kernel(TableParams p)
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
-    extern __shared__ __align__(16) float sm[];
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 3-D tiled TMA load: box (c0.., c1.., c2) of the tensor map -> dense smem tile, completes on `bar`
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::
+            "r"(smem_u32(dst)), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <int S, int SH, bool FILTER>
+__global__ void __launch_bounds__(MAX_NT)
+shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TableParams p)
+{
+    extern __shared__ __align__(128) float sm[];
     constexpr int HS = (S - 1) / 2;                  // max |shift|
-    constexpr int NA4 = (S + 3 + 3) / 4;             // float4 loads covering S+3 floats of an A row
-    const int tid = threadIdx.x;
-    const int slot_floats = p.AH * p.AP + p.EH * p.EWs;
-    float *cbuf = sm + (size_t)p.nslot * slot_floats; // [S][EH][EWs] (FILTER only)
+    // TMA needs the innermost box coordinate 16 B aligned (measured: unaligned -> illegal
+    // instruction).  The B tile origin is aligned by construction (host shifts the table
+    // origin); the A tile starts HS + DELTA columns to its left so that it is aligned too.
+    constexpr int DELTA = (4 - HS % 4) % 4;
+    constexpr int NA4 = (DELTA + S + 3 + 3) / 4;     // float4 loads covering DELTA+S+3 floats of an A row
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
     __shared__ float gs[UMPA_MAX_K];
+
+    const int tid = threadIdx.x, nt = blockDim.x;
     const int K = 2 * p.Nw + 1;
-    if (FILTER && tid < K) gs[tid] = p.g[tid];
-
     const int halo = FILTER ? p.Nw : 0;
-    const int ty0 = blockIdx.y * p.TH, tx0 = blockIdx.x * TILE_W;       // table coords of the tile
-    const int by = p.oy + ty0 - halo, bx = p.ox + tx0 - halo;           // raw origin of the B tile
-    const int ay = by - HS, ax = bx - HS;                               // raw origin of the A tile
-    const size_t fstride = (size_t)p.H * p.pitch;
+    const int TG = p.EH * (EXT_W / 4);               // threads per group
+    const int grp = tid / TG, lt = tid - grp * TG;
+    const int er = lt >> 3, ec = (lt & 7) << 2;      // strip: extended row, first extended column
+    const bool worker = grp < p.G;
+    const int ty0 = blockIdx.y * p.TH, tx0 = blockIdx.x * p.TW;          // table coords of the tile
+    const int by = p.oy + ty0 - halo, bx = p.ox + tx0 - halo;            // raw origin of the B tile
+    const int ay = by - HS, ax = bx - HS - DELTA;                        // raw origin of the A tile
+    float *cbuf = sm + (size_t)p.nstage * p.stage_floats;                // [G*S][EH][EXT_W] (FILTER only)
+    const uint32_t stage_bytes = (uint32_t)(p.AH * p.AP + p.EH * EXT_W) * sizeof(float);
 
-    // this thread's strip of 4 consecutive extended-tile pixels
-    const int spr = p.EWs / 4;                       // strips per row
-    const int nstrips = p.EH * spr;
-    const bool active = tid < nstrips;
-    const int er = active ? tid / spr : 0, ec = active ? 4 * (tid - er * spr) : 0;
-
-    auto issue_load = [&](int frame, int slot) {
-        float *As = sm + (size_t)slot * slot_floats, *Bs = As + p.AH * p.AP;
-        const float *Ag = p.A + frame * fstride, *Bg = p.B + frame * fstride;
-        const int na = p.AH * p.AP;
-        for (int n = tid; n < na; n += p.nt) {
-            const int r = n / p.AP, c = n - r * p.AP;
-            const int y = ay + r, x = ax + c;
-            const bool ok = y >= 0 && y < p.H && x >= 0 && x < p.W;
-            cp_async4(As + n, ok ? Ag + (size_t)y * p.pitch + x : Ag, ok);
-        }
-        const int nb = p.EH * p.EWs;
-        for (int n = tid; n < nb; n += p.nt) {
-            const int r = n / p.EWs, c = n - r * p.EWs;
-            const int y = by + r, x = bx + c;
-            const bool ok = y >= 0 && y < p.H && x >= 0 && x < p.W;
-            cp_async4(Bs + n, ok ? Bg + (size_t)y * p.pitch + x : Bg, ok);
-        }
-    };
-
-    constexpr int NPASS = (S + SH - 1) / SH;
-    const int total = NPASS * p.Na;
-    const int nload = p.resident ? p.Na : total;
-    for (int g = 0; g < PF_DEPTH; g++) {
-        if (g < nload) issue_load(g % p.Na, p.resident ? g : g % p.nslot);
-        cp_async_commit();
+    if (FILTER && tid < K) gs[tid] = p.g[tid];
+    if (tid == 0) {
+        for (int s = 0; s < p.nstage; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], nt / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     }
+    __syncthreads();
+
+    const int total = p.npass * p.Na;
+    auto issue = [&](int it) {                       // thread 0: frame of iteration `it` -> its stage
+        const int s = it % p.nstage, frame = it % p.Na;
+        float *As = sm + (size_t)s * p.stage_floats, *Bs = As + p.a_stage_floats;
+        mbar_expect_tx(&full_bar[s], stage_bytes);
+        tma_load_3d(As, &mapA, ax, ay, frame, &full_bar[s]);
+        tma_load_3d(Bs, &mapB, bx, by, frame, &full_bar[s]);
+    };
+    if (tid == 0)
+        for (int it = 0; it < p.nstage && it < total; it++) issue(it);
 
     float acc[SH][S][4];
-    for (int g = 0; g < total; g++) {
-        const int k = g % p.Na, pass = g / p.Na;
-        if (g < nload + PF_DEPTH) {                  // loads may still be in flight
-            cp_async_wait<PF_DEPTH - 1>();
-            __syncthreads();
-            const int gl = g + PF_DEPTH;
-            if (gl < nload) issue_load(gl % p.Na, p.resident ? gl : gl % p.nslot);
-            cp_async_commit();
+    for (int it = 0; it < total; it++) {
+        const int frame = it % p.Na, pass = it / p.Na;
+        const int s = it % p.nstage;
+        if (tid == 0 && it >= 1) {                   // refill the stage that frame it-1 used
+            const int nxt = it - 1 + p.nstage;
+            if (nxt < total) {
+                mbar_wait(&empty_bar[(it - 1) % p.nstage], ((it - 1) / p.nstage) & 1);
+                issue(nxt);
+            }
         }
-        if (k == 0) {
+        if (frame == 0) {
 #pragma unroll
             for (int a = 0; a < SH; a++)
 #pragma unroll
@@ -295,16 +331,17 @@ __global__ void __launch_bounds__(MAX_NT) shift_table_kernel(TableParams p)
 #pragma unroll
                     for (int c = 0; c < 4; c++) acc[a][b][c] = 0.f;
         }
-        if (active) {
-            const float *As = sm + (size_t)(p.resident ? k : g % p.nslot) * slot_floats;
-            const float *Bs = As + p.AH * p.AP;
-            const float4 b4 = *reinterpret_cast<const float4 *>(Bs + er * p.EWs + ec);
+        mbar_wait(&full_bar[s], (it / p.nstage) & 1);
+        const int si0 = (pass * p.G + grp) * SH;     // first shift row of this thread in this pass
+        if (worker && si0 < S) {
+            const float *As = sm + (size_t)s * p.stage_floats;
+            const float *Bs = As + p.a_stage_floats;
+            const float4 b4 = *reinterpret_cast<const float4 *>(Bs + er * EXT_W + ec);
             const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int sh = 0; sh < SH; sh++) {
-                const int si = pass * SH + sh;
-                if (si < S) {
-                    const float *arow = As + (er + si) * p.AP + ec;
+                if (si0 + sh < S) {
+                    const float *arow = As + (er + si0 + sh) * p.AP + ec;
                     float av[4 * NA4];
 #pragma unroll
                     for (int v = 0; v < NA4; v++) {
@@ -314,79 +351,93 @@ __global__ void __launch_bounds__(MAX_NT) shift_table_kernel(TableParams p)
 #pragma unroll
                     for (int sj = 0; sj < S; sj++)
 #pragma unroll
-                        for (int x = 0; x < 4; x++) acc[sh][sj][x] = fmaf(bv[x], av[sj + x], acc[sh][sj][x]);
+                        for (int x = 0; x < 4; x++) acc[sh][sj][x] = fmaf(bv[x], av[DELTA + sj + x], acc[sh][sj][x]);
                 }
             }
         }
-        if (k == p.Na - 1) {
-            // ---- epilogue of this pass: one shift row at a time ----
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);      // this warp is done with the stage
+
+        if (frame == p.Na - 1) {
+            // ---------------- epilogue of this pass ----------------
+            const size_t plane_sz = (size_t)p.rows_p * p.cols_p;
+            if (!FILTER) {
+                if (worker) {
 #pragma unroll
-            for (int sh = 0; sh < SH; sh++) {
-                const int si = pass * SH + sh;
-                if (si >= S) break;
-                float *plane0 = p.table + (size_t)(si * S) * p.rows_p * p.cols_p;
-                if (!FILTER) {
-                    if (active) {
-                        const int ty = ty0 + er, tx = tx0 + ec;
+                    for (int sh = 0; sh < SH; sh++) {
+                        const int si = si0 + sh;
+                        if (si < S && ec < p.TW) {
+                            float *dst = p.table + (size_t)(si * S) * plane_sz + (size_t)(ty0 + er) * p.cols_p + tx0 + ec;
 #pragma unroll
-                        for (int sj = 0; sj < S; sj++)
-                            *reinterpret_cast<float4 *>(plane0 + ((size_t)sj * p.rows_p + ty) * p.cols_p + tx) =
-                                make_float4(acc[sh][sj][0], acc[sh][sj][1], acc[sh][sj][2], acc[sh][sj][3]);
+                            for (int sj = 0; sj < S; sj++)
+                                *reinterpret_cast<float4 *>(dst + sj * plane_sz) =
+                                    make_float4(acc[sh][sj][0], acc[sh][sj][1], acc[sh][sj][2], acc[sh][sj][3]);
+                        }
                     }
-                } else {
-                    const int plane = p.EH * p.EWs;
-                    if (active) {
+                }
+            } else {
+                const int plane = p.EH * EXT_W;      // one shift's row-filtered extended tile in cbuf
+                const int ostrips = p.TW / 4;        // output strips per row
+                const int nplanes = p.G * S;
 #pragma unroll
-                        for (int sj = 0; sj < S; sj++)
-                            *reinterpret_cast<float4 *>(cbuf + sj * plane + er * p.EWs + ec) =
-                                make_float4(acc[sh][sj][0], acc[sh][sj][1], acc[sh][sj][2], acc[sh][sj][3]);
-                    }
-                    __syncthreads();
-                    // row pass: thread (row r of EH, output strip oc) -> 4 outputs per shift, kept in registers
-                    const int ospr = TILE_W / 4;
-                    const bool ract = tid < p.EH * ospr;
-                    const int rr = ract ? tid / ospr : 0, oc = ract ? 4 * (tid - rr * ospr) : 0;
-                    float rp[S][4];
-                    if (ract) {
+                for (int sh = 0; sh < SH; sh++) {
+                    // shift rows handled in this round: si(g) = (pass*G+g)*SH + sh for g < G.
+                    // Row pass in registers: the 8 lanes of a quarter warp hold one extended row
+                    // (32 columns); output x needs columns x .. x+2Nw, fetched from the lanes to the
+                    // right with shuffles (lanes past the row end only feed unused outputs x >= TW).
+                    if (worker && si0 + sh < S) {
 #pragma unroll
                         for (int sj = 0; sj < S; sj++) {
-                            const float *src = cbuf + sj * plane + rr * p.EWs + oc;
+                            const float a0 = acc[sh][sj][0], a1 = acc[sh][sj][1], a2 = acc[sh][sj][2], a3 = acc[sh][sj][3];
+                            float w0 = a0, w1 = a1, w2 = a2, w3;
                             float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-                            float w0 = src[0], w1 = src[1], w2 = src[2], w3;
-                            for (int v = 0; v < K; v++) {       // sliding 4-wide window over the row
-                                w3 = src[v + 3];
+                            for (int v = 0; v < K; v++) {
+                                const int e = v + 3, c = e & 3;
+                                const float mine = c == 0 ? a0 : (c == 1 ? a1 : (c == 2 ? a2 : a3));
+                                w3 = __shfl_down_sync(0xffffffffu, mine, e >> 2, 8);
                                 const float gv = gs[v];
                                 o0 = fmaf(gv, w0, o0); o1 = fmaf(gv, w1, o1);
                                 o2 = fmaf(gv, w2, o2); o3 = fmaf(gv, w3, o3);
                                 w0 = w1; w1 = w2; w2 = w3;
                             }
-                            rp[sj][0] = o0; rp[sj][1] = o1; rp[sj][2] = o2; rp[sj][3] = o3;
+                            *reinterpret_cast<float4 *>(cbuf + (grp * S + sj) * plane + er * EXT_W + ec) =
+                                make_float4(o0, o1, o2, o3);
                         }
                     }
                     __syncthreads();
-                    if (ract) {
+                    // column pass: item = (plane q, block of 4 output rows, strip c)
+                    const int rblocks = (p.TH + 3) / 4;
+                    const int citems = nplanes * rblocks * ostrips;
+                    for (int item = tid; item < citems; item += nt) {
+                        const int q = item / (rblocks * ostrips), rem = item - q * (rblocks * ostrips);
+                        const int rb = rem / ostrips, c4 = 4 * (rem - rb * ostrips);
+                        const int g_of_q = q / S, sj = q - g_of_q * S;
+                        const int si = (pass * p.G + g_of_q) * SH + sh;
+                        if (si >= S) continue;
+                        const float *src = cbuf + q * plane + (4 * rb) * EXT_W + c4;
+                        float o[4][4];
 #pragma unroll
-                        for (int sj = 0; sj < S; sj++)
-                            *reinterpret_cast<float4 *>(cbuf + sj * plane + rr * p.EWs + oc) =
-                                make_float4(rp[sj][0], rp[sj][1], rp[sj][2], rp[sj][3]);
-                    }
-                    __syncthreads();
-                    // column pass: work item = (shift sj, output row y, strip oc)
-                    const int items = S * p.TH * ospr;
-                    for (int it = tid; it < items; it += p.nt) {
-                        const int sj = it / (p.TH * ospr);
-                        const int rem = it - sj * (p.TH * ospr);
-                        const int y = rem / ospr, c4 = 4 * (rem - y * ospr);
-                        const float *src = cbuf + sj * plane + y * p.EWs + c4;
-                        float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-                        for (int u = 0; u < K; u++) {
-                            const float4 t = *reinterpret_cast<const float4 *>(src + u * p.EWs);
-                            const float gu = gs[u];
-                            o0 = fmaf(gu, t.x, o0); o1 = fmaf(gu, t.y, o1);
-                            o2 = fmaf(gu, t.z, o2); o3 = fmaf(gu, t.w, o3);
+                        for (int a = 0; a < 4; a++)
+#pragma unroll
+                            for (int b = 0; b < 4; b++) o[a][b] = 0.f;
+                        for (int u = 0; u < K + 3; u++) {        // input row 4*rb + u feeds output rows u-K+1 .. u
+                            if (4 * rb + u >= p.EH) break;
+                            const float4 t = *reinterpret_cast<const float4 *>(src + u * EXT_W);
+#pragma unroll
+                            for (int a = 0; a < 4; a++) {
+                                const int tap = u - a;
+                                if (tap >= 0 && tap < K) {
+                                    const float gu = gs[tap];
+                                    o[a][0] = fmaf(gu, t.x, o[a][0]); o[a][1] = fmaf(gu, t.y, o[a][1]);
+                                    o[a][2] = fmaf(gu, t.z, o[a][2]); o[a][3] = fmaf(gu, t.w, o[a][3]);
+                                }
+                            }
                         }
-                        *reinterpret_cast<float4 *>(plane0 + ((size_t)sj * p.rows_p + ty0 + y) * p.cols_p + tx0 + c4) =
-                            make_float4(o0, o1, o2, o3);
+                        float *dst = p.table + (size_t)(si * S + sj) * plane_sz + (size_t)(ty0 + 4 * rb) * p.cols_p + tx0 + c4;
+#pragma unroll
+                        for (int a = 0; a < 4; a++)
+                            if (4 * rb + a < p.TH)
+                                *reinterpret_cast<float4 *>(dst + (size_t)a * p.cols_p) = make_float4(o[a][0], o[a][1], o[a][2], o[a][3]);
                     }
                     __syncthreads();
                 }
@@ -398,13 +449,15 @@ __global__ void __launch_bounds__(MAX_NT) shift_table_kernel(TableParams p)
 // ------------------------------------------------------------------ table-driven walk
 
 struct WalkParams {
-    const float *tabX, *tabM;       // cross / mean tables [S*S][rows_p][cols_p]; tabM nullptr for NoDF
+    const float *tabX, *tabM;       // cross / mean tables; tabM nullptr for NoDF
     const float4 *auxS, *auxR;      // [H][pitch], raw coordinates
     int pitch;
-    int rows_p, cols_p;
-    int oy, ox;                     // raw coords of table (0,0)
+    int rowsX, colsX, rowsM, colsM; // padded plane geometry of the two tables
+    int oy, ox;                     // raw coords of output pixel (0,0) of the dense region
+    int dxX, dxM;                   // column of that pixel inside the cross / mean table (TMA alignment shift)
     int kind, Na, max_shift, subpx;
     double sw, cd, cc, dd;          // sum of window; sum_k c_k d_k, c_k^2, d_k^2
+    double inv_sw, inv_sw2, inv_Na;
     const double *quad;
 };
 
@@ -420,32 +473,44 @@ struct TableEval {
         if (sj <= -ms) return UMPA_ST_BOUND | UMPA_ST_DIM;
         if (sj >= ms) return UMPA_ST_BOUND | UMPA_ST_DIM | UMPA_ST_POS;
         const int S = 2 * ms - 1;
-        const size_t e = ((size_t)((si + ms - 1) * S + (sj + ms - 1)) * w.rows_p + ty) * w.cols_p + tx;
+        const size_t sidx = (size_t)((si + ms - 1) * S + (sj + ms - 1));
         const float4 r = __ldg(w.auxR + (size_t)(w.oy + ty + si) * w.pitch + (w.ox + tx + sj));
+        const float xv = __ldg(w.tabX + (sidx * w.rowsX + ty) * w.colsX + tx + w.dxX);
         const double T3 = r.x, P3 = r.y, U = r.z, M2 = r.w;
         const double t3 = T3 + 2. * P3 + w.sw * w.cc;
         const double lin = U + V + w.sw * w.cd;
-        const double t5 = (double)__ldg(w.tabX + e) + lin;
+        const double t5 = (double)xv + lin;
         if (w.kind == UMPA_DF) {
-            const double t2 = M2 / (w.sw * w.sw) + 2. * P3 / w.sw + w.cc;
+            const float mv = __ldg(w.tabM + (sidx * w.rowsM + ty) * w.colsM + tx + w.dxM);
+            const double t2 = M2 * w.inv_sw2 + 2. * P3 * w.inv_sw + w.cc;
             const double t6 = w.sw * t2;
-            const double t4 = (double)__ldg(w.tabM + e) / w.sw + lin;
-            const double den = t2 * t3 - t6 * t6;
-            const double Kc = (t2 * t5 - t4 * t6) / den;
-            const double beta = (t3 * t4 - t5 * t6) / den;
+            const double t4 = (double)mv * w.inv_sw + lin;
+            const double rden = 1. / (t2 * t3 - t6 * t6);
+            const double Kc = (t2 * t5 - t4 * t6) * rden;
+            const double beta = (t3 * t4 - t5 * t6) * rden;
             args.t = beta + Kc;
-            args.v = Kc / args.t;
-            cost = (t1 + beta * beta * t2 + Kc * Kc * t3 - 2. * beta * t4 - 2. * Kc * t5 + 2. * beta * Kc * t6) / w.Na;
+            args.v = Kc;                  // dark field = Kc / t, divided once at the end (finish())
+            cost = (t1 + beta * beta * t2 + Kc * Kc * t3 - 2. * beta * t4 - 2. * Kc * t5 + 2. * beta * Kc * t6) * w.inv_Na;
         } else {
             args.t = t5 / t3;
-            cost = (t1 - t5 * args.t) / w.Na;
+            cost = (t1 - t5 * args.t) * w.inv_Na;
         }
         return UMPA_ST_OK;
     }
 };
 
-__global__ void __launch_bounds__(128) table_walk_kernel(WalkParams w, RoiView roi, umpa_outputs out)
+constexpr int WALK_NT = 128;
+
+// d (the 5x5 cost cache) lives in shared memory, one column per thread: dynamic indexing
+// without local-memory traffic.
+struct SharedGrid {
+    double *base;                   // &d_sm[0][threadIdx.x]
+    __device__ __forceinline__ double &operator[](int n) const { return base[n * WALK_NT]; }
+};
+
+__global__ void __launch_bounds__(WALK_NT, 6) table_walk_kernel(WalkParams w, RoiView roi, umpa_outputs out)
 {
+    __shared__ double d_sm[25][WALK_NT];
     const int xj = blockIdx.x * blockDim.x + threadIdx.x;
     const int xi = blockIdx.y;
     if (xj >= roi.N1 || xi >= roi.N0) return;
@@ -455,75 +520,120 @@ __global__ void __launch_bounds__(128) table_walk_kernel(WalkParams w, RoiView r
     const float4 s = __ldg(w.auxS + (size_t)(w.oy + ty) * w.pitch + (w.ox + tx));
     TableEval eval{w, ty, tx, (double)s.x + 2. * (double)s.y + w.sw * w.dd, (double)s.z};
     FitArgs args{0., 0.};
-    double d[25], a[16], uv[2] = {roi.uv0[0], roi.uv0[1]}, f = 0.;
+    SharedGrid d{&d_sm[0][threadIdx.x]};
+    double a[16], uv[2] = {roi.uv0[0], roi.uv0[1]}, f = 0.;
     int ncalls;
 #pragma unroll
     for (int t = 0; t < 16; t++) a[t] = 0.;
     const int st = walk_minimise(eval, w.subpx, w.quad, args, f, uv, d, a, ncalls);
+    if (w.kind == UMPA_DF && args.t != 0.) args.v = args.v / args.t;
     store_pixel(out, n, w.kind, st, f, args, uv, d, a, ncalls, true);
 }
 
 // ------------------------------------------------------------------ host side
 
-template <int S, bool FILTER>
-int launch_shift_table(const TableParams &p, dim3 grid, size_t smem, cudaStream_t st)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn()
 {
-    constexpr int SH = (S <= 9) ? 1 : 1;
-    auto kern = shift_table_kernel<S, SH, FILTER>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { umpa_set_error("cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e)); return UMPA_ERR_CUDA; }
-    kern<<<grid, p.nt, smem, st>>>(p);
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 3-D map over a stack [Na][H][pitch] of floats, box (bw, bh, 1), zero fill outside [0,W)x[0,H)
+int make_stack_map(CUtensorMap *map, const float *base, int Na, int H, int W, int pitch, int bw, int bh)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { umpa_set_error("cuTensorMapEncodeTiled is not available from the driver"); return UMPA_ERR_CUDA; }
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Na};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * sizeof(float), (cuuint64_t)pitch * H * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        umpa_set_error("cuTensorMapEncodeTiled failed (%d) for W=%d H=%d Na=%d pitch=%d box=%dx%d", (int)r, W, H, Na, pitch, bw, bh);
+        return UMPA_ERR_CUDA;
+    }
+    return UMPA_OK;
+}
+
+// compile-time choice of the per-thread shift-row block: keeps SH*S*4 accumulators <= ~120
+template <int S> struct RowBlock { static constexpr int SH = S <= 9 ? 3 : (S <= 17 ? 2 : 1); };
+
+template <int S, bool FILTER>
+int launch_shift_table(const CUtensorMap &mapA, const CUtensorMap &mapB, const TableParams &p, dim3 grid, int nt,
+                       size_t smem, cudaStream_t st)
+{
+    auto kern = shift_table_kernel<S, RowBlock<S>::SH, FILTER>;
+    static size_t attr_set = 0;
+    if (smem > attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { umpa_set_error("cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e)); return UMPA_ERR_CUDA; }
+        attr_set = smem;
+    }
+    kern<<<grid, nt, smem, st>>>(mapA, mapB, p);
     UMPA_CUDA(cudaGetLastError());
     return UMPA_OK;
 }
 
 template <bool FILTER>
-int dispatch_shift_table(int S, const TableParams &p, dim3 grid, size_t smem, cudaStream_t st)
+int dispatch_shift_table(int S, const CUtensorMap &a, const CUtensorMap &b, const TableParams &p, dim3 grid, int nt,
+                         size_t smem, cudaStream_t st)
 {
     switch (S) {
-        case 3: return launch_shift_table<3, FILTER>(p, grid, smem, st);
-        case 5: return launch_shift_table<5, FILTER>(p, grid, smem, st);
-        case 7: return launch_shift_table<7, FILTER>(p, grid, smem, st);
-        case 9: return launch_shift_table<9, FILTER>(p, grid, smem, st);
-        case 11: return launch_shift_table<11, FILTER>(p, grid, smem, st);
-        case 13: return launch_shift_table<13, FILTER>(p, grid, smem, st);
-        case 15: return launch_shift_table<15, FILTER>(p, grid, smem, st);
-        case 17: return launch_shift_table<17, FILTER>(p, grid, smem, st);
-        case 19: return launch_shift_table<19, FILTER>(p, grid, smem, st);
+        case 3: return launch_shift_table<3, FILTER>(a, b, p, grid, nt, smem, st);
+        case 5: return launch_shift_table<5, FILTER>(a, b, p, grid, nt, smem, st);
+        case 7: return launch_shift_table<7, FILTER>(a, b, p, grid, nt, smem, st);
+        case 9: return launch_shift_table<9, FILTER>(a, b, p, grid, nt, smem, st);
+        case 11: return launch_shift_table<11, FILTER>(a, b, p, grid, nt, smem, st);
+        case 13: return launch_shift_table<13, FILTER>(a, b, p, grid, nt, smem, st);
+        case 15: return launch_shift_table<15, FILTER>(a, b, p, grid, nt, smem, st);
+        case 17: return launch_shift_table<17, FILTER>(a, b, p, grid, nt, smem, st);
+        case 19: return launch_shift_table<19, FILTER>(a, b, p, grid, nt, smem, st);
     }
     umpa_set_error("table path: max_shift %d not instantiated", (S + 1) / 2);
     return UMPA_ERR_UNSUPPORTED;
 }
 
-// Fill in tile geometry for one table kernel; returns dynamic smem bytes (0 = does not fit).
-size_t plan_tiles(TableParams &p, int S, bool filter)
+int row_block_of(int S) { return S <= 9 ? 3 : (S <= 17 ? 2 : 1); }
+
+// Tile geometry of one table kernel.  Returns dynamic smem bytes (0 = unsupported) and the block size.
+size_t plan_tiles(TableParams &p, int S, bool filter, int *nt)
 {
-    const int HS = (S - 1) / 2;
-    const int halo = filter ? p.Nw : 0;
-    const int NA4 = (S + 3 + 3) / 4;
-    for (int TH = 16; TH >= 2; TH /= 2) {
-        p.TH = TH;
-        p.EH = TH + 2 * halo;
-        p.EWs = 4 * ((TILE_W + 2 * halo + 3) / 4);
-        p.AH = p.EH + 2 * HS;
-        p.AP = p.EWs - 4 + 4 * NA4;
-        const int nstrips = p.EH * (p.EWs / 4);
-        if (nstrips > MAX_NT) continue;
-        p.nt = std::max(128, 32 * ((nstrips + 31) / 32));
-        const size_t slot = (size_t)(p.AH * p.AP + p.EH * p.EWs) * sizeof(float);
-        const size_t cbuf = filter ? (size_t)S * p.EH * p.EWs * sizeof(float) : 0;
-        const size_t budget = SMEM_CAP - 1024;
-        if ((size_t)p.Na * slot + cbuf <= budget) {
-            p.resident = 1; p.nslot = p.Na;
-            return p.Na * slot + cbuf;
-        }
-        const int ns = PF_DEPTH + 1;
-        if (ns * slot + cbuf <= budget) {
-            p.resident = 0; p.nslot = ns;
-            return ns * slot + cbuf;
-        }
-    }
-    return 0;
+    const int HS = (S - 1) / 2, halo = filter ? p.Nw : 0;
+    const int delta = (4 - HS % 4) % 4;
+    const int NA4 = (delta + S + 3 + 3) / 4, SH = row_block_of(S);
+    p.TW = (EXT_W - 2 * halo) & ~3;
+    if (p.TW < 8) return 0;
+    p.EH = 16;                                         // 16 rows x 8 strips = 128 threads per group
+    p.TH = p.EH - 2 * halo;
+    if (p.TH < 2) return 0;
+    p.G = std::min(MAX_NT / (p.EH * 8), (S + SH - 1) / SH);
+    p.npass = (S + p.G * SH - 1) / (p.G * SH);
+    p.AH = p.EH + 2 * HS;
+    p.AP = EXT_W - 4 + 4 * NA4;
+    *nt = p.G * p.EH * 8;
+    auto up32 = [](int floats) { return (floats + 31) & ~31; };      // 128 B
+    p.a_stage_floats = up32(p.AH * p.AP);
+    p.stage_floats = p.a_stage_floats + up32(p.EH * EXT_W);
+    const size_t cbuf = filter ? (size_t)p.G * S * p.EH * EXT_W * sizeof(float) : 0;
+    const size_t budget = SMEM_CAP - 2048;
+    int ns = MAX_STAGES;
+    while (ns > 2 && (size_t)ns * p.stage_floats * sizeof(float) + cbuf > budget) ns--;
+    if ((size_t)ns * p.stage_floats * sizeof(float) + cbuf > budget) return 0;
+    p.nstage = std::min(ns, 6);
+    return (size_t)p.nstage * p.stage_floats * sizeof(float) + cbuf;
 }
 
 }  // namespace
@@ -569,10 +679,21 @@ bool table_eligible(const umpa_model *m, const RoiView &roi, std::string *why)
     if (!m->separable) return no("window is not separable");
     if (m->refshift) return no("reference_shift=1");
     if (m->max_shift < 2 || m->max_shift > 10) return no("max_shift outside 2..10");
-    if (m->Nw > 15) return no("window too large");
+    if (m->Nw > 6) return no("window too large for the tiled kernel (Nw > 6)");
     if (roi.step0 * roi.step1 > 16) return no("sparse ROI (step product > 16)");
     if (!m->d_sam32) return no("FP32 stacks not prepared");
+    if (!encode_tiled_fn()) return no("driver has no cuTensorMapEncodeTiled");
     return true;
+}
+
+// UMPA_DEBUG_SYNC=1: synchronise after every stage and name the one that faulted
+static int stage_check(const char *name, cudaStream_t st)
+{
+    static const bool on = getenv("UMPA_DEBUG_SYNC") != nullptr;
+    if (!on) return UMPA_OK;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { umpa_set_error("stage '%s' failed: %s", name, cudaGetErrorString(e)); return UMPA_ERR_CUDA; }
+    return UMPA_OK;
 }
 
 int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st)
@@ -585,19 +706,23 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
     const int rows = (roi.N0 - 1) * roi.step0 + 1, cols = (roi.N1 - 1) * roi.step1 + 1;
 
     TableParams px{};
-    px.Na = Na; px.Nw = m->Nw; px.H = H; px.W = m->W; px.pitch = pitch; px.oy = oy; px.ox = ox; px.g = m->d_g;
+    px.Na = Na; px.Nw = m->Nw; px.oy = oy; px.g = m->d_g;
     TableParams pm = px;
-    const size_t smx = plan_tiles(px, S, true);
-    const size_t smm = df ? plan_tiles(pm, S, false) : 1;
+    // shift each table's origin left so that its B-tile columns (origin - halo) are 16 B aligned
+    const int dxX = (ox - m->Nw) & 3, dxM = ox & 3;
+    px.ox = ox - dxX; pm.ox = ox - dxM;
+    int ntx = 0, ntm = 0;
+    const size_t smx = plan_tiles(px, S, true, &ntx);
+    const size_t smm = df ? plan_tiles(pm, S, false, &ntm) : 1;
     if (!smx || !smm) { umpa_set_error("table path: tile does not fit shared memory"); return UMPA_ERR_UNSUPPORTED; }
-    // one table geometry for both kernels: pad to the larger tile height
-    const int THmax = std::max(px.TH, df ? pm.TH : px.TH);
-    const int rows_p = THmax * ((rows + THmax - 1) / THmax), cols_p = TILE_W * ((cols + TILE_W - 1) / TILE_W);
-    px.rows_p = pm.rows_p = rows_p; px.cols_p = pm.cols_p = cols_p;
-    const size_t tab_bytes = (size_t)S * S * rows_p * cols_p * sizeof(float);
+    auto padded = [](int n, int t) { return t * ((n + t - 1) / t); };
+    px.rows_p = padded(rows, px.TH); px.cols_p = padded(cols + dxX, px.TW);
     int rc;
-    if ((rc = scratch_reserve(m, m->tabX, tab_bytes))) return rc;
-    if (df && (rc = scratch_reserve(m, m->tabM, tab_bytes))) return rc;
+    if ((rc = scratch_reserve(m, m->tabX, (size_t)S * S * px.rows_p * px.cols_p * sizeof(float)))) return rc;
+    if (df) {
+        pm.rows_p = padded(rows, pm.TH); pm.cols_p = padded(cols + dxM, pm.TW);
+        if ((rc = scratch_reserve(m, m->tabM, (size_t)S * S * pm.rows_p * pm.cols_p * sizeof(float)))) return rc;
+    }
     const size_t img = (size_t)H * pitch;
     if ((rc = scratch_reserve(m, m->auxS, img * sizeof(float4)))) return rc;
     if ((rc = scratch_reserve(m, m->auxR, img * sizeof(float4)))) return rc;
@@ -628,24 +753,33 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         moments_kernel<<<grid, MO_NT, smem, st>>>(mp);
         UMPA_CUDA(cudaGetLastError());
         m->last_launches++;
+        if ((rc = stage_check("moments", st))) return rc;
     }
     if (m->profiling) UMPA_CUDA(cudaEventRecord(m->ev[1], st));
 
-    // 2. cross table: A = centred reference, B = centred sample, window-filtered
-    px.A = m->d_ref32; px.B = m->d_sam32; px.table = (float *)m->tabX.p;
+    // 2. cross table: A = centred reference (read at p+s), B = centred sample, window-filtered
     {
-        dim3 grid(cols_p / TILE_W, rows_p / px.TH);
-        if ((rc = dispatch_shift_table<true>(S, px, grid, smx, st))) return rc;
+        CUtensorMap ma, mb;
+        if ((rc = make_stack_map(&ma, m->d_ref32, Na, H, m->W, pitch, px.AP, px.AH))) return rc;
+        if ((rc = make_stack_map(&mb, m->d_sam32, Na, H, m->W, pitch, EXT_W, px.EH))) return rc;
+        px.table = (float *)m->tabX.p;
+        dim3 grid(px.cols_p / px.TW, px.rows_p / px.TH);
+        if ((rc = dispatch_shift_table<true>(S, ma, mb, px, grid, ntx, smx, st))) return rc;
         m->last_launches++;
+        if ((rc = stage_check("cross table", st))) return rc;
     }
     if (m->profiling) UMPA_CUDA(cudaEventRecord(m->ev[2], st));
 
     // 3. mean table (DF): A = a_k, B = b_k, no filter
     if (df) {
-        pm.A = (const float *)m->filtA.p; pm.B = (const float *)m->filtB.p; pm.table = (float *)m->tabM.p;
-        dim3 grid(cols_p / TILE_W, rows_p / pm.TH);
-        if ((rc = dispatch_shift_table<false>(S, pm, grid, smm, st))) return rc;
+        CUtensorMap ma, mb;
+        if ((rc = make_stack_map(&ma, (const float *)m->filtA.p, Na, H, m->W, pitch, pm.AP, pm.AH))) return rc;
+        if ((rc = make_stack_map(&mb, (const float *)m->filtB.p, Na, H, m->W, pitch, EXT_W, pm.EH))) return rc;
+        pm.table = (float *)m->tabM.p;
+        dim3 grid(pm.cols_p / pm.TW, pm.rows_p / pm.TH);
+        if ((rc = dispatch_shift_table<false>(S, ma, mb, pm, grid, ntm, smm, st))) return rc;
         m->last_launches++;
+        if ((rc = stage_check("mean table", st))) return rc;
     }
     if (m->profiling) UMPA_CUDA(cudaEventRecord(m->ev[3], st));
 
@@ -654,9 +788,11 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         WalkParams w{};
         w.tabX = (const float *)m->tabX.p; w.tabM = df ? (const float *)m->tabM.p : nullptr;
         w.auxS = (const float4 *)m->auxS.p; w.auxR = (const float4 *)m->auxR.p;
-        w.pitch = pitch; w.rows_p = rows_p; w.cols_p = cols_p; w.oy = oy; w.ox = ox;
+        w.pitch = pitch; w.rowsX = px.rows_p; w.colsX = px.cols_p; w.rowsM = pm.rows_p; w.colsM = pm.cols_p;
+        w.oy = oy; w.ox = ox; w.dxX = dxX; w.dxM = dxM;
         w.kind = m->kind; w.Na = Na; w.max_shift = m->max_shift; w.subpx = m->subpx;
         w.sw = m->win_sum; w.quad = m->d_quad;
+        w.inv_sw = 1. / w.sw; w.inv_sw2 = 1. / (w.sw * w.sw); w.inv_Na = 1. / (double)Na;
         double cd = 0., cc = 0., dd = 0.;
         for (int k = 0; k < Na; k++) {
             cd += m->mean_r[k] * m->mean_s[k];
@@ -664,11 +800,11 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
             dd += m->mean_s[k] * m->mean_s[k];
         }
         w.cd = cd; w.cc = cc; w.dd = dd;
-        const int threads = 128;
-        dim3 grid((roi.N1 + threads - 1) / threads, roi.N0);
-        table_walk_kernel<<<grid, threads, 0, st>>>(w, roi, out);
+        dim3 grid((roi.N1 + WALK_NT - 1) / WALK_NT, roi.N0);
+        table_walk_kernel<<<grid, WALK_NT, 0, st>>>(w, roi, out);
         UMPA_CUDA(cudaGetLastError());
         m->last_launches++;
+        if ((rc = stage_check("walk", st))) return rc;
     }
     if (m->profiling) { UMPA_CUDA(cudaEventRecord(m->ev[4], st)); m->ev_valid = true; }
     return UMPA_OK;

@@ -104,9 +104,10 @@ __device__ inline double subpixel_quadratic(const double *__restrict__ c_quad, c
 // reference's args_copy: the fit parameters of the best shift seen so far -- deliberately
 // NOT refreshed on a restart (Optim.cpp:364-377), which the reference's outputs depend on.
 // Eval: int operator()(int si, int sj, double &cost, FitArgs &args) -> error_status bits.
-template <class Eval>
+// Grid: anything indexable by [int] yielding double& (a local array, or a shared-memory column).
+template <class Eval, class Grid>
 __device__ inline int walk_minimise(Eval &eval, int subpx, const double *quad, FitArgs &args, double &out,
-                                    double *uv, double *d, double *a, int &ncalls)
+                                    double *uv, Grid d, double *a, int &ncalls)
 {
     const double tol = 1e-8;                       // absolute, Optim.cpp:243
     int settled0 = 0, settled1 = 0, axis = 0, st;
@@ -219,8 +220,9 @@ __device__ inline int walk_minimise(Eval &eval, int subpx, const double *quad, F
 }
 
 // Writes one pixel's results the way Model*::min packs `values` (Model.cpp:573-576, 934-938).
+template <class Grid>
 __device__ __forceinline__ void store_pixel(const umpa_outputs &o, size_t n, int kind, int st, double f,
-                                            const FitArgs &args, const double *uv, const double *d,
+                                            const FitArgs &args, const double *uv, Grid d,
                                             const double *a, int ncalls, bool have_a)
 {
     if (o.f) o.f[n] = f;
