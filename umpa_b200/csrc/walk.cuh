@@ -103,120 +103,143 @@ __device__ inline double subpixel_quadratic(const double *__restrict__ c_quad, c
 // not evaluated).  axis 0 scans the column shift, axis 1 the row shift.  `keep` is the
 // reference's args_copy: the fit parameters of the best shift seen so far -- deliberately
 // NOT refreshed on a restart (Optim.cpp:364-377), which the reference's outputs depend on.
+//
+// The reference calls the cost function from four places (centre, minus neighbour, plus
+// neighbour, 4x4 fill).  On a GPU that would serialise the lanes of a warp that happen to be
+// at different call sites, so the same control flow is written as a state machine with ONE
+// evaluation site: each lane advances its state until it knows which shift it needs next,
+// all lanes evaluate together, then each lane files the result.  The sequence of
+// evaluations per pixel -- and therefore Ncalls, d, the 4x4 block and every tie decision --
+// is exactly the reference's.
 // Eval: int operator()(int si, int sj, double &cost, FitArgs &args) -> error_status bits.
 // Grid: anything indexable by [int] yielding double& (a local array, or a shared-memory column).
 template <class Eval, class Grid>
 __device__ inline int walk_minimise(Eval &eval, int subpx, const double *quad, FitArgs &args, double &out,
                                     double *uv, Grid d, double *a, int &ncalls)
 {
+    enum { P_INIT, P_TOP, P_LO, P_HI, P_DECIDE, P_FILL, P_DONE };
     const double tol = 1e-8;                       // absolute, Optim.cpp:243
-    int settled0 = 0, settled1 = 0, axis = 0, st;
-    FitArgs keep;
+    int settled0 = 0, settled1 = 0, axis = 0, st = UMPA_ST_OK;
+    int phase = P_INIT, fill = 0, ip = 0, jp = 0;
+    bool up_m = false, up_p = false, skip_limit = false, finished = false;
+    FitArgs keep = args;
 #pragma unroll
     for (int n = 0; n < 25; n++) d[n] = -1.;
     ncalls = 0;
     int c0 = (int)round(uv[0]), c1 = (int)round(uv[1]);
 
-    st = eval(c0, c1, d[12], args);
-    ncalls++;
-    if (st != UMPA_ST_OK) return st;
-    keep = args;
-
-    bool skip_limit = false;                       // a restart re-enters the loop body unconditionally
-    while (skip_limit || ncalls < UMPA_MAX_CALLS) {
-        skip_limit = false;
-        const int lo = axis ? 7 : 11, hi = axis ? 17 : 13;
-        const int dr = axis, dc = 1 - axis;
-        bool up_m, up_p;
-
-        if (d[lo] < -.5) {
-            st = eval(c0 - dr, c1 - dc, d[lo], args);
-            ncalls++;
-            if (st != UMPA_ST_OK) return st;
-            up_m = d[lo] > d[12] + tol;
-            if (!up_m) keep = args;
-        } else up_m = d[lo] > d[12] + tol;
-
-        if (d[hi] < -.5) {
-            st = eval(c0 + dr, c1 + dc, d[hi], args);
-            ncalls++;
-            if (st != UMPA_ST_OK) return st;
-            up_p = d[hi] > d[12] - tol;
-            if (!up_p) keep = args;
-        } else up_p = d[hi] > d[12] - tol;
-
-        if (up_m && up_p) {
-            const int dir = d[lo] < d[hi] ? -1 : 1;
-            if (axis) settled1 = dir; else settled0 = dir;
-            if ((axis ? settled0 : settled1) == 0) { axis = 1 - axis; continue; }
-
-            const int ip = d[17] < d[7] ? 1 : 0;
-            const int jp = d[13] < d[11] ? 1 : 0;
-            bool restarted = false;
-            for (int r = 0; r < 4 && !restarted; r++)
-                for (int q = 0; q < 4; q++) {
-                    const int n = 5 * (ip + r) + jp + q;
-                    if (d[n] < -.9) {
-                        const int e0 = c0 + ip + r - 2, e1 = c1 + jp + q - 2;
-                        double v;
-                        st = eval(e0, e1, v, args);
-                        ncalls++;
-                        if (st != UMPA_ST_OK) return st;
-                        a[4 * r + q] = v;
-                        d[n] = v;
-                        if (v < d[12]) {           // lower value off-axis: hard restart there
-                            c0 = e0; c1 = e1;
-#pragma unroll
-                            for (int t = 0; t < 25; t++) d[t] = -1.;
-                            d[12] = v;
-                            args = keep;
-                            settled0 = settled1 = 0;
-                            restarted = true;
-                            break;
+    while (true) {
+        // ---- advance this lane's state until it needs a cost value (or is done) ----
+        bool want = false;
+        int e0 = 0, e1 = 0, slot = 12;
+        while (!want && phase != P_DONE) {
+            if (phase == P_INIT) {
+                want = true; e0 = c0; e1 = c1; slot = 12;
+            } else if (phase == P_TOP) {
+                if (!skip_limit && ncalls >= UMPA_MAX_CALLS) { st = 0; phase = P_DONE; }   // Optim.cpp:267,477
+                else { skip_limit = false; phase = P_LO; }
+            } else if (phase == P_LO) {
+                slot = axis ? 7 : 11;
+                if (d[slot] < -.5) { want = true; e0 = c0 - axis; e1 = c1 - (1 - axis); }
+                else { up_m = d[slot] > d[12] + tol; phase = P_HI; }
+            } else if (phase == P_HI) {
+                slot = axis ? 17 : 13;
+                if (d[slot] < -.5) { want = true; e0 = c0 + axis; e1 = c1 + (1 - axis); }
+                else { up_p = d[slot] > d[12] - tol; phase = P_DECIDE; }
+            } else if (phase == P_DECIDE) {
+                const int lo = axis ? 7 : 11, hi = axis ? 17 : 13;
+                if (up_m && up_p) {
+                    const int dir = d[lo] < d[hi] ? -1 : 1;
+                    if (axis) settled1 = dir; else settled0 = dir;
+                    if ((axis ? settled0 : settled1) == 0) { axis = 1 - axis; phase = P_TOP; }
+                    else {
+                        ip = d[17] < d[7] ? 1 : 0;
+                        jp = d[13] < d[11] ? 1 : 0;
+                        fill = 0;
+                        phase = P_FILL;
+                    }
+                } else {
+                    uv[0] = c0; uv[1] = c1;        // best so far, Optim.cpp:421-423
+                    out = d[12];
+                    bool plus = up_m;
+                    if (!up_p && !up_m) plus = d[hi] < d[lo];      // local maximum: go downhill
+                    if (plus) {
+                        if (axis) {
+                            c0 += 1;
+                            for (int n = 0; n < 20; n++) d[n] = d[n + 5];
+                            for (int n = 20; n < 25; n++) d[n] = -1.;
+                        } else {
+                            c1 += 1;
+                            for (int n = 0; n < 24; n++) d[n] = d[n + 1];
+                            for (int r = 0; r < 5; r++) d[5 * r + 4] = -1.;
                         }
-                    } else a[4 * r + q] = d[n];
+                    } else {
+                        if (axis) {
+                            c0 -= 1;
+                            for (int n = 24; n >= 5; n--) d[n] = d[n - 5];
+                            for (int n = 0; n < 5; n++) d[n] = -1.;
+                        } else {
+                            c1 -= 1;
+                            for (int n = 24; n >= 1; n--) d[n] = d[n - 1];
+                            for (int r = 0; r < 5; r++) d[5 * r] = -1.;
+                        }
+                    }
+                    if (axis) settled0 = 0; else settled1 = 0;
+                    phase = P_TOP;
                 }
-            if (restarted) { skip_limit = true; continue; }
-
-            args = keep;
-            uv[0] = 1. - ip;
-            uv[1] = 1. - jp;
-            if (subpx == 0) out = uv[0];                           // reference quirk, Optim.cpp:399
-            else if (subpx == 1) out = subpixel_quadratic(quad, a, uv);
-            else out = subpixel_spline(a, uv);
-            uv[0] += c0 + ip - 1.;
-            uv[1] += c1 + jp - 1.;
-            return st;
-        }
-
-        uv[0] = c0; uv[1] = c1;                    // best so far, Optim.cpp:421-423
-        out = d[12];
-        if (!up_p && !up_m) up_m = d[hi] < d[lo];  // local maximum: go downhill
-
-        if (up_m) {                                // step to the plus side
-            if (axis) {
-                c0 += 1;
-                for (int n = 0; n < 20; n++) d[n] = d[n + 5];
-                for (int n = 20; n < 25; n++) d[n] = -1.;
-            } else {
-                c1 += 1;
-                for (int n = 0; n < 24; n++) d[n] = d[n + 1];
-                for (int r = 0; r < 5; r++) d[5 * r + 4] = -1.;
-            }
-        } else {                                   // step to the minus side
-            if (axis) {
-                c0 -= 1;
-                for (int n = 24; n >= 5; n--) d[n] = d[n - 5];
-                for (int n = 0; n < 5; n++) d[n] = -1.;
-            } else {
-                c1 -= 1;
-                for (int n = 24; n >= 1; n--) d[n] = d[n - 1];
-                for (int r = 0; r < 5; r++) d[5 * r] = -1.;
+            } else {                               // P_FILL: next missing entry of the 4x4 block
+                while (fill < 16) {
+                    const int r = fill >> 2, q = fill & 3;
+                    slot = 5 * (ip + r) + jp + q;
+                    if (d[slot] < -.9) { want = true; e0 = c0 + ip + r - 2; e1 = c1 + jp + q - 2; break; }
+                    fill++;
+                }
+                if (!want) { finished = true; phase = P_DONE; }
             }
         }
-        if (axis) settled0 = 0; else settled1 = 0;
+        if (!want) break;
+
+        // ---- the one evaluation site ----
+        double v;
+        const int se = eval(e0, e1, v, args);
+        ncalls++;
+        if (se != UMPA_ST_OK) { st = se; break; }  // bound error: return at once (Optim.cpp:264,291,324,359)
+
+        // ---- file the result ----
+        d[slot] = v;
+        if (phase == P_INIT) { keep = args; phase = P_TOP; }
+        else if (phase == P_LO) { up_m = v > d[12] + tol; if (!up_m) keep = args; phase = P_HI; }
+        else if (phase == P_HI) { up_p = v > d[12] - tol; if (!up_p) keep = args; phase = P_DECIDE; }
+        else {                                     // P_FILL
+            if (v < d[12]) {                       // lower value off-axis: hard restart there
+                c0 = e0; c1 = e1;
+#pragma unroll
+                for (int t = 0; t < 25; t++) d[t] = -1.;
+                d[12] = v;
+                args = keep;
+                settled0 = settled1 = 0;
+                skip_limit = true;
+                phase = P_TOP;
+            } else fill++;
+        }
     }
-    return 0;                                      // too many calls, Optim.cpp:477
+
+    if (finished) {                                // minimum bracketed on both axes: sub-pixel fit
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) a[4 * r + q] = d[5 * (ip + r) + jp + q];
+        args = keep;
+        uv[0] = 1. - ip;
+        uv[1] = 1. - jp;
+        if (subpx == 0) out = uv[0];                                   // reference quirk, Optim.cpp:399
+        else if (subpx == 1) out = subpixel_quadratic(quad, a, uv);
+        else out = subpixel_spline(a, uv);
+        uv[0] += c0 + ip - 1.;
+        uv[1] += c1 + jp - 1.;
+        st = UMPA_ST_OK;
+    }
+    return st;
 }
 
 // Writes one pixel's results the way Model*::min packs `values` (Model.cpp:573-576, 934-938).
