@@ -262,6 +262,7 @@ int umpa_create(umpa_model **out, int kind, int Na, const int32_t *dim, const in
     m->kind = kind; m->Na = Na; m->max_shift = max_shift; m->padding = padding;
     cudaError_t e = cudaGetDevice(&m->device);
     if (e != cudaSuccess) { umpa_set_error("no CUDA device: %s", cudaGetErrorString(e)); delete m; return UMPA_ERR_CUDA; }
+    cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device);
     m->dim.assign(dim, dim + 2 * Na);
     if (pos) m->pos.assign(pos, pos + 2 * Na); else m->pos.assign(2 * Na, 0);
     m->uniform = true;

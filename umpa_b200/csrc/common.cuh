@@ -63,7 +63,7 @@ struct Scratch {
 struct umpa_model {
     int kind = 0, Na = 0, Nw = 0, K = 0, max_shift = 0, padding = 0;
     int subpx = -1, refshift = 0, path_opt = UMPA_PATH_AUTO;
-    int device = 0;
+    int device = 0, sm_count = 148;
     std::vector<int> dim, pos;                   // host copies
     std::vector<double> win;                     // K*K
     bool uniform = false;                        // equal shapes and zero positions

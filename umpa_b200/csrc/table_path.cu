@@ -225,6 +225,7 @@ struct TableParams {
     int AH, AP;                  // A tile rows, pitch (= TMA box width)
     int G, npass, nstage;
     int a_stage_floats, stage_floats;   // per-stage layout: A tile then B tile (128 B aligned)
+    int tiles_x, tiles_y;               // tile grid (the kernel is persistent over it)
 };
 
 constexpr int EXT_W = 32;          // extended tile width: one 128 B line per row
@@ -286,12 +287,9 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     const int TG = p.EH * (EXT_W / 4);               // threads per group
     const int grp = tid / TG, lt = tid - grp * TG;
     const int er = lt >> 3, ec = (lt & 7) << 2;      // strip: extended row, first extended column
-    const bool worker = grp < p.G;
-    const int ty0 = blockIdx.y * p.TH, tx0 = blockIdx.x * p.TW;          // table coords of the tile
-    const int by = p.oy + ty0 - halo, bx = p.ox + tx0 - halo;            // raw origin of the B tile
-    const int ay = by - HS, ax = bx - HS - DELTA;                        // raw origin of the A tile
     float *cbuf = sm + (size_t)p.nstage * p.stage_floats;                // [G*S][EH][EXT_W] (FILTER only)
     const uint32_t stage_bytes = (uint32_t)(p.AH * p.AP + p.EH * EXT_W) * sizeof(float);
+    const size_t plane_sz = (size_t)p.rows_p * p.cols_p;
 
     if (FILTER && tid < K) gs[tid] = p.g[tid];
     if (tid == 0) {
@@ -301,68 +299,93 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     }
     __syncthreads();
 
-    const int total = p.npass * p.Na;
-    auto issue = [&](int it) {                       // thread 0: frame of iteration `it` -> its stage
-        const int s = it % p.nstage, frame = it % p.Na;
-        float *As = sm + (size_t)s * p.stage_floats, *Bs = As + p.a_stage_floats;
-        mbar_expect_tx(&full_bar[s], stage_bytes);
-        tma_load_3d(As, &mapA, ax, ay, frame, &full_bar[s]);
-        tma_load_3d(Bs, &mapB, bx, by, frame, &full_bar[s]);
-    };
-    if (tid == 0)
-        for (int it = 0; it < p.nstage && it < total; it++) issue(it);
+    // ---- persistent CTA: tiles blockIdx.x, +gridDim.x, ... ; the frame ring runs across tiles ----
+    const int ntiles = p.tiles_x * p.tiles_y;
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int per_tile = p.npass * p.Na;
+    const int total = my_tiles * per_tile;
 
+    // producer state (thread 0): next (tile, frame) to request, and where
+    int pr_issued = 0, pr_tile = blockIdx.x, pr_left = per_tile, pr_frame = 0, pr_stage = 0;
+    int pr_ax = 0, pr_ay = 0, pr_bx = 0, pr_by = 0;
+    auto pr_coords = [&]() {
+        const int tyi = pr_tile / p.tiles_x, txi = pr_tile - tyi * p.tiles_x;
+        pr_by = p.oy + tyi * p.TH - halo; pr_bx = p.ox + txi * p.TW - halo;
+        pr_ay = pr_by - HS; pr_ax = pr_bx - HS - DELTA;
+    };
+    auto issue_next = [&]() {
+        float *As = sm + (size_t)pr_stage * p.stage_floats, *Bs = As + p.a_stage_floats;
+        mbar_expect_tx(&full_bar[pr_stage], stage_bytes);
+        tma_load_3d(As, &mapA, pr_ax, pr_ay, pr_frame, &full_bar[pr_stage]);
+        tma_load_3d(Bs, &mapB, pr_bx, pr_by, pr_frame, &full_bar[pr_stage]);
+        pr_issued++;
+        if (++pr_stage == p.nstage) pr_stage = 0;
+        if (++pr_frame == p.Na) pr_frame = 0;
+        if (--pr_left == 0) { pr_left = per_tile; pr_tile += gridDim.x; pr_coords(); }
+    };
+    if (tid == 0) {
+        pr_coords();
+        for (int n = 0; n < p.nstage && n < total; n++) issue_next();
+    }
+
+    int stage = 0, phase = 0;                        // consumer ring position
+    int prev_stage = 0, prev_phase = 0;
+    bool first = true;
     float acc[SH][S][4];
-    for (int it = 0; it < total; it++) {
-        const int frame = it % p.Na, pass = it / p.Na;
-        const int s = it % p.nstage;
-        if (tid == 0 && it >= 1) {                   // refill the stage that frame it-1 used
-            const int nxt = it - 1 + p.nstage;
-            if (nxt < total) {
-                mbar_wait(&empty_bar[(it - 1) % p.nstage], ((it - 1) / p.nstage) & 1);
-                issue(nxt);
-            }
-        }
-        if (frame == 0) {
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tyi = tile / p.tiles_x, txi = tile - tyi * p.tiles_x;
+        const int ty0 = tyi * p.TH, tx0 = txi * p.TW;                    // table coords of the tile
+        for (int pass = 0; pass < p.npass; pass++) {
+            const int si0 = (pass * p.G + grp) * SH; // first shift row of this thread in this pass
+            const bool work = si0 < S;
 #pragma unroll
             for (int a = 0; a < SH; a++)
 #pragma unroll
                 for (int b = 0; b < S; b++)
 #pragma unroll
                     for (int c = 0; c < 4; c++) acc[a][b][c] = 0.f;
-        }
-        mbar_wait(&full_bar[s], (it / p.nstage) & 1);
-        const int si0 = (pass * p.G + grp) * SH;     // first shift row of this thread in this pass
-        if (worker && si0 < S) {
-            const float *As = sm + (size_t)s * p.stage_floats;
-            const float *Bs = As + p.a_stage_floats;
-            const float4 b4 = *reinterpret_cast<const float4 *>(Bs + er * EXT_W + ec);
-            const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-            for (int sh = 0; sh < SH; sh++) {
-                if (si0 + sh < S) {
-                    const float *arow = As + (er + si0 + sh) * p.AP + ec;
-                    float av[4 * NA4];
-#pragma unroll
-                    for (int v = 0; v < NA4; v++) {
-                        const float4 t = *reinterpret_cast<const float4 *>(arow + 4 * v);
-                        av[4 * v] = t.x; av[4 * v + 1] = t.y; av[4 * v + 2] = t.z; av[4 * v + 3] = t.w;
-                    }
-#pragma unroll
-                    for (int sj = 0; sj < S; sj++)
-#pragma unroll
-                        for (int x = 0; x < 4; x++) acc[sh][sj][x] = fmaf(bv[x], av[DELTA + sj + x], acc[sh][sj][x]);
-                }
-            }
-        }
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);      // this warp is done with the stage
 
-        if (frame == p.Na - 1) {
+            for (int frame = 0; frame < p.Na; frame++) {
+                if (tid == 0 && !first && pr_issued < total) {           // refill the stage the previous frame used
+                    mbar_wait(&empty_bar[prev_stage], prev_phase);
+                    issue_next();
+                }
+                first = false;
+                mbar_wait(&full_bar[stage], phase);
+                if (work) {
+                    const float *As = sm + (size_t)stage * p.stage_floats;
+                    const float *Bs = As + p.a_stage_floats;
+                    const float4 b4 = *reinterpret_cast<const float4 *>(Bs + er * EXT_W + ec);
+                    const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+                    const float *arow0 = As + (er + si0) * p.AP + ec;
+#pragma unroll
+                    for (int sh = 0; sh < SH; sh++) {
+                        if (si0 + sh < S) {
+                            const float *arow = arow0 + sh * p.AP;
+                            float av[4 * NA4];
+#pragma unroll
+                            for (int v = 0; v < NA4; v++) {
+                                const float4 t = *reinterpret_cast<const float4 *>(arow + 4 * v);
+                                av[4 * v] = t.x; av[4 * v + 1] = t.y; av[4 * v + 2] = t.z; av[4 * v + 3] = t.w;
+                            }
+#pragma unroll
+                            for (int sj = 0; sj < S; sj++)
+#pragma unroll
+                                for (int x = 0; x < 4; x++)
+                                    acc[sh][sj][x] = fmaf(bv[x], av[DELTA + sj + x], acc[sh][sj][x]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);     // this warp is done with the stage
+                prev_stage = stage; prev_phase = phase;
+                if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+            }
+
             // ---------------- epilogue of this pass ----------------
-            const size_t plane_sz = (size_t)p.rows_p * p.cols_p;
             if (!FILTER) {
-                if (worker) {
+                if (work) {
 #pragma unroll
                     for (int sh = 0; sh < SH; sh++) {
                         const int si = si0 + sh;
@@ -378,14 +401,16 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             } else {
                 const int plane = p.EH * EXT_W;      // one shift's row-filtered extended tile in cbuf
                 const int ostrips = p.TW / 4;        // output strips per row
-                const int nplanes = p.G * S;
+                const int rblocks = (p.TH + 3) / 4;
+                const int per_plane = rblocks * ostrips;
+                const int citems = p.G * S * per_plane;
 #pragma unroll
                 for (int sh = 0; sh < SH; sh++) {
                     // shift rows handled in this round: si(g) = (pass*G+g)*SH + sh for g < G.
                     // Row pass in registers: the 8 lanes of a quarter warp hold one extended row
                     // (32 columns); output x needs columns x .. x+2Nw, fetched from the lanes to the
                     // right with shuffles (lanes past the row end only feed unused outputs x >= TW).
-                    if (worker && si0 + sh < S) {
+                    if (work && si0 + sh < S) {
 #pragma unroll
                         for (int sj = 0; sj < S; sj++) {
                             const float a0 = acc[sh][sj][0], a1 = acc[sh][sj][1], a2 = acc[sh][sj][2], a3 = acc[sh][sj][3];
@@ -406,10 +431,8 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                     }
                     __syncthreads();
                     // column pass: item = (plane q, block of 4 output rows, strip c)
-                    const int rblocks = (p.TH + 3) / 4;
-                    const int citems = nplanes * rblocks * ostrips;
                     for (int item = tid; item < citems; item += nt) {
-                        const int q = item / (rblocks * ostrips), rem = item - q * (rblocks * ostrips);
+                        const int q = item / per_plane, rem = item - q * per_plane;
                         const int rb = rem / ostrips, c4 = 4 * (rem - rb * ostrips);
                         const int g_of_q = q / S, sj = q - g_of_q * S;
                         const int si = (pass * p.G + g_of_q) * SH + sh;
@@ -420,8 +443,8 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                         for (int a = 0; a < 4; a++)
 #pragma unroll
                             for (int b = 0; b < 4; b++) o[a][b] = 0.f;
-                        for (int u = 0; u < K + 3; u++) {        // input row 4*rb + u feeds output rows u-K+1 .. u
-                            if (4 * rb + u >= p.EH) break;
+                        const int nrows = min(K + 3, p.EH - 4 * rb);
+                        for (int u = 0; u < nrows; u++) {        // input row 4*rb + u feeds output rows u-K+1 .. u
                             const float4 t = *reinterpret_cast<const float4 *>(src + u * EXT_W);
 #pragma unroll
                             for (int a = 0; a < 4; a++) {
@@ -763,7 +786,8 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         if ((rc = make_stack_map(&ma, m->d_ref32, Na, H, m->W, pitch, px.AP, px.AH))) return rc;
         if ((rc = make_stack_map(&mb, m->d_sam32, Na, H, m->W, pitch, EXT_W, px.EH))) return rc;
         px.table = (float *)m->tabX.p;
-        dim3 grid(px.cols_p / px.TW, px.rows_p / px.TH);
+        px.tiles_x = px.cols_p / px.TW; px.tiles_y = px.rows_p / px.TH;
+        dim3 grid(std::min(px.tiles_x * px.tiles_y, m->sm_count));
         if ((rc = dispatch_shift_table<true>(S, ma, mb, px, grid, ntx, smx, st))) return rc;
         m->last_launches++;
         if ((rc = stage_check("cross table", st))) return rc;
@@ -776,7 +800,8 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         if ((rc = make_stack_map(&ma, (const float *)m->filtA.p, Na, H, m->W, pitch, pm.AP, pm.AH))) return rc;
         if ((rc = make_stack_map(&mb, (const float *)m->filtB.p, Na, H, m->W, pitch, EXT_W, pm.EH))) return rc;
         pm.table = (float *)m->tabM.p;
-        dim3 grid(pm.cols_p / pm.TW, pm.rows_p / pm.TH);
+        pm.tiles_x = pm.cols_p / pm.TW; pm.tiles_y = pm.rows_p / pm.TH;
+        dim3 grid(std::min(pm.tiles_x * pm.tiles_y, m->sm_count));
         if ((rc = dispatch_shift_table<false>(S, ma, mb, pm, grid, ntm, smm, st))) return rc;
         m->last_launches++;
         if ((rc = stage_check("mean table", st))) return rc;
