@@ -78,3 +78,87 @@ def compare(got, exp, tol=1e-9, walk_exact=True, max_err_mismatch=0, max_outlier
         if outlier_tol is not None and bad.any():
             assert rel.max() <= outlier_tol, f"{label}: {k} outlier {rel.max():.3g} > {outlier_tol:g}"
     return stats
+
+
+# ---------------------------------------------------------------------------------------------
+# FP32 table path: which deviations are "documented exceptions"?
+#
+# The table path feeds the reference's own spline/Newton refinement with costs that carry FP32
+# rounding (relative ~1e-6 of the block's cost scale, see tests/test_table_algebra.py).  In a
+# well-conditioned pixel that moves dx/dy by ~1e-6.  In an ill-conditioned one (flat or saddle-
+# like 4x4 block: Newton wanders far outside the block, or stops one iteration earlier/later on
+# its absolute 1e-8 criterion) the REFERENCE'S OWN answer moves by more than the tolerance when
+# its own inputs are perturbed at that level -- e.g. its -ffast-math and strict builds already
+# disagree there.  sensitivity() measures exactly that, with the oracle's spline on the
+# reference's debug_a block; a deviation is excused only where the reference is that sensitive.
+
+def block_corner(d, a):
+    """(ip, jp) such that a == d[ip:ip+4, jp:jp+4] (Optim.cpp:344-384)."""
+    d5 = np.asarray(d).reshape(5, 5)
+    a4 = np.asarray(a).reshape(4, 4)
+    for ip in (0, 1):
+        for jp in (0, 1):
+            if np.array_equal(d5[ip:ip + 4, jp:jp + 4], a4):
+                return ip, jp
+    return None
+
+
+def sensitivity(d, a, eps, trials=12, seed=0):
+    """Largest move of the reference's sub-pixel position / value when its 4x4 block is perturbed
+    by eps * max|a| (Gaussian); inf when the block cannot be located."""
+    from oracle import port
+    c = block_corner(d, a)
+    if c is None:
+        return np.inf, np.inf
+    ip, jp = c
+    a = np.asarray(a, dtype=np.float64).reshape(16)
+    p0, v0 = port.spmin(a, (1. - ip, 1. - jp))
+    rng = np.random.default_rng(seed)
+    dp, dv = 0., 0.
+    for _ in range(trials):
+        p1, v1 = port.spmin(a + eps * np.abs(a).max() * rng.standard_normal(16), (1. - ip, 1. - jp))
+        if not (np.all(np.isfinite(p1)) and np.isfinite(v1)):
+            return np.inf, np.inf
+        dp = max(dp, float(np.abs(p1 - p0).max()))
+        dv = max(dv, abs(v1 - v0))
+    return dp, dv
+
+
+def compare_fp32(got, exp, tol=1e-4, eps=3e-6, max_exception_frac=0.03, noise_floor=3e-6, label=""):
+    """Parity check of the FP32 table path (tolerances of BASELINE.json north_star):
+    err map and Ncalls (the integer walk) must be EQUAL; T, df within tol relative; dx, dy within
+    tol*max(1,|ref|) and f within tol*|ref| + noise_floor*cost_scale, except in pixels where the
+    reference's own refinement is that sensitive to eps-level input noise (see above)."""
+    err_g, err_e = np.asarray(got["err"]), np.asarray(exp["err"])
+    assert np.array_equal(err_g, err_e), f"{label}: err map differs in {(err_g != err_e).sum()} pixels"
+    ok = err_e == 1
+    assert np.array_equal(np.asarray(got["debug_Ncalls"])[ok], exp["debug_Ncalls"][ok]), f"{label}: Ncalls differ"
+    stats = {"n_ok": int(ok.sum())}
+    for k in ("T", "df"):
+        if k in exp:
+            rel = np.abs(got[k][ok] - exp[k][ok]) / np.abs(exp[k][ok])
+            stats[k] = float(rel.max()) if rel.size else 0.
+            assert rel.size == 0 or rel.max() <= tol, f"{label}: {k} off by {rel.max():.3g}"
+    dpos = exp["debug_d"][ok]
+    cost_scale = float(np.median(dpos[dpos > 0])) if (dpos > 0).any() else 1.
+    bad = np.zeros(err_e.shape, dtype=bool)
+    for k in ("dx", "dy"):
+        rel = np.abs(got[k] - exp[k]) / np.maximum(1., np.abs(exp[k]))
+        bad |= ok & ~(rel <= tol)
+        stats[k + "_p99"] = float(np.percentile(rel[ok], 99)) if ok.any() else 0.
+    df_ = np.abs(got["f"] - exp["f"])
+    bad_f = ok & ~(df_ <= tol * np.abs(exp["f"]) + noise_floor * cost_scale)
+    idx = np.argwhere(bad | bad_f)
+    stats["exceptions"] = len(idx)
+    assert len(idx) <= max(2, int(max_exception_frac * ok.sum())), (
+        f"{label}: {len(idx)} of {int(ok.sum())} ok-pixels deviate by more than {tol:g}")
+    for i, j in idx:
+        dp, dv = sensitivity(exp["debug_d"][i, j], exp["debug_a"][i, j], eps)
+        if bad[i, j]:
+            assert dp > tol / 2, (f"{label}: pixel ({i},{j}) dx/dy off by "
+                                  f"{abs(got['dx'][i, j] - exp['dx'][i, j]):.3g}/{abs(got['dy'][i, j] - exp['dy'][i, j]):.3g} "
+                                  f"but the reference moves only {dp:.3g} under eps={eps:g}")
+        else:
+            assert dv > (tol * abs(exp["f"][i, j]) + noise_floor * cost_scale) / 2, (
+                f"{label}: pixel ({i},{j}) f off by {df_[i, j]:.3g} but the reference moves only {dv:.3g}")
+    return stats

@@ -1,0 +1,89 @@
+"""CPU: host-side logic (geometry / ROI / step, window, sharding arithmetic) and the C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import golden_names, load_case
+from umpa_b200.geometry import Geometry
+from umpa_b200 import sharding
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SAFE_CROP = {"NoDF": 0, "DF": 0, "DFKernel": 8}
+
+
+def _geo(c):
+    shapes = [s.shape for s in c["sam"]]
+    pos = c["pos"] if c["pos"] is not None else [(0, 0)] * len(shapes)
+    return Geometry(shapes, pos, c["max_shift"] + c["Nw"] + SAFE_CROP[c["kind"]])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_geometry_matches_reference(name):
+    """extent, the ROI the reference ended up with after match(step=/ROI=), and its output shape."""
+    c = load_case(name)
+    g = _geo(c)
+    assert g.padding == c["padding"]
+    assert g.extent() == tuple(int(v) for v in c["extent"])
+    s0, s1 = g.match_roi(ROI=c["ROI"], step=c["step"])
+    assert (s0, s1) == tuple(tuple(int(v) for v in r) for r in c["ROI_after"])
+    assert g.ROI == (s0, s1)                      # sticky (model.pyx:406)
+    assert g.sh == tuple(int(v) for v in c["sh_after"]) == c["expected"]["err"].shape
+
+
+def test_roi_semantics():
+    g = Geometry([(40, 44)] * 3, [(0, 0)] * 3, 6)
+    assert g.ROI == ((0, 28, 1), (0, 32, 1))
+    assert g.convert(ROI=(slice(2, 20, 2), slice(None, None, 3))) == ((2, 20, 2), (0, 32, 3))
+    with pytest.raises(RuntimeError):
+        g.convert(ROI=((0, 4, 1), (0, 4, 1)), step=2)        # model.pyx:566-568
+    assert g.match_roi(ROI=((1, 9, 2), (0, 8, 1)), step=5) == ((1, 9, 2), (0, 8, 1))   # step ignored, 372-375
+    assert g.set_step(3) == ((1, 9, 3), (0, 8, 3))           # re-slices the STORED ROI (576-580)
+    assert g.sh == (3, 3)
+    r, c = g.coords()
+    assert list(r) == [7, 10, 13] and list(c) == [6, 9, 12]
+    assert Geometry.shape_of((5, 5, 1), (0, 3, 1)) == (0, 3)
+
+
+def test_window_is_the_reference_window():
+    from oracle import port
+    c = load_case("df_nw3_ms6")
+    np.testing.assert_allclose(port.make_window(3), c["window"], rtol=0, atol=1e-16)
+
+
+def test_row_bands():
+    for n, w in ((2034, 8), (10, 4), (3, 8), (28, 1)):
+        b = sharding.row_bands(n, w)
+        assert len(b) == w and b[0][0] == 0 and b[-1][1] == n
+        assert all(b[k][1] == b[k + 1][0] for k in range(w - 1))
+        sizes = [y - x for x, y in b]
+        assert max(sizes) - min(sizes) <= 1
+    assert sharding.band_input_rows((10, 20), 7) == (10, 34)
+
+
+def test_capi_exports_every_declared_symbol():
+    """The C-ABI library loads without a GPU and exports what include/umpa_b200.h declares."""
+    from umpa_b200 import _capi, build
+    build.build()
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    hdr = open(os.path.join(ROOT, "include", "umpa_b200.h")).read()
+    declared = set(re.findall(r"UMPA_API[^;(]*?\b(umpa_[a-z0-9_]+)\s*\(", hdr))
+    assert declared and declared == set(_capi.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    L = _capi.lib()
+    assert b"sm_100a" in L.umpa_version()
+
+
+def test_product_does_not_import_oracle():
+    """The product path may not route through the oracle (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "umpa_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+    for fn in os.listdir(os.path.join(pkg, "csrc")):
+        if fn.endswith((".cu", ".cuh")):
+            assert "oracle" not in open(os.path.join(pkg, "csrc", fn)).read(), fn

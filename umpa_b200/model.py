@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from . import _capi
+from .geometry import Geometry
 
 DEBUG = True      # mirrors `DEF DEBUG = True` (model.pyx:26)
 
@@ -101,6 +102,7 @@ class UMPAModelBase:
         self._window = self._make_window(Nw)
         self._uniform = (all(tuple(s) == tuple(shape_list[0]) for s in shape_list)
                          and not np.any(np.array(pos_list)))
+        self._geo = Geometry(shape_list, pos_list, self._padding)
         self._masked = masks is not None
 
         L = _capi.lib()
@@ -121,8 +123,7 @@ class UMPAModelBase:
         _capi.check(L.umpa_set_frames(self._h, ptrs(sams), ptrs(refs),
                                       ptrs(masks) if masks is not None else None,
                                       1 if self._on_device else 0, self._stream()))
-        self._ROI = None
-        self._set_ROI(ROI)
+        self._geo.set_ROI(ROI)
 
     # ------------------------------------------------------------------ plumbing
     @staticmethod
@@ -162,59 +163,27 @@ class UMPAModelBase:
         return np.ascontiguousarray(window, dtype=np.float64)
 
     # ------------------------------------------------------------------ geometry (model.pyx:531-646)
+    # delegated to geometry.Geometry (GPU-free, unit-tested on CPU)
     def _calculate_extent(self):
-        padding = self._padding
-        pmax = np.max(np.array(self._pos_list) + np.array(self._shape_list), axis=0)
-        N0 = 1 + (int(pmax[0]) - 2 * padding - 1)
-        N1 = 1 + (int(pmax[1]) - 2 * padding - 1)
-        return N0, N1
+        return self._geo.extent()
 
     def _convert_ROI_slice(self, ROI=None, step=None):
-        N0, N1 = self._calculate_extent()
-        if ROI is not None:
-            if step is not None:
-                raise RuntimeError('Step and ROI should not be specified simultaneously.')
-            s0, s1 = ROI
-            if type(s0) is slice:
-                s0 = s0.indices(N0)
-            if type(s1) is slice:
-                s1 = s1.indices(N1)
-        else:
-            s0, s1 = self._ROI
-            if step is not None:
-                s0 = slice(s0[0], s0[1], step).indices(N0)
-                s1 = slice(s1[0], s1[1], step).indices(N1)
-        return s0, s1
+        return self._geo.convert(ROI, step)
 
     def _set_ROI(self, ROI=None):
-        N0, N1 = self._calculate_extent()
-        if ROI is None:
-            self._ROI = ((0, N0, 1), (0, N1, 1))
-        else:
-            s0, s1 = ROI
-            if type(s0) is slice:
-                s0 = s0.indices(N0)
-            if type(s1) is slice:
-                s1 = s1.indices(N1)
-            self._ROI = (s0, s1)
+        self._geo.set_ROI(ROI)
 
     def set_step(self, step):
-        self._set_ROI(ROI=self._convert_ROI_slice(step=step))
-        return self._ROI
+        return self._geo.set_step(step)
 
     def coords(self, ROI=None):
-        offset = self.padding
-        if ROI is not None:
-            s0, s1 = self._convert_ROI_slice(ROI=ROI)
-        else:
-            s0, s1 = self._ROI
-        return offset + np.arange(*s0), offset + np.arange(*s1)
+        return self._geo.coords(ROI)
 
-    @staticmethod
-    def _shape_of(s0, s1):
-        N0 = 1 + (s0[1] - s0[0] - 1) // s0[2]
-        N1 = 1 + (s1[1] - s1[0] - 1) // s1[2]
-        return max(int(N0), 0), max(int(N1), 0)
+    _shape_of = staticmethod(Geometry.shape_of)
+
+    @property
+    def _ROI(self):
+        return self._geo.ROI
 
     # ------------------------------------------------------------------ properties
     extent = property(lambda self: self._calculate_extent())

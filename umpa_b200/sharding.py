@@ -57,25 +57,36 @@ class ShardedMatcher:
 
     def gather(self, local, keys=("f", "T", "dx", "dy", "df", "err"), dst=0):
         """Concatenate the bands' maps on rank `dst` (returns None elsewhere)."""
-        import torch.distributed as dist
-        out = {}
-        for k in keys:
-            if not any(k in l for l in [local]) and self.model is not None:
-                continue
-            t = local.get(k)
-            shapes = [None] * self.world
-            dist.all_gather_object(shapes, None if t is None else (tuple(t.shape), str(t.dtype)))
-            if all(s is None for s in shapes):
-                continue
-            ref_shape, ref_dtype = next(s for s in shapes if s is not None)
-            dev = t.device if t is not None else torch.device("cuda" if dist.get_backend() == "nccl" else "cpu")
-            dtype = getattr(torch, ref_dtype.split(".")[-1])
-            if t is None:
-                t = torch.empty((0,) + tuple(ref_shape[1:]), dtype=dtype, device=dev)
-            parts = None
-            if self.rank == dst:
-                parts = [torch.empty((b[1] - b[0],) + tuple(ref_shape[1:]), dtype=dtype, device=dev) for b in self.bands]
-            dist.gather(t.contiguous(), parts, dst=dst)
-            if self.rank == dst:
-                out[k] = torch.cat(parts, dim=0)
-        return out if self.rank == dst else None
+        return gather_bands(local, self.bands, self.rank, keys=keys, dst=dst)
+
+
+def gather_bands(local, bands, rank, keys=("f", "T", "dx", "dy", "df", "err"), dst=0):
+    """The only inter-GPU traffic of a sharded match: rank r contributes maps of shape
+    (bands[r][1]-bands[r][0], N1, ...); rank `dst` receives their row-wise concatenation.
+    One torch.distributed.gather per map (NCCL for CUDA tensors, gloo for CPU tensors)."""
+    import torch.distributed as dist
+    world = len(bands)
+    out = {}
+    for k in keys:
+        t = local.get(k)
+        meta = [None] * world
+        dist.all_gather_object(meta, None if t is None else (tuple(t.shape[1:]), str(t.dtype).split(".")[-1]))
+        known = [m for m in meta if m is not None]
+        if not known:
+            continue
+        tail, dtype = known[0][0], getattr(torch, known[0][1])
+        if t is None:               # a rank with an empty band still takes part
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+            t = torch.empty((0,) + tuple(tail), dtype=dtype, device=dev)
+        # gather wants equal shapes: bands differ by at most one row, pad to the tallest
+        rows = max(b[1] - b[0] for b in bands)
+        send = t.contiguous()
+        if send.shape[0] < rows:
+            send = torch.cat([send, send.new_zeros((rows - send.shape[0],) + tuple(tail))], dim=0)
+        parts = None
+        if rank == dst:
+            parts = [torch.empty((rows,) + tuple(tail), dtype=dtype, device=t.device) for _ in bands]
+        dist.gather(send, parts, dst=dst)
+        if rank == dst:
+            out[k] = torch.cat([p_[:b[1] - b[0]] for p_, b in zip(parts, bands)], dim=0)
+    return out if rank == dst else None
