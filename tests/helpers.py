@@ -134,13 +134,28 @@ def compare_fp32(got, exp, tol=1e-4, eps=3e-6, max_exception_frac=0.03, noise_fl
     ok = err_e == 1
     assert np.array_equal(np.asarray(got["debug_Ncalls"])[ok], exp["debug_Ncalls"][ok]), f"{label}: Ncalls differ"
     stats = {"n_ok": int(ok.sum())}
-    for k in ("T", "df"):
-        if k in exp:
-            rel = np.abs(got[k][ok] - exp[k][ok]) / np.abs(exp[k][ok])
-            stats[k] = float(rel.max()) if rel.size else 0.
-            assert rel.size == 0 or rel.max() <= tol, f"{label}: {k} off by {rel.max():.3g}"
     dpos = exp["debug_d"][ok]
     cost_scale = float(np.median(dpos[dpos > 0])) if (dpos > 0).any() else 1.
+    # T and df belong to the INTEGER shift the walk settled on (reference's args_copy).  They may
+    # differ only at a documented tie: two neighbouring integer shifts whose costs agree to FP32
+    # noise (|d_n - d_centre| <= 1e-5 * cost scale in the reference's own 5x5 cache), where the
+    # reference's `> d + tol` comparisons (tol = 1e-8 absolute, Optim.cpp:294,325) are a coin flip.
+    ties = 0
+    for k in ("T", "df"):
+        if k in exp:
+            # relative for |value| >= 0.25 (T ~ 0.8, df ~ 0.5-1 on real data), absolute tol/4 below:
+            # on the noisy fixtures df = K/T passes through zero, where "relative" is meaningless
+            rel = np.abs(got[k] - exp[k]) / np.maximum(np.abs(exp[k]), .25)
+            for i, j in np.argwhere(ok & ~(rel <= tol)):
+                d5 = exp["debug_d"][i, j]
+                near = min(abs(d5[n] - d5[12]) for n in (7, 11, 13, 17) if d5[n] > -.5)
+                assert near <= 1e-5 * cost_scale, (
+                    f"{label}: {k} off by {rel[i, j]:.3g} at ({i},{j}) without a tie (nearest neighbour cost "
+                    f"differs by {near:.3g})")
+                ties += 1
+            stats[k] = float(np.max(rel[ok])) if ok.any() else 0.
+    stats["ties"] = ties
+    assert ties <= max(2, int(2e-3 * ok.sum())), f"{label}: {ties} integer-shift ties"
     bad = np.zeros(err_e.shape, dtype=bool)
     for k in ("dx", "dy"):
         rel = np.abs(got[k] - exp[k]) / np.maximum(1., np.abs(exp[k]))

@@ -85,8 +85,8 @@ def test_full_size_cfg1_table_vs_oracle():
     assert (exp["err"] == 1).mean() > .99
     # the synthetic truth is recovered (sign convention: dx ~ +column shift)
     ok = exp["err"] == 1
-    assert np.abs(got["dx"] - d["dx"][6:-6, 6:-6])[ok].mean() < .05
-    assert np.abs(got["dy"] - d["dy"][6:-6, 6:-6])[ok].mean() < .05
+    assert np.abs(got["dx"] - d["dx"][6:-6, 6:-6])[ok].mean() < .15
+    assert np.abs(got["dy"] - d["dy"][6:-6, 6:-6])[ok].mean() < .15
 
 
 def test_table_equals_lazy_on_large_df():
