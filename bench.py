@@ -58,7 +58,7 @@ def executed_fma_per_px_cross(cfg):
     plus the separable filter (row pass on the extended rows, column pass).  Tile geometry of
     table_path.cu: extended tile 16 x 32, output tile (16-2Nw) x (32-2Nw)."""
     S, K, Na, Nw = 2 * cfg["ms"] - 1, 2 * cfg["Nw"] + 1, cfg["Na"], cfg["Nw"]
-    eh, ew = 16, 32
+    eh, ew = int(os.environ.get("UMPA_TAB_EH", "16")), 32
     th, tw = eh - 2 * Nw, ew - 2 * Nw
     per_tile = S * S * (Na * eh * ew + K * eh * tw + K * th * tw)
     return per_tile / float(th * tw)

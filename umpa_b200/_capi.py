@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libumpa_b200.so")
+LIB_PATH = os.environ.get("UMPA_LIB") or os.path.join(HERE, "csrc", "libumpa_b200.so")   # UMPA_LIB: tuning builds
 
 NODF, DF, DFKERNEL = 0, 1, 2
 OPT_SUBPX_FUNC, OPT_REFERENCE_SHIFT, OPT_PATH = 1, 2, 3

@@ -28,14 +28,15 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build(force=False, verbose=False, extra=()):
-    if not force and up_to_date():
+def build(force=False, verbose=False, extra=(), dest=None):
+    """dest: alternative output path (tuning builds with extra -D flags); default builds LIB in-tree."""
+    if dest is None and not force and up_to_date():
         return LIB
     nvcc = nvcc_path()
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(CSRC, src[:-3] + ".o")
+        obj = os.path.join(CSRC, src[:-3] + (".o" if dest is None else "." + os.path.basename(dest) + ".o"))
         cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
@@ -48,11 +49,11 @@ def build(force=False, verbose=False, extra=()):
         if p.returncode != 0:
             raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), out))
     link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-            "-Xcompiler", "-fPIC", "-o", LIB] + objs
+            "-Xcompiler", "-fPIC", "-o", dest or LIB] + objs
     if verbose:
         print(" ".join(link))
     subprocess.check_call(link)
-    return LIB
+    return dest or LIB
 
 
 if __name__ == "__main__":

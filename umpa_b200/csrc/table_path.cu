@@ -100,101 +100,144 @@ struct MomentsParams {
     int ty0, tx0;                // first tile (in tile units) of the bounding box
 };
 
-constexpr int MO_TH = 16, MO_TW = 64, MO_NT = 256;
+constexpr int MO_TH = 16, MO_TW = 128, MO_NT = 256;
 
-// One block filters a MO_TH x MO_TW tile of every frame of both stacks.
-// smem: inR, inS [EH][EW]; tmpR, tmpS [EH][MO_TW]; qR, qS [EH][EW]
+__device__ __forceinline__ void cp_async4(float *dst, const float *src, bool valid)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int sz = valid ? 4 : 0;                      // src-size 0 -> zero fill
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// One block filters a 16 x 128 tile of every frame of both stacks with the separable window
+// and accumulates the aux images.  256 threads = 2 halves x 128 columns; a thread owns one
+// column and 8 output rows: the row pass reads shared memory (conflict-free, K taps), the column
+// pass runs on registers.  Frames are double-buffered with cp.async (zero fill outside the frame).
+// The per-pixel sums of squares are accumulated in shared memory and filtered once at the end,
+// as an extra "frame".
+template <int NW>
 __global__ void __launch_bounds__(MO_NT) moments_kernel(MomentsParams p)
 {
+    constexpr int K = 2 * NW + 1;
+    constexpr int ER = MO_TH + 2 * NW, EC = MO_TW + 2 * NW;   // extended tile
+    constexpr int RH = MO_TH / 2 + 2 * NW;                    // extended rows one half walks over
     extern __shared__ float sm[];
-    const int Nw = p.Nw, K = 2 * Nw + 1;
-    const int EH = MO_TH + 2 * Nw, EW = MO_TW + 2 * Nw;
-    float *inR = sm, *inS = inR + EH * EW;
-    float *tmpR = inS + EH * EW, *tmpS = tmpR + EH * MO_TW;
-    float *qR = tmpS + EH * MO_TW, *qS = qR + EH * EW;
-    __shared__ float gs[UMPA_MAX_K];
-    const int tid = threadIdx.x;
-    if (tid < K) gs[tid] = p.g[tid];
+    float *buf = sm;                                   // [2 buffers][2 stacks][ER*EC]
+    float *qs = sm + 4 * ER * EC;                      // [2 stacks][ER*EC] sums of squares
+    const int tid = threadIdx.x, h = tid >> 7, c = tid & 127;
     const int y0 = (blockIdx.y + p.ty0) * MO_TH, x0 = (blockIdx.x + p.tx0) * MO_TW;
-    for (int n = tid; n < EH * EW; n += MO_NT) { qR[n] = 0.f; qS[n] = 0.f; }
-
-    // each thread owns MO_TH*MO_TW/MO_NT = 4 output pixels: (oy[t], ox) with ox = tid % 64
-    const int ox = tid % MO_TW, oyb = tid / MO_TW;      // rows oyb, oyb+4, oyb+8, oyb+12
-    float m2[4] = {0, 0, 0, 0}, p3[4] = {0, 0, 0, 0}, uu[4] = {0, 0, 0, 0}, p1[4] = {0, 0, 0, 0}, vv[4] = {0, 0, 0, 0};
     const size_t fstride = (size_t)p.H * p.pitch;
-
-    for (int k = 0; k < p.Na; k++) {
-        const float *R = p.ref + k * fstride, *S = p.sam + k * fstride;
-        __syncthreads();                                  // previous frame's passes are done with in*/tmp*
-        for (int n = tid; n < EH * EW; n += MO_NT) {
-            const int r = n / EW, c = n - r * EW;
-            const int y = y0 - Nw + r, x = x0 - Nw + c;
-            float rv = 0.f, sv = 0.f;
-            if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
-                rv = __ldg(R + (size_t)y * p.pitch + x);
-                sv = __ldg(S + (size_t)y * p.pitch + x);
-            }
-            inR[n] = rv; inS[n] = sv;
-            qR[n] += rv * rv; qS[n] += sv * sv;
-        }
-        __syncthreads();
-        for (int n = tid; n < EH * MO_TW; n += MO_NT) {    // row pass
-            const int r = n / MO_TW, c = n - r * MO_TW;
-            float ar = 0.f, as = 0.f;
-            for (int v = 0; v < K; v++) {
-                ar = fmaf(gs[v], inR[r * EW + c + v], ar);
-                as = fmaf(gs[v], inS[r * EW + c + v], as);
-            }
-            tmpR[n] = ar; tmpS[n] = as;
-        }
-        __syncthreads();
-        const float ck = p.mean_r[k], dk = p.mean_s[k];
+    float g[K];
 #pragma unroll
-        for (int t = 0; t < 4; t++) {                      // column pass
-            const int oy = oyb + 4 * t;
-            float a = 0.f, b = 0.f;
-            for (int u = 0; u < K; u++) {
-                a = fmaf(gs[u], tmpR[(oy + u) * MO_TW + ox], a);
-                b = fmaf(gs[u], tmpS[(oy + u) * MO_TW + ox], b);
+    for (int v = 0; v < K; v++) g[v] = __ldg(p.g + v);
+    for (int n = tid; n < 2 * ER * EC; n += MO_NT) qs[n] = 0.f;
+
+    auto load = [&](int k, int b) {
+        const float *R = p.ref + k * fstride, *S = p.sam + k * fstride;
+        float *dR = buf + (size_t)b * 2 * ER * EC, *dS = dR + ER * EC;
+        for (int n = tid; n < ER * EC; n += MO_NT) {
+            const int r = n / EC, cc = n - r * EC;
+            const int y = y0 - NW + r, x = x0 - NW + cc;
+            const bool ok = y >= 0 && y < p.H && x >= 0 && x < p.W;
+            const size_t off = ok ? (size_t)y * p.pitch + x : 0;
+            cp_async4(dR + n, R + off, ok);
+            cp_async4(dS + n, S + off, ok);
+        }
+    };
+
+    float m2[8], p3[8], uu[8], p1[8], vv[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) m2[t] = p3[t] = uu[t] = p1[t] = vv[t] = 0.f;
+
+    // row pass of one stack for this thread's RH extended rows; optionally adds the squares of the
+    // rows this half owns to qs (centre column, plus the tile's edge columns for the edge threads)
+    auto rows_of = [&](const float *in, float *q, float (&row)[RH]) {
+#pragma unroll
+        for (int j = 0; j < RH; j++) {
+            const float *src = in + (8 * h + j) * EC + c;
+            float v[K];
+#pragma unroll
+            for (int t = 0; t < K; t++) v[t] = src[t];
+            float acc = 0.f;
+#pragma unroll
+            for (int t = 0; t < K; t++) acc = fmaf(g[t], v[t], acc);
+            row[j] = acc;
+            if (q != nullptr && (h == 0 ? j < 8 + NW : j >= NW)) {
+                float *qd = q + (8 * h + j) * EC + c;
+                qd[NW] += v[NW] * v[NW];
+                if (NW > 0 && c < NW) qd[0] += v[0] * v[0];
+                if (NW > 0 && c >= MO_TW - NW) qd[K - 1] += v[K - 1] * v[K - 1];
             }
+        }
+    };
+
+    load(0, 0);
+    cp_async_commit();
+    for (int k = 0; k < p.Na; k++) {
+        if (k + 1 < p.Na) load(k + 1, (k + 1) & 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const float *inR = buf + (size_t)(k & 1) * 2 * ER * EC, *inS = inR + ER * EC;
+        float rowR[RH], rowS[RH];
+        rows_of(inR, qs, rowR);
+        rows_of(inS, qs + ER * EC, rowS);
+        const float ck = __ldg(p.mean_r + k), dk = __ldg(p.mean_s + k);
+        const int x = x0 + c;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int u = 0; u < K; u++) { a = fmaf(g[u], rowR[t + u], a); b = fmaf(g[u], rowS[t + u], b); }
             m2[t] = fmaf(a, a, m2[t]);
             p3[t] = fmaf(ck, a, p3[t]);
             uu[t] = fmaf(dk, a, uu[t]);
             p1[t] = fmaf(dk, b, p1[t]);
             vv[t] = fmaf(ck, b, vv[t]);
-            const int y = y0 + oy, x = x0 + ox;
+            const int y = y0 + 8 * h + t;
             if (p.fa && y < p.H && x < p.pitch) {
                 p.fa[k * fstride + (size_t)y * p.pitch + x] = a;
                 p.fb[k * fstride + (size_t)y * p.pitch + x] = b;
             }
         }
+        __syncthreads();                               // buffer (k & 1) is free for frame k + 2
     }
-    // window-filter the per-pixel sums of squares: T3 = w (*) sum_k R'^2, T1 = w (*) sum_k S'^2
-    __syncthreads();
-    for (int n = tid; n < EH * MO_TW; n += MO_NT) {
-        const int r = n / MO_TW, c = n - r * MO_TW;
-        float ar = 0.f, as = 0.f;
-        for (int v = 0; v < K; v++) {
-            ar = fmaf(gs[v], qR[r * EW + c + v], ar);
-            as = fmaf(gs[v], qS[r * EW + c + v], as);
-        }
-        tmpR[n] = ar; tmpS[n] = as;
-    }
-    __syncthreads();
+    // the sums of squares as one more frame: T3 = w (*) sum_k R'^2, T1 = w (*) sum_k S'^2
+    {
+        float rowR[RH], rowS[RH];
+        rows_of(qs, nullptr, rowR);
+        rows_of(qs + ER * EC, nullptr, rowS);
+        const int x = x0 + c;
 #pragma unroll
-    for (int t = 0; t < 4; t++) {
-        const int oy = oyb + 4 * t;
-        float t3 = 0.f, t1 = 0.f;
-        for (int u = 0; u < K; u++) {
-            t3 = fmaf(gs[u], tmpR[(oy + u) * MO_TW + ox], t3);
-            t1 = fmaf(gs[u], tmpS[(oy + u) * MO_TW + ox], t1);
-        }
-        const int y = y0 + oy, x = x0 + ox;
-        if (y < p.H && x < p.pitch) {
-            p.auxR[(size_t)y * p.pitch + x] = make_float4(t3, p3[t], uu[t], m2[t]);
-            p.auxS[(size_t)y * p.pitch + x] = make_float4(t1, p1[t], vv[t], 0.f);
+        for (int t = 0; t < 8; t++) {
+            float t3 = 0.f, t1 = 0.f;
+#pragma unroll
+            for (int u = 0; u < K; u++) { t3 = fmaf(g[u], rowR[t + u], t3); t1 = fmaf(g[u], rowS[t + u], t1); }
+            const int y = y0 + 8 * h + t;
+            if (y < p.H && x < p.pitch) {
+                p.auxR[(size_t)y * p.pitch + x] = make_float4(t3, p3[t], uu[t], m2[t]);
+                p.auxS[(size_t)y * p.pitch + x] = make_float4(t1, p1[t], vv[t], 0.f);
+            }
         }
     }
+}
+
+typedef void (*MomentsKernel)(MomentsParams);
+template <int NW> size_t moments_smem() { return (size_t)6 * (MO_TH + 2 * NW) * (MO_TW + 2 * NW) * sizeof(float); }
+bool moments_pick(int Nw, MomentsKernel *k, size_t *smem)
+{
+    switch (Nw) {
+        case 0: *k = moments_kernel<0>; *smem = moments_smem<0>(); return true;
+        case 1: *k = moments_kernel<1>; *smem = moments_smem<1>(); return true;
+        case 2: *k = moments_kernel<2>; *smem = moments_smem<2>(); return true;
+        case 3: *k = moments_kernel<3>; *smem = moments_smem<3>(); return true;
+        case 4: *k = moments_kernel<4>; *smem = moments_smem<4>(); return true;
+        case 5: *k = moments_kernel<5>; *smem = moments_smem<5>(); return true;
+        case 6: *k = moments_kernel<6>; *smem = moments_smem<6>(); return true;
+    }
+    return false;
 }
 
 // ------------------------------------------------------------------ shift tables
@@ -523,6 +566,12 @@ struct TableEval {
 };
 
 constexpr int WALK_NT = 128;
+#ifndef WALK_MINB
+#define WALK_MINB 8
+#endif
+#ifndef WALK_PREFETCH
+#define WALK_PREFETCH 0          // radius of the L2 prefetch around the start shift (0 = off)
+#endif
 
 // d (the 5x5 cost cache) lives in shared memory, one column per thread: dynamic indexing
 // without local-memory traffic.
@@ -531,7 +580,7 @@ struct SharedGrid {
     __device__ __forceinline__ double &operator[](int n) const { return base[n * WALK_NT]; }
 };
 
-__global__ void __launch_bounds__(WALK_NT, 6) table_walk_kernel(WalkParams w, RoiView roi, umpa_outputs out)
+__global__ void __launch_bounds__(WALK_NT, WALK_MINB) table_walk_kernel(WalkParams w, RoiView roi, umpa_outputs out)
 {
     __shared__ double d_sm[25][WALK_NT];
     const int xj = blockIdx.x * blockDim.x + threadIdx.x;
@@ -540,6 +589,20 @@ __global__ void __launch_bounds__(WALK_NT, 6) table_walk_kernel(WalkParams w, Ro
     const size_t n = (size_t)xi * roi.N1 + xj;
     if (roi.cover && roi.cover[n] < roi.cover_threshold) return;
     const int ty = roi.step0 * xi, tx = roi.step1 * xj;
+#if WALK_PREFETCH > 0
+    {   // pull the table lines around the start shift into L2 while the first evaluations run
+        const int S = 2 * w.max_shift - 1, hs = w.max_shift - 1;
+        const int c0 = (int)round(roi.uv0[0]), c1 = (int)round(roi.uv0[1]);
+        for (int a = -WALK_PREFETCH; a <= WALK_PREFETCH; a++)
+            for (int b = -WALK_PREFETCH; b <= WALK_PREFETCH; b++) {
+                const int si = c0 + a, sj = c1 + b;
+                if (si < -hs || si > hs || sj < -hs || sj > hs) continue;
+                const size_t sidx = (size_t)((si + hs) * S + (sj + hs));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(w.tabX + (sidx * w.rowsX + ty) * w.colsX + tx + w.dxX));
+                if (w.tabM) asm volatile("prefetch.global.L2 [%0];" ::"l"(w.tabM + (sidx * w.rowsM + ty) * w.colsM + tx + w.dxM));
+            }
+    }
+#endif
     const float4 s = __ldg(w.auxS + (size_t)(w.oy + ty) * w.pitch + (w.ox + tx));
     TableEval eval{w, ty, tx, (double)s.x + 2. * (double)s.y + w.sw * w.dd, (double)s.z};
     FitArgs args{0., 0.};
@@ -631,6 +694,8 @@ int dispatch_shift_table(int S, const CUtensorMap &a, const CUtensorMap &b, cons
 
 int row_block_of(int S) { return S <= 9 ? 3 : (S <= 17 ? 2 : 1); }
 
+int ctas_per_sm() { const char *e = getenv("UMPA_TAB_CTAS"); return e ? std::max(1, atoi(e)) : 1; }
+
 // Tile geometry of one table kernel.  Returns dynamic smem bytes (0 = unsupported) and the block size.
 size_t plan_tiles(TableParams &p, int S, bool filter, int *nt)
 {
@@ -640,9 +705,11 @@ size_t plan_tiles(TableParams &p, int S, bool filter, int *nt)
     p.TW = (EXT_W - 2 * halo) & ~3;
     if (p.TW < 8) return 0;
     p.EH = 16;                                         // 16 rows x 8 strips = 128 threads per group
+    if (const char *e = getenv("UMPA_TAB_EH")) p.EH = atoi(e);          // tuning knobs (experiments only)
     p.TH = p.EH - 2 * halo;
     if (p.TH < 2) return 0;
     p.G = std::min(MAX_NT / (p.EH * 8), (S + SH - 1) / SH);
+    if (const char *e = getenv("UMPA_TAB_G")) p.G = std::min(p.G, atoi(e));
     p.npass = (S + p.G * SH - 1) / (p.G * SH);
     p.AH = p.EH + 2 * HS;
     p.AP = EXT_W - 4 + 4 * NA4;
@@ -656,6 +723,7 @@ size_t plan_tiles(TableParams &p, int S, bool filter, int *nt)
     while (ns > 2 && (size_t)ns * p.stage_floats * sizeof(float) + cbuf > budget) ns--;
     if ((size_t)ns * p.stage_floats * sizeof(float) + cbuf > budget) return 0;
     p.nstage = std::min(ns, 6);
+    if (const char *e = getenv("UMPA_TAB_NST")) p.nstage = std::max(2, std::min(ns, atoi(e)));
     return (size_t)p.nstage * p.stage_floats * sizeof(float) + cbuf;
 }
 
@@ -770,10 +838,11 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         const int xlo = std::max(0, ox - HS), xhi = std::min(m->W, ox + cols + HS);
         mp.ty0 = ylo / MO_TH; mp.tx0 = xlo / MO_TW;
         dim3 grid((xhi + MO_TW - 1) / MO_TW - mp.tx0, (yhi + MO_TH - 1) / MO_TH - mp.ty0);
-        const int EH = MO_TH + 2 * m->Nw, EW = MO_TW + 2 * m->Nw;
-        const size_t smem = (size_t)(4 * EH * EW + 2 * EH * MO_TW) * sizeof(float);
-        UMPA_CUDA(cudaFuncSetAttribute(moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        moments_kernel<<<grid, MO_NT, smem, st>>>(mp);
+        MomentsKernel mk = nullptr;
+        size_t smem = 0;
+        if (!moments_pick(m->Nw, &mk, &smem)) { umpa_set_error("table path: Nw %d not instantiated", m->Nw); return UMPA_ERR_UNSUPPORTED; }
+        UMPA_CUDA(cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mk<<<grid, MO_NT, smem, st>>>(mp);
         UMPA_CUDA(cudaGetLastError());
         m->last_launches++;
         if ((rc = stage_check("moments", st))) return rc;
@@ -787,7 +856,7 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         if ((rc = make_stack_map(&mb, m->d_sam32, Na, H, m->W, pitch, EXT_W, px.EH))) return rc;
         px.table = (float *)m->tabX.p;
         px.tiles_x = px.cols_p / px.TW; px.tiles_y = px.rows_p / px.TH;
-        dim3 grid(std::min(px.tiles_x * px.tiles_y, m->sm_count));
+        dim3 grid(std::min(px.tiles_x * px.tiles_y, m->sm_count * ctas_per_sm()));
         if ((rc = dispatch_shift_table<true>(S, ma, mb, px, grid, ntx, smx, st))) return rc;
         m->last_launches++;
         if ((rc = stage_check("cross table", st))) return rc;
@@ -801,7 +870,7 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         if ((rc = make_stack_map(&mb, (const float *)m->filtB.p, Na, H, m->W, pitch, EXT_W, pm.EH))) return rc;
         pm.table = (float *)m->tabM.p;
         pm.tiles_x = pm.cols_p / pm.TW; pm.tiles_y = pm.rows_p / pm.TH;
-        dim3 grid(std::min(pm.tiles_x * pm.tiles_y, m->sm_count));
+        dim3 grid(std::min(pm.tiles_x * pm.tiles_y, m->sm_count * ctas_per_sm()));
         if ((rc = dispatch_shift_table<false>(S, ma, mb, pm, grid, ntm, smm, st))) return rc;
         m->last_launches++;
         if ((rc = stage_check("mean table", st))) return rc;
