@@ -28,10 +28,13 @@ if R is None:
 
 CLS = {"NoDF": R.UMPAModelNoDF, "DF": R.UMPAModelDF, "DFKernel": R.UMPAModelDFKernel}
 KEYS = ("f", "T", "dx", "dy", "df", "err", "debug_Ncalls", "debug_d", "debug_a")
+ONLY = set(sys.argv[1:])            # optional: regenerate just the named cases
 
 
 def run_case(name, kind, sam, ref, mask=None, pos=None, Nw=2, max_shift=4, abc=None,
              assign=None, subpx=None, step=None, ROI=None, dxdy=None):
+    if ONLY and name not in ONLY:
+        return
     sam_l = [np.ascontiguousarray(s) for s in sam]
     ref_l = [np.ascontiguousarray(r) for r in ref]
     mask_l = None if mask is None else [np.ascontiguousarray(m) for m in mask]
@@ -108,6 +111,18 @@ def main():
     run_case("nodf_nw1", "NoDF", clean["sam"], clean["ref"], Nw=1, max_shift=3)
     run_case("dfk_clean", "DFKernel", big["sam"], big["ref"], Nw=2, max_shift=3)
 
+    # DFKernel at the shape class of BASELINE config 3 (Nw=3, max_shift=5), a strided ROI, and a wide
+    # blur whose 17x17 truncation matters (a, c ~ 0.03-0.08)
+    kbig = synth.speckle_stack(6, 72, 76, seed=17, max_shift=5, dark_field=True)
+    run_case("dfk_nw3_ms5", "DFKernel", kbig["sam"], kbig["ref"], Nw=3, max_shift=5)
+    run_case("dfk_roi_step", "DFKernel", kbig["sam"], kbig["ref"], Nw=2, max_shift=4,
+             ROI=((1, 40, 2), (3, 44, 3)), abc=synth.blur_abc(20, 14))
+    wide_abc = synth.blur_abc(44, 48)
+    wide_abc[..., 0] *= .12
+    wide_abc[..., 2] *= .08
+    wide_abc[..., 1] *= .2
+    run_case("dfk_wide_blur", "DFKernel", kbig["sam"], kbig["ref"], Nw=1, max_shift=5, abc=wide_abc)
+
     # masks: smooth positive weights with a dead block and a few dead pixels
     rng = np.random.default_rng(5)
     mask = .5 + .5 * rng.random(clean_df["sam"].shape)
@@ -134,6 +149,8 @@ def main():
     run_case("df_roi", "DF", clean_df["sam"], clean_df["ref"], ROI=((2, 20, 2), (1, 25, 3)))
     run_case("df_dxdy", "DF", clean_df["sam"], clean_df["ref"], dxdy=(1., -1.))
 
+    if ONLY and "hooks" not in ONLY:
+        return
     # module-level hooks (model.pyx:31-114; note spm -> spmin_quad, spmq -> spmin)
     blocks = []
     for n in range(8):

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libumpa_b200.so")
-SOURCES = ["capi.cu", "lazy_path.cu", "table_path.cu"]
+SOURCES = ["capi.cu", "lazy_path.cu", "table_path.cu", "kernel_path.cu"]
 HEADERS = ["common.cuh", "walk.cuh", os.path.join("..", "..", "include", "umpa_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden", "-cudart", "static"]

@@ -115,3 +115,8 @@ int coverage_map(umpa_model *m, const RoiView &roi, double *out_dev, cudaStream_
 int table_prepare_frames(umpa_model *m, cudaStream_t st);      // FP64 stacks -> centred FP32 stacks
 bool table_eligible(const umpa_model *m, const RoiView &roi, std::string *why);
 int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st);
+
+// implemented in kernel_path.cu: per-pixel FP32 tables of UMPAModelDFKernel (blur fused into the window pass)
+bool ktable_supported(int Nw, int max_shift, int step0);
+int ktable_row_floats(int max_shift);                          // floats per pixel row: t5c[S^2], t3c[S^2], sigma-1
+int ktable_build(umpa_model *m, const RoiView &roi, float *tab, cudaStream_t st);

@@ -525,12 +525,16 @@ struct WalkParams {
     double sw, cd, cc, dd;          // sum of window; sum_k c_k d_k, c_k^2, d_k^2
     double inv_sw, inv_sw2, inv_Na;
     const double *quad;
+    const float *ktab;              // DFKernel: pixel-major rows [t5c(S^2) | t3c(S^2) | sigma-1] (kernel_path.cu)
+    int kstride;                    // floats per row
+    double swk;                     // exact sum of the FP32 2-D window kernel_path.cu applies
 };
 
 struct TableEval {
     const WalkParams &w;
     int ty, tx;                     // table coords of this pixel
     double t1, V;                   // pixel-only terms
+    const float *krow;              // DFKernel: this pixel's table row
 
     __device__ int operator()(int si, int sj, double &cost, FitArgs &args) const
     {
@@ -540,6 +544,16 @@ struct TableEval {
         if (sj >= ms) return UMPA_ST_BOUND | UMPA_ST_DIM | UMPA_ST_POS;
         const int S = 2 * ms - 1;
         const size_t sidx = (size_t)((si + ms - 1) * S + (sj + ms - 1));
+        if (w.kind == UMPA_DFKERNEL) {
+            // t3 = sum w B^2, t5 = sum w B S with B = k_p (*) R (Model.cpp:1076-1099), rebuilt from the
+            // centred FP32 sums: B = B' + sigma c_k
+            const double sig = 1. + (double)__ldg(krow + 2 * S * S);
+            const double t5 = (double)__ldg(krow + sidx) + sig * (V + w.swk * w.cd);
+            const double t3 = (double)__ldg(krow + S * S + sidx) + sig * sig * w.swk * w.cc;
+            args.t = t5 / t3;
+            cost = (t1 - t5 * args.t) * w.inv_Na;
+            return UMPA_ST_OK;
+        }
         const float4 r = __ldg(w.auxR + (size_t)(w.oy + ty + si) * w.pitch + (w.ox + tx + sj));
         const float xv = __ldg(w.tabX + (sidx * w.rowsX + ty) * w.colsX + tx + w.dxX);
         const double T3 = r.x, P3 = r.y, U = r.z, M2 = r.w;
@@ -604,7 +618,8 @@ __global__ void __launch_bounds__(WALK_NT, WALK_MINB) table_walk_kernel(WalkPara
     }
 #endif
     const float4 s = __ldg(w.auxS + (size_t)(w.oy + ty) * w.pitch + (w.ox + tx));
-    TableEval eval{w, ty, tx, (double)s.x + 2. * (double)s.y + w.sw * w.dd, (double)s.z};
+    TableEval eval{w, ty, tx, (double)s.x + 2. * (double)s.y + w.sw * w.dd, (double)s.z,
+                   w.ktab ? w.ktab + n * (size_t)w.kstride : nullptr};
     FitArgs args{0., 0.};
     SharedGrid d{&d_sm[0][threadIdx.x]};
     double a[16], uv[2] = {roi.uv0[0], roi.uv0[1]}, f = 0.;
@@ -732,7 +747,7 @@ size_t plan_tiles(TableParams &p, int S, bool filter, int *nt)
 // FP64 device stacks -> per-frame means + centred FP32 stacks (pitch multiple of 4 floats)
 int table_prepare_frames(umpa_model *m, cudaStream_t st)
 {
-    if (!m->uniform || m->masked || m->kind == UMPA_DFKERNEL) return UMPA_OK;
+    if (!m->uniform || m->masked) return UMPA_OK;
     const int Na = m->Na, H = m->H, W = m->W;
     m->pitch = 4 * ((W + 3) / 4);
     const size_t n32 = (size_t)Na * H * m->pitch;
@@ -764,11 +779,15 @@ int table_prepare_frames(umpa_model *m, cudaStream_t st)
 bool table_eligible(const umpa_model *m, const RoiView &roi, std::string *why)
 {
     auto no = [&](const char *s) { if (why) *why = s; return false; };
-    if (m->kind == UMPA_DFKERNEL) return no("DFKernel model");
     if (!m->uniform) return no("ragged frames or non-zero positions");
     if (m->masked) return no("masks");
     if (!m->separable) return no("window is not separable");
     if (m->refshift) return no("reference_shift=1");
+    if (m->kind == UMPA_DFKERNEL) {
+        if (!ktable_supported(m->Nw, m->max_shift, roi.step0)) return no("DFKernel: (Nw, max_shift, step) outside the instantiated blur-table kernels");
+        if (!m->d_sam32) return no("FP32 stacks not prepared");
+        return true;
+    }
     if (m->max_shift < 2 || m->max_shift > 10) return no("max_shift outside 2..10");
     if (m->Nw > 6) return no("window too large for the tiled kernel (Nw > 6)");
     if (roi.step0 * roi.step1 > 16) return no("sparse ROI (step product > 16)");
@@ -796,6 +815,7 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
     const int oy = roi.off0, ox = roi.off1;
     const int rows = (roi.N0 - 1) * roi.step0 + 1, cols = (roi.N1 - 1) * roi.step1 + 1;
 
+    const bool dfk = m->kind == UMPA_DFKERNEL;
     TableParams px{};
     px.Na = Na; px.Nw = m->Nw; px.oy = oy; px.g = m->d_g;
     TableParams pm = px;
@@ -803,16 +823,22 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
     const int dxX = (ox - m->Nw) & 3, dxM = ox & 3;
     px.ox = ox - dxX; pm.ox = ox - dxM;
     int ntx = 0, ntm = 0;
-    const size_t smx = plan_tiles(px, S, true, &ntx);
-    const size_t smm = df ? plan_tiles(pm, S, false, &ntm) : 1;
-    if (!smx || !smm) { umpa_set_error("table path: tile does not fit shared memory"); return UMPA_ERR_UNSUPPORTED; }
-    auto padded = [](int n, int t) { return t * ((n + t - 1) / t); };
-    px.rows_p = padded(rows, px.TH); px.cols_p = padded(cols + dxX, px.TW);
+    size_t smx = 0, smm = 0;
     int rc;
-    if ((rc = scratch_reserve(m, m->tabX, (size_t)S * S * px.rows_p * px.cols_p * sizeof(float)))) return rc;
-    if (df) {
-        pm.rows_p = padded(rows, pm.TH); pm.cols_p = padded(cols + dxM, pm.TW);
-        if ((rc = scratch_reserve(m, m->tabM, (size_t)S * S * pm.rows_p * pm.cols_p * sizeof(float)))) return rc;
+    if (dfk) {
+        if (!roi.abc) { umpa_set_error("abc array has to be provided"); return UMPA_ERR_ARG; }
+        if ((rc = scratch_reserve(m, m->tabX, (size_t)roi.N0 * roi.N1 * ktable_row_floats(m->max_shift) * sizeof(float)))) return rc;
+    } else {
+        smx = plan_tiles(px, S, true, &ntx);
+        smm = df ? plan_tiles(pm, S, false, &ntm) : 1;
+        if (!smx || !smm) { umpa_set_error("table path: tile does not fit shared memory"); return UMPA_ERR_UNSUPPORTED; }
+        auto padded = [](int n, int t) { return t * ((n + t - 1) / t); };
+        px.rows_p = padded(rows, px.TH); px.cols_p = padded(cols + dxX, px.TW);
+        if ((rc = scratch_reserve(m, m->tabX, (size_t)S * S * px.rows_p * px.cols_p * sizeof(float)))) return rc;
+        if (df) {
+            pm.rows_p = padded(rows, pm.TH); pm.cols_p = padded(cols + dxM, pm.TW);
+            if ((rc = scratch_reserve(m, m->tabM, (size_t)S * S * pm.rows_p * pm.cols_p * sizeof(float)))) return rc;
+        }
     }
     const size_t img = (size_t)H * pitch;
     if ((rc = scratch_reserve(m, m->auxS, img * sizeof(float4)))) return rc;
@@ -849,8 +875,13 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
     }
     if (m->profiling) UMPA_CUDA(cudaEventRecord(m->ev[1], st));
 
+    // 2. DFKernel: per-pixel blur tables (kernel_path.cu)
+    if (dfk) {
+        if ((rc = ktable_build(m, roi, (float *)m->tabX.p, st))) return rc;
+        if ((rc = stage_check("blur table", st))) return rc;
+    }
     // 2. cross table: A = centred reference (read at p+s), B = centred sample, window-filtered
-    {
+    else {
         CUtensorMap ma, mb;
         if ((rc = make_stack_map(&ma, m->d_ref32, Na, H, m->W, pitch, px.AP, px.AH))) return rc;
         if ((rc = make_stack_map(&mb, m->d_sam32, Na, H, m->W, pitch, EXT_W, px.EH))) return rc;
@@ -881,6 +912,13 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
     {
         WalkParams w{};
         w.tabX = (const float *)m->tabX.p; w.tabM = df ? (const float *)m->tabM.p : nullptr;
+        if (dfk) {
+            w.ktab = w.tabX; w.kstride = ktable_row_floats(m->max_shift);
+            double swk = 0.;                           // exact sum of float(g_a) * float(g_b) as FP32 products
+            for (int a = 0; a < m->K; a++)
+                for (int b = 0; b < m->K; b++) swk += (double)((float)m->g[a] * (float)m->g[b]);
+            w.swk = swk;
+        }
         w.auxS = (const float4 *)m->auxS.p; w.auxR = (const float4 *)m->auxR.p;
         w.pitch = pitch; w.rowsX = px.rows_p; w.colsX = px.cols_p; w.rowsM = pm.rows_p; w.colsM = pm.cols_p;
         w.oy = oy; w.ox = ox; w.dxX = dxX; w.dxM = dxM;
