@@ -132,10 +132,23 @@ def compare_fp32(got, exp, tol=1e-4, eps=3e-6, max_exception_frac=0.03, noise_fl
     err_g, err_e = np.asarray(got["err"]), np.asarray(exp["err"])
     assert np.array_equal(err_g, err_e), f"{label}: err map differs in {(err_g != err_e).sum()} pixels"
     ok = err_e == 1
-    assert np.array_equal(np.asarray(got["debug_Ncalls"])[ok], exp["debug_Ncalls"][ok]), f"{label}: Ncalls differ"
     stats = {"n_ok": int(ok.sum())}
     dpos = exp["debug_d"][ok]
     cost_scale = float(np.median(dpos[dpos > 0])) if (dpos > 0).any() else 1.
+    # the integer walk (Ncalls) must be equal, except at a documented tie (see below): there the walk
+    # may settle on the neighbouring shift, and the sub-pixel fit then starts from another 4x4 block
+    walk_ties = 0
+    for i, j in np.argwhere(ok & (np.asarray(got["debug_Ncalls"]) != exp["debug_Ncalls"])):
+        d5 = exp["debug_d"][i, j]
+        near = min(abs(d5[n] - d5[12]) for n in (7, 11, 13, 17) if d5[n] > -.5)
+        assert near <= 1e-5 * cost_scale, (
+            f"{label}: Ncalls {got['debug_Ncalls'][i, j]} vs {exp['debug_Ncalls'][i, j]} at ({i},{j}) without a tie "
+            f"(nearest neighbour cost differs by {near:.3g})")
+        walk_ties += 1
+        ok = ok.copy()
+        ok[i, j] = False
+    stats["walk_ties"] = walk_ties
+    assert walk_ties <= max(2, int(2e-3 * ok.sum())), f"{label}: {walk_ties} walk ties"
     # T and df belong to the INTEGER shift the walk settled on (reference's args_copy).  They may
     # differ only at a documented tie: two neighbouring integer shifts whose costs agree to FP32
     # noise (|d_n - d_centre| <= 1e-5 * cost scale in the reference's own 5x5 cache), where the

@@ -219,8 +219,12 @@ void free_frames(umpa_model *m)
     pool_free(m->d_sam64, b64); pool_free(m->d_ref64, b64); pool_free(m->d_mask64, b64);
     pool_free(m->d_sam32, b32); pool_free(m->d_ref32, b32);
     for (void *p : {(void *)m->d_sam_ptrs, (void *)m->d_ref_ptrs, (void *)m->d_mask_ptrs,
-                    (void *)m->d_mean_s, (void *)m->d_mean_r, (void *)m->d_means64, (void *)m->d_partials})
+                    (void *)m->d_mean_s, (void *)m->d_mean_r, (void *)m->d_means64, (void *)m->d_partials,
+                    (void *)m->d_consts})
         if (p) cudaFree(p);
+    m->d_consts = nullptr;
+    m->h_sam.clear(); m->h_ref.clear(); m->h_mask.clear();
+    m->host_pending = false;
     m->d_sam64 = m->d_ref64 = m->d_mask64 = nullptr;
     m->d_sam_ptrs = m->d_ref_ptrs = m->d_mask_ptrs = nullptr;
     m->d_sam32 = m->d_ref32 = nullptr;
@@ -240,6 +244,223 @@ int zero_outputs(const umpa_outputs &o, size_t n, cudaStream_t st)
     if (o.ncalls) UMPA_CUDA(cudaMemsetAsync(o.ncalls, 0, n * sizeof(int32_t), st));
     if (o.debug_d) UMPA_CUDA(cudaMemsetAsync(o.debug_d, 0, 25 * n * sizeof(double), st));
     if (o.debug_a) UMPA_CUDA(cudaMemsetAsync(o.debug_a, 0, 16 * n * sizeof(double), st));
+    return UMPA_OK;
+}
+
+// Deferred host frames (umpa_set_frames on_device = 2): copy everything now, on `st`.
+int ensure_resident(umpa_model *m, cudaStream_t st)
+{
+    if (!m->host_pending) return UMPA_OK;
+    const std::vector<const double *> *srcs[3] = {&m->h_sam, &m->h_ref, &m->h_mask};
+    double *dsts[3] = {m->d_sam64, m->d_ref64, m->d_mask64};
+    for (int a = 0; a < 3; a++)
+        for (int k = 0; k < (int)srcs[a]->size(); k++) {
+            const size_t n = (size_t)m->dim[2 * k] * m->dim[2 * k + 1];
+            UMPA_CUDA(cudaMemcpyAsync(dsts[a] + m->frame_off[k], (*srcs[a])[k], n * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+    int rc = table_prepare_frames(m, st);
+    if (rc) return rc;
+    UMPA_CUDA(cudaStreamSynchronize(st));
+    m->host_pending = false;
+    return UMPA_OK;
+}
+
+int ensure_streams(umpa_model *m)
+{
+    if (m->s_comp) return UMPA_OK;
+    UMPA_CUDA(cudaStreamCreateWithFlags(&m->s_copy, cudaStreamNonBlocking));
+    UMPA_CUDA(cudaStreamCreateWithFlags(&m->s_comp, cudaStreamNonBlocking));
+    UMPA_CUDA(cudaStreamCreateWithFlags(&m->s_out, cudaStreamNonBlocking));
+    return UMPA_OK;
+}
+
+// path selection + launch for one (sub-)ROI; everything is resident (or being streamed in by the caller)
+int match_view(umpa_model *m, const RoiView &v, const umpa_outputs &out, cudaStream_t st)
+{
+    const size_t n = (size_t)v.N0 * v.N1;
+    int rc;
+    if (v.cover) { if ((rc = zero_outputs(out, n, st))) return rc; }
+    else if (out.df && m->kind != UMPA_DF) UMPA_CUDA(cudaMemsetAsync(out.df, 0, n * sizeof(double), st));
+    std::string why;
+    bool use_table = false;
+    if (m->path_opt != UMPA_PATH_LAZY) {
+        use_table = table_eligible(m, v, &why);
+        if (!use_table && m->path_opt == UMPA_PATH_TABLE) {
+            umpa_set_error("table path requested but not eligible: %s", why.c_str());
+            return UMPA_ERR_UNSUPPORTED;
+        }
+    }
+    if (use_table) { m->last_path = UMPA_PATH_TABLE; return table_match(m, v, out, st); }
+    m->last_path = UMPA_PATH_LAZY;
+    return lazy_match(m, v, out, st);
+}
+
+umpa_outputs offset_outputs(const umpa_outputs &o, size_t px)
+{
+    umpa_outputs r = o;
+    if (r.f) r.f += px;
+    if (r.T) r.T += px;
+    if (r.dx) r.dx += px;
+    if (r.dy) r.dy += px;
+    if (r.df) r.df += px;
+    if (r.err) r.err += px;
+    if (r.ncalls) r.ncalls += px;
+    if (r.debug_d) r.debug_d += 25 * px;
+    if (r.debug_a) r.debug_a += 16 * px;
+    return r;
+}
+
+// device -> host copies of `n` pixels of every requested map, asynchronous on `st`
+int download_outputs(const umpa_outputs &host, const umpa_outputs &dev, size_t n, cudaStream_t st)
+{
+    auto back = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
+        return (dst && src) ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) : cudaSuccess;
+    };
+    UMPA_CUDA(back(host.f, dev.f, n * sizeof(double)));
+    UMPA_CUDA(back(host.T, dev.T, n * sizeof(double)));
+    UMPA_CUDA(back(host.dx, dev.dx, n * sizeof(double)));
+    UMPA_CUDA(back(host.dy, dev.dy, n * sizeof(double)));
+    UMPA_CUDA(back(host.df, dev.df, n * sizeof(double)));
+    UMPA_CUDA(back(host.err, dev.err, n * sizeof(int32_t)));
+    UMPA_CUDA(back(host.ncalls, dev.ncalls, n * sizeof(int32_t)));
+    UMPA_CUDA(back(host.debug_d, dev.debug_d, 25 * n * sizeof(double)));
+    UMPA_CUDA(back(host.debug_a, dev.debug_a, 16 * n * sizeof(double)));
+    return UMPA_OK;
+}
+
+// The pipelined host-to-host match: frames still in host memory are uploaded in row bands on a
+// copy stream while the kernels of the previous band run and the maps of the band before that go
+// back to the host.  Band b needs input rows below off0 + step0*(r1-1) + padding only, so its
+// kernels start as soon as those rows (and the sampled rows that define the centring constants)
+// have landed.  Pixels are independent: the result is the one the unpipelined path gives.
+int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, const umpa_outputs &host)
+{
+    const int Na = m->Na, H = m->H, W = m->W;
+    // bands: equal slices of the output rows, the last one halved twice so that little work is left
+    // when the final rows arrive (the upload is the critical path; kernels and download hide behind it)
+    std::vector<int> edge;                      // band b = output rows [edge[b], edge[b+1])
+    {
+        int nu = std::max(1, std::min(12, v.N0 / 256));
+        if (const char *e = getenv("UMPA_BANDS")) nu = std::max(1, std::min(v.N0, atoi(e)));
+        const int rows_per = (v.N0 + nu - 1) / nu;
+        for (int r = 0; r < v.N0; r += rows_per) edge.push_back(r);
+        edge.push_back(v.N0);
+        for (int split = 0; split < 2 && nu > 1; split++) {
+            const int lo = edge[edge.size() - 2], hi = edge.back();
+            if (hi - lo < 64) break;
+            edge.insert(edge.end() - 1, lo + (hi - lo + 1) / 2);
+        }
+    }
+    const int nb = (int)edge.size() - 1;
+    // frames that are equally spaced slices of one host stack go up with one 2-D copy per stack and band
+    auto spacing = [&](const std::vector<const double *> &h) -> ptrdiff_t {
+        if (Na < 2) return (ptrdiff_t)H * W;
+        const ptrdiff_t d = h[1] - h[0];
+        if (d < (ptrdiff_t)H * W) return 0;
+        for (int k = 2; k < Na; k++) if (h[k] - h[k - 1] != d) return 0;
+        return d;
+    };
+    const ptrdiff_t gap_s = spacing(m->h_sam), gap_r = spacing(m->h_ref);
+    std::vector<cudaEvent_t> ev(2 * nb + 1, nullptr);
+    int rc = UMPA_OK;
+    auto fail = [&](int code) {
+        cudaStreamSynchronize(m->s_copy); cudaStreamSynchronize(m->s_comp); cudaStreamSynchronize(m->s_out);
+        for (auto e : ev) if (e) cudaEventDestroy(e);
+        return code;
+    };
+#define ST_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+        umpa_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return fail(UMPA_ERR_CUDA); } } while (0)
+    const bool trace = getenv("UMPA_STREAM_TRACE") != nullptr;     // timeline of the three streams on stderr
+    for (auto &e : ev) ST_CUDA(cudaEventCreateWithFlags(&e, trace ? cudaEventDefault : cudaEventDisableTiming));
+    std::vector<cudaEvent_t> tev;                // trace only: [start, sampled rows, then per band: copy, comp, out]
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tev.push_back(e);
+    };
+    if (trace) { cudaStreamSynchronize(m->s_copy); cudaStreamSynchronize(m->s_comp); }
+    mark(m->s_copy);
+
+    // 0. the sampled rows first: they define the centring constants
+    const int rs = table_row_step(H), nrs = (H + rs - 1) / rs;
+    const size_t rowb = (size_t)W * sizeof(double);
+    if (nb > 1)                                 // (one band: everything is up before the constants are taken)
+        for (int k = 0; k < Na; k++) {
+            ST_CUDA(cudaMemcpy2DAsync(m->d_sam64 + m->frame_off[k], rs * rowb, m->h_sam[k], rs * rowb, rowb, nrs,
+                                      cudaMemcpyHostToDevice, m->s_copy));
+            ST_CUDA(cudaMemcpy2DAsync(m->d_ref64 + m->frame_off[k], rs * rowb, m->h_ref[k], rs * rowb, rowb, nrs,
+                                      cudaMemcpyHostToDevice, m->s_copy));
+        }
+    // rows [y0, y1) of every frame of one stack
+    auto upload_rows = [&](double *dst, const std::vector<const double *> &h, ptrdiff_t gap, int y0, int y1) -> cudaError_t {
+        const size_t bytes = (size_t)(y1 - y0) * rowb;
+        if (gap > 0)
+            return cudaMemcpy2DAsync(dst + (size_t)y0 * W, (size_t)H * rowb, h[0] + (size_t)y0 * W, (size_t)gap * sizeof(double),
+                                     bytes, Na, cudaMemcpyHostToDevice, m->s_copy);
+        for (int k = 0; k < Na; k++) {
+            cudaError_t e = cudaMemcpyAsync(dst + m->frame_off[k] + (size_t)y0 * W, h[k] + (size_t)y0 * W, bytes,
+                                            cudaMemcpyHostToDevice, m->s_copy);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
+    mark(m->s_copy);
+    int up_hi = 0;                              // rows [0, up_hi) are uploaded and centred
+    bool have_means = false;
+    int launches = 0;
+    for (int b = 0; b < nb; b++) {
+        const int r0 = edge[b], r1 = edge[b + 1];
+        const int need_hi = b == nb - 1 ? H : std::min(H, v.off0 + v.step0 * (r1 - 1) + m->padding + 1);
+        if (need_hi > up_hi) {
+            ST_CUDA(upload_rows(m->d_sam64, m->h_sam, gap_s, up_hi, need_hi));
+            ST_CUDA(upload_rows(m->d_ref64, m->h_ref, gap_r, up_hi, need_hi));
+        }
+        ST_CUDA(cudaEventRecord(ev[2 * b], m->s_copy));
+        mark(m->s_copy);
+        ST_CUDA(cudaStreamWaitEvent(m->s_comp, ev[2 * b], 0));
+        if (!have_means) {
+            if ((rc = table_means(m, m->s_comp))) return fail(rc);
+            have_means = true;
+        }
+        if ((rc = table_center_rows(m, up_hi, std::max(up_hi, need_hi), m->s_comp))) return fail(rc);
+        up_hi = std::max(up_hi, need_hi);
+        RoiView vb = v;
+        vb.off0 = v.off0 + v.step0 * r0; vb.N0 = r1 - r0;
+        const size_t px0 = (size_t)r0 * v.N1;
+        if (v.abc) vb.abc = v.abc + 3 * px0;
+        if (v.cover) vb.cover = v.cover + px0;
+        const umpa_outputs db = offset_outputs(dev, px0);
+        m->last_launches = 0;
+        if ((rc = match_view(m, vb, db, m->s_comp))) return fail(rc);
+        launches += m->last_launches;
+        ST_CUDA(cudaEventRecord(ev[2 * b + 1], m->s_comp));
+        mark(m->s_comp);
+        ST_CUDA(cudaStreamWaitEvent(m->s_out, ev[2 * b + 1], 0));
+        if ((rc = download_outputs(offset_outputs(host, px0), db, (size_t)(r1 - r0) * v.N1, m->s_out))) return fail(rc);
+        mark(m->s_out);
+    }
+    m->last_launches = launches;
+    ST_CUDA(cudaStreamSynchronize(m->s_out));
+    ST_CUDA(cudaStreamSynchronize(m->s_comp));
+    ST_CUDA(cudaStreamSynchronize(m->s_copy));
+#undef ST_CUDA
+    if (trace) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, tev[0], tev[1]);
+        fprintf(stderr, "[umpa stream] %d bands; sampled rows up at %.2f ms\n", nb, t);
+        for (int b = 0; b < nb; b++) {
+            float tc = 0.f, tk = 0.f, to = 0.f;
+            cudaEventElapsedTime(&tc, tev[0], tev[2 + 3 * b]);
+            cudaEventElapsedTime(&tk, tev[0], tev[3 + 3 * b]);
+            cudaEventElapsedTime(&to, tev[0], tev[4 + 3 * b]);
+            fprintf(stderr, "[umpa stream] band %2d: uploaded %.2f  computed %.2f  downloaded %.2f ms\n", b, tc, tk, to);
+        }
+        for (auto e : tev) cudaEventDestroy(e);
+    }
+    for (auto e : ev) if (e) cudaEventDestroy(e);
+    m->host_pending = false;
     return UMPA_OK;
 }
 
@@ -295,8 +516,10 @@ void umpa_destroy(umpa_model *m)
     if (!m) return;
     cudaDeviceSynchronize();      // blocks go back to the cache: nothing of this model may still be running
     free_frames(m);
-    for (Scratch *s : {&m->filtA, &m->filtB, &m->auxS, &m->auxR, &m->tabX, &m->tabM})
+    for (Scratch *s : {&m->filtA, &m->filtB, &m->auxS, &m->auxR, &m->tabX, &m->tabM, &m->outbuf})
         if (s->p) pool_free(s->p, s->bytes);
+    for (cudaStream_t st : {m->s_copy, m->s_comp, m->s_out})
+        if (st) cudaStreamDestroy(st);
     for (void *p : {(void *)m->d_dim, (void *)m->d_pos, (void *)m->d_win, (void *)m->d_quad, (void *)m->d_g})
         if (p) cudaFree(p);
     for (int i = 0; i < 5; i++)
@@ -308,6 +531,7 @@ int umpa_set_frames(umpa_model *m, const double *const *sam, const double *const
                     int on_device, void *stream)
 {
     if (!m || !sam || !ref) { umpa_set_error("umpa_set_frames: NULL argument"); return UMPA_ERR_ARG; }
+    if (on_device < 0 || on_device > 2) { umpa_set_error("umpa_set_frames: on_device must be 0, 1 or 2"); return UMPA_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     free_frames(m);
     const int Na = m->Na;
@@ -316,8 +540,10 @@ int umpa_set_frames(umpa_model *m, const double *const *sam, const double *const
     for (int k = 0; k < Na; k++) { m->frame_off[k] = total; total += (size_t)m->dim[2 * k] * m->dim[2 * k + 1]; }
     m->stack_elems = total;
     m->masked = mask != nullptr;
-    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     const double *const *srcs[3] = {sam, ref, mask};
+    for (int a = 0; a < 3; a++)
+        for (int k = 0; srcs[a] && k < Na; k++)
+            if (!srcs[a][k]) { umpa_set_error("umpa_set_frames: frame %d is NULL", k); return UMPA_ERR_ARG; }
     double **dsts[3] = {&m->d_sam64, &m->d_ref64, &m->d_mask64};
     const double ***ptrs[3] = {&m->d_sam_ptrs, &m->d_ref_ptrs, &m->d_mask_ptrs};
     for (int a = 0; a < 3; a++) {
@@ -325,19 +551,27 @@ int umpa_set_frames(umpa_model *m, const double *const *sam, const double *const
         UMPA_CUDA(pool_malloc((void **)dsts[a], total * sizeof(double)));
         UMPA_CUDA(cudaMalloc((void **)ptrs[a], Na * sizeof(double *)));
         std::vector<const double *> hp(Na);
-        for (int k = 0; k < Na; k++) {
-            if (!srcs[a][k]) { umpa_set_error("umpa_set_frames: frame %d is NULL", k); return UMPA_ERR_ARG; }
-            const size_t n = (size_t)m->dim[2 * k] * m->dim[2 * k + 1];
-            UMPA_CUDA(cudaMemcpyAsync(*dsts[a] + m->frame_off[k], srcs[a][k], n * sizeof(double), kind, st));
-            hp[k] = *dsts[a] + m->frame_off[k];
-        }
-        UMPA_CUDA(cudaMemcpyAsync((void *)*ptrs[a], hp.data(), Na * sizeof(double *), cudaMemcpyHostToDevice, st));
-        UMPA_CUDA(cudaStreamSynchronize(st));          // hp goes out of scope
+        for (int k = 0; k < Na; k++) hp[k] = *dsts[a] + m->frame_off[k];
+        UMPA_CUDA(cudaMemcpy((void *)*ptrs[a], hp.data(), Na * sizeof(double *), cudaMemcpyHostToDevice));
     }
     m->dev_bytes += (int64_t)(total * sizeof(double) * (mask ? 3 : 2));
-    m->frames_set = true;
-    int rc = table_prepare_frames(m, st);
+    int rc = table_alloc32(m);
     if (rc) return rc;
+    m->frames_set = true;
+    if (on_device == 2) {                       // keep the host pointers; the first match uploads
+        m->h_sam.assign(sam, sam + Na);
+        m->h_ref.assign(ref, ref + Na);
+        if (mask) m->h_mask.assign(mask, mask + Na);
+        m->host_pending = true;
+        return UMPA_OK;
+    }
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    for (int a = 0; a < 3; a++)
+        for (int k = 0; srcs[a] && k < Na; k++) {
+            const size_t n = (size_t)m->dim[2 * k] * m->dim[2 * k + 1];
+            UMPA_CUDA(cudaMemcpyAsync(*dsts[a] + m->frame_off[k], srcs[a][k], n * sizeof(double), kind, st));
+        }
+    if ((rc = table_prepare_frames(m, st))) return rc;
     UMPA_CUDA(cudaStreamSynchronize(st));
     return UMPA_OK;
 }
@@ -389,38 +623,29 @@ int umpa_match(umpa_model *m, const int32_t roi[6], const double uv0[2], const d
     if ((rc = check_roi_bounds(m, v))) return rc;
     v.abc = abc; v.cover = cover; v.cover_threshold = cover_threshold;
     if (m->kind == UMPA_DFKERNEL && !abc) { umpa_set_error("abc array has to be provided"); return UMPA_ERR_ARG; }   // model.pyx:973-974
-    const size_t n = (size_t)v.N0 * v.N1;
-    if (cover) { if ((rc = zero_outputs(*out, n, st))) return rc; }
-    else if (out->df && m->kind != UMPA_DF) UMPA_CUDA(cudaMemsetAsync(out->df, 0, n * sizeof(double), st));
-
-    std::string why;
-    bool use_table = false;
-    if (m->path_opt != UMPA_PATH_LAZY) {
-        use_table = table_eligible(m, v, &why);
-        if (!use_table && m->path_opt == UMPA_PATH_TABLE) {
-            umpa_set_error("table path requested but not eligible: %s", why.c_str());
-            return UMPA_ERR_UNSUPPORTED;
-        }
-    }
-    if (use_table) { m->last_path = UMPA_PATH_TABLE; return table_match(m, v, *out, st); }
-    m->last_path = UMPA_PATH_LAZY;
-    return lazy_match(m, v, *out, st);
+    if ((rc = ensure_resident(m, st))) return rc;
+    return match_view(m, v, *out, st);
 }
 
 int umpa_match_host(umpa_model *m, const int32_t roi[6], const double uv0[2], const double *abc, const double *cover,
                     double cover_threshold, const umpa_outputs *out)
 {
     if (!m || !out) { umpa_set_error("umpa_match_host: NULL argument"); return UMPA_ERR_ARG; }
+    if (!m->frames_set) { umpa_set_error("umpa_match_host: frames were not set"); return UMPA_ERR_STATE; }
     RoiView v;
     int rc = make_roi(m, roi, uv0, &v);
     if (rc) return rc;
-    if (v.N0 <= 0 || v.N1 <= 0) return UMPA_OK;
+    m->last_launches = 0;
+    m->ev_valid = false;
+    if (v.N0 <= 0 || v.N1 <= 0) { m->last_path = 0; return UMPA_OK; }
+    if ((rc = check_roi_bounds(m, v))) return rc;
+    if (m->kind == UMPA_DFKERNEL && !abc) { umpa_set_error("abc array has to be provided"); return UMPA_ERR_ARG; }
+    if ((rc = ensure_streams(m))) return rc;
     const size_t n = (size_t)v.N0 * v.N1;
     // one device block: f,T,dx,dy,df | debug_d | debug_a | abc | cover | err,ncalls
-    size_t nd = 5 * n + (out->debug_d ? 25 * n : 0) + (out->debug_a ? 16 * n : 0) + (abc ? 3 * n : 0) + (cover ? n : 0);
-    void *block = nullptr;
-    UMPA_CUDA(cudaMalloc(&block, nd * sizeof(double) + 2 * n * sizeof(int32_t)));
-    double *p = (double *)block;
+    const size_t nd = 5 * n + (out->debug_d ? 25 * n : 0) + (out->debug_a ? 16 * n : 0) + (abc ? 3 * n : 0) + (cover ? n : 0);
+    if ((rc = scratch_reserve(m, m->outbuf, nd * sizeof(double) + 2 * n * sizeof(int32_t)))) return rc;
+    double *p = (double *)m->outbuf.p;
     umpa_outputs d{};
     d.f = p; p += n; d.T = p; p += n; d.dx = p; p += n; d.dy = p; p += n; d.df = p; p += n;
     if (out->debug_d) { d.debug_d = p; p += 25 * n; }
@@ -429,31 +654,27 @@ int umpa_match_host(umpa_model *m, const int32_t roi[6], const double uv0[2], co
     if (abc) { d_abc = p; p += 3 * n; }
     if (cover) { d_cover = p; p += n; }
     d.err = (int32_t *)p; d.ncalls = d.err + n;
-    cudaError_t e = cudaSuccess;
-    if (abc) e = cudaMemcpy(d_abc, abc, 3 * n * sizeof(double), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && cover) e = cudaMemcpy(d_cover, cover, n * sizeof(double), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(block); umpa_set_error("H2D copy failed: %s", cudaGetErrorString(e)); return UMPA_ERR_CUDA; }
-    rc = umpa_match(m, roi, uv0, d_abc, d_cover, cover_threshold, &d, nullptr);
-    if (rc == UMPA_OK) {
-        e = cudaDeviceSynchronize();
-        auto back = [&](void *dst, const void *src, size_t bytes) {
-            if (dst && e == cudaSuccess) e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
-        };
-        back(out->f, d.f, n * sizeof(double)); back(out->T, d.T, n * sizeof(double));
-        back(out->dx, d.dx, n * sizeof(double)); back(out->dy, d.dy, n * sizeof(double));
-        back(out->df, d.df, n * sizeof(double));
-        back(out->debug_d, d.debug_d, 25 * n * sizeof(double)); back(out->debug_a, d.debug_a, 16 * n * sizeof(double));
-        back(out->err, d.err, n * sizeof(int32_t)); back(out->ncalls, d.ncalls, n * sizeof(int32_t));
-        if (e != cudaSuccess) { umpa_set_error("match failed on the device: %s", cudaGetErrorString(e)); rc = UMPA_ERR_CUDA; }
-    }
-    cudaFree(block);
-    return rc;
+    if (abc) UMPA_CUDA(cudaMemcpyAsync(d_abc, abc, 3 * n * sizeof(double), cudaMemcpyHostToDevice, m->s_comp));
+    if (cover) UMPA_CUDA(cudaMemcpyAsync(d_cover, cover, n * sizeof(double), cudaMemcpyHostToDevice, m->s_comp));
+    v.abc = d_abc; v.cover = d_cover; v.cover_threshold = cover_threshold;
+
+    // frames still on the host and the table path applies: pipeline upload / kernels / download
+    if (m->host_pending && m->path_opt != UMPA_PATH_LAZY && !getenv("UMPA_NO_STREAMING") && table_eligible(m, v, nullptr))
+        return streamed_match(m, v, d, *out);
+
+    if ((rc = ensure_resident(m, m->s_comp))) return rc;
+    if ((rc = match_view(m, v, d, m->s_comp))) return rc;
+    if ((rc = download_outputs(*out, d, n, m->s_comp))) return rc;
+    cudaError_t e = cudaStreamSynchronize(m->s_comp);
+    if (e != cudaSuccess) { umpa_set_error("match failed on the device: %s", cudaGetErrorString(e)); return UMPA_ERR_CUDA; }
+    return UMPA_OK;
 }
 
 int umpa_cost(umpa_model *m, int i, int j, int si, int sj, const double abc[3], double values[3], int *status)
 {
     if (!m || !values) { umpa_set_error("umpa_cost: NULL argument"); return UMPA_ERR_ARG; }
     if (!m->frames_set) { umpa_set_error("umpa_cost: frames were not set"); return UMPA_ERR_STATE; }
+    if (int rc = ensure_resident(m, nullptr)) return rc;
     return lazy_cost(m, i, j, si, sj, abc, values, status);
 }
 
@@ -462,6 +683,7 @@ int umpa_min(umpa_model *m, int i, int j, double *values, double uv[2], double d
 {
     if (!m || !values || !uv) { umpa_set_error("umpa_min: NULL argument"); return UMPA_ERR_ARG; }
     if (!m->frames_set) { umpa_set_error("umpa_min: frames were not set"); return UMPA_ERR_STATE; }
+    if (int rc = ensure_resident(m, nullptr)) return rc;
     return lazy_min(m, i, j, values, uv, dbg_d, dbg_a, ncalls, ok);
 }
 
@@ -473,6 +695,7 @@ int umpa_coverage(umpa_model *m, const int32_t roi[6], double *out, int on_devic
     RoiView v;
     int rc = make_roi(m, roi, nullptr, &v);
     if (rc) return rc;
+    if (m->masked && (rc = ensure_resident(m, st))) return rc;      // only the masked coverage reads frame data
     if (v.N0 <= 0 || v.N1 <= 0) return UMPA_OK;
     const size_t n = (size_t)v.N0 * v.N1;
     if (on_device) return coverage_map(m, v, out, st);

@@ -84,10 +84,17 @@ struct umpa_model {
     // device: centred FP32 stacks (TABLE path); pitch in floats, multiple of 4
     float *d_sam32 = nullptr, *d_ref32 = nullptr;
     int pitch = 0;
-    std::vector<double> mean_s, mean_r;          // per-frame means (FP64)
-    float *d_mean_s = nullptr, *d_mean_r = nullptr, *d_g = nullptr;
-    double *d_means64 = nullptr;                 // [2*Na]: sample means then reference means
+    float *d_mean_s = nullptr, *d_mean_r = nullptr, *d_g = nullptr;   // centring constants d_k, c_k (FP32 copies)
+    double *d_means64 = nullptr;                 // [2*Na]: sample then reference centring constants (FP64)
+    double *d_consts = nullptr;                  // [3]: sum_k c_k d_k, sum_k c_k^2, sum_k d_k^2
     double *d_partials = nullptr;
+
+    // host frames whose upload is deferred to the first match (umpa_set_frames with on_device = 2):
+    // umpa_match_host then pipelines upload, kernels and download in row bands
+    std::vector<const double *> h_sam, h_ref, h_mask;
+    bool host_pending = false;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_out = nullptr;
+    Scratch outbuf;
 
     // TABLE-path scratch (grow-only)
     Scratch filtA, filtB, auxS, auxR, tabX, tabM;
@@ -112,7 +119,11 @@ int lazy_min(umpa_model *m, int i, int j, double *values, double uv[2], double *
 int coverage_map(umpa_model *m, const RoiView &roi, double *out_dev, cudaStream_t st);
 
 // implemented in table_path.cu
-int table_prepare_frames(umpa_model *m, cudaStream_t st);      // FP64 stacks -> centred FP32 stacks
+int table_prepare_frames(umpa_model *m, cudaStream_t st);      // FP64 stacks -> centred FP32 stacks (all three steps)
+int table_alloc32(umpa_model *m);                              // 1. FP32 stacks + constants (no-op when not applicable)
+int table_means(umpa_model *m, cudaStream_t st);               // 2. centring constants from the sampled rows (see table_row_step)
+int table_center_rows(umpa_model *m, int y0, int y1, cudaStream_t st);   // 3. rows [y0,y1) of every frame -> centred FP32
+int table_row_step(int H);                                     // rows y = 0, step, 2 step, ... define the centring constants
 bool table_eligible(const umpa_model *m, const RoiView &roi, std::string *why);
 int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st);
 

@@ -43,16 +43,24 @@ constexpr int SMEM_CAP = 227 * 1024;
 
 constexpr int SUM_BLOCKS = 64;
 
-// grid (SUM_BLOCKS, 2*Na): partial sums of one FP64 frame
-__global__ void frame_partial_sums(const double *sam, const double *ref, size_t frame_elems, int Na,
+// Centring constants.  Any constant close to the frame mean works (the identities that rebuild
+// the uncentred sums hold for every c_k, d_k; only the FP32 cancellation depends on how close
+// they are), so they are defined as the mean over the rows y = 0, step, 2 step, ... : those
+// rows can be uploaded ahead of the rest (umpa_match_host pipelines the upload in row bands)
+// and the result does not depend on how the upload was split.
+// grid (SUM_BLOCKS, 2*Na): partial sums of the sampled rows of one FP64 frame (fixed order)
+__global__ void frame_partial_sums(const double *sam, const double *ref, int H, int W, int row_step, int Na,
                                    double *partials)
 {
     const int f = blockIdx.y;
+    const size_t frame_elems = (size_t)H * W;
     const double *src = (f < Na ? sam + (size_t)f * frame_elems : ref + (size_t)(f - Na) * frame_elems);
-    const size_t chunk = (frame_elems + SUM_BLOCKS - 1) / SUM_BLOCKS;
-    const size_t lo = (size_t)blockIdx.x * chunk, hi = min(frame_elems, lo + chunk);
+    const int nrows = (H + row_step - 1) / row_step;
     double s = 0.;
-    for (size_t n = lo + threadIdx.x; n < hi; n += blockDim.x) s += src[n];
+    for (int r = blockIdx.x; r < nrows; r += SUM_BLOCKS) {
+        const double *row = src + (size_t)r * row_step * W;
+        for (int x = threadIdx.x; x < W; x += blockDim.x) s += row[x];
+    }
     __shared__ double red[256];
     red[threadIdx.x] = s;
     __syncthreads();
@@ -63,23 +71,33 @@ __global__ void frame_partial_sums(const double *sam, const double *ref, size_t 
     if (threadIdx.x == 0) partials[(size_t)f * SUM_BLOCKS + blockIdx.x] = red[0];
 }
 
-__global__ void finish_means(const double *partials, int nframes, double inv_count, double *means64, float *mean_s,
-                             float *mean_r, int Na)
+// one block: constants of all 2*Na frames, then sum c_k d_k, sum c_k^2, sum d_k^2
+__global__ void finish_means(const double *partials, int Na, double inv_count, double *means64, float *mean_s,
+                             float *mean_r, double *consts)
 {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nframes) return;
-    double s = 0.;
-    for (int b = 0; b < SUM_BLOCKS; b++) s += partials[(size_t)f * SUM_BLOCKS + b];
-    const double mu = s * inv_count;
-    means64[f] = mu;
-    if (f < Na) mean_s[f] = (float)mu; else mean_r[f - Na] = (float)mu;
+    for (int f = threadIdx.x; f < 2 * Na; f += blockDim.x) {
+        double s = 0.;
+        for (int b = 0; b < SUM_BLOCKS; b++) s += partials[(size_t)f * SUM_BLOCKS + b];
+        const double mu = s * inv_count;
+        means64[f] = mu;
+        if (f < Na) mean_s[f] = (float)mu; else mean_r[f - Na] = (float)mu;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double cd = 0., cc = 0., dd = 0.;
+        for (int k = 0; k < Na; k++) {
+            const double d = means64[k], c = means64[Na + k];
+            cd += c * d; cc += c * c; dd += d * d;
+        }
+        consts[0] = cd; consts[1] = cc; consts[2] = dd;
+    }
 }
 
-// grid (ceil(W/256), H, 2*Na): x' = (float)(x - mean)
+// grid (ceil(pitch/256), y1-y0, 2*Na): x' = (float)(x - c) for rows [y0, y1)
 __global__ void center_frames(const double *sam, const double *ref, const double *means64, int Na, int H, int W,
-                              int pitch, float *sam32, float *ref32)
+                              int pitch, int y0, float *sam32, float *ref32)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = y0 + blockIdx.y, f = blockIdx.z;
     if (x >= pitch) return;
     const bool is_s = f < Na;
     const int k = is_s ? f : f - Na;
@@ -522,7 +540,8 @@ struct WalkParams {
     int oy, ox;                     // raw coords of output pixel (0,0) of the dense region
     int dxX, dxM;                   // column of that pixel inside the cross / mean table (TMA alignment shift)
     int kind, Na, max_shift, subpx;
-    double sw, cd, cc, dd;          // sum of window; sum_k c_k d_k, c_k^2, d_k^2
+    double sw;                      // sum of window
+    const double *consts;           // device: sum_k c_k d_k, c_k^2, d_k^2
     double inv_sw, inv_sw2, inv_Na;
     const double *quad;
     const float *ktab;              // DFKernel: pixel-major rows [t5c(S^2) | t3c(S^2) | sigma-1] (kernel_path.cu)
@@ -535,6 +554,7 @@ struct TableEval {
     int ty, tx;                     // table coords of this pixel
     double t1, V;                   // pixel-only terms
     const float *krow;              // DFKernel: this pixel's table row
+    double cd, cc;
 
     __device__ int operator()(int si, int sj, double &cost, FitArgs &args) const
     {
@@ -548,8 +568,8 @@ struct TableEval {
             // t3 = sum w B^2, t5 = sum w B S with B = k_p (*) R (Model.cpp:1076-1099), rebuilt from the
             // centred FP32 sums: B = B' + sigma c_k
             const double sig = 1. + (double)__ldg(krow + 2 * S * S);
-            const double t5 = (double)__ldg(krow + sidx) + sig * (V + w.swk * w.cd);
-            const double t3 = (double)__ldg(krow + S * S + sidx) + sig * sig * w.swk * w.cc;
+            const double t5 = (double)__ldg(krow + sidx) + sig * (V + w.swk * cd);
+            const double t3 = (double)__ldg(krow + S * S + sidx) + sig * sig * w.swk * cc;
             args.t = t5 / t3;
             cost = (t1 - t5 * args.t) * w.inv_Na;
             return UMPA_ST_OK;
@@ -557,12 +577,12 @@ struct TableEval {
         const float4 r = __ldg(w.auxR + (size_t)(w.oy + ty + si) * w.pitch + (w.ox + tx + sj));
         const float xv = __ldg(w.tabX + (sidx * w.rowsX + ty) * w.colsX + tx + w.dxX);
         const double T3 = r.x, P3 = r.y, U = r.z, M2 = r.w;
-        const double t3 = T3 + 2. * P3 + w.sw * w.cc;
-        const double lin = U + V + w.sw * w.cd;
+        const double t3 = T3 + 2. * P3 + w.sw * cc;
+        const double lin = U + V + w.sw * cd;
         const double t5 = (double)xv + lin;
         if (w.kind == UMPA_DF) {
             const float mv = __ldg(w.tabM + (sidx * w.rowsM + ty) * w.colsM + tx + w.dxM);
-            const double t2 = M2 * w.inv_sw2 + 2. * P3 * w.inv_sw + w.cc;
+            const double t2 = M2 * w.inv_sw2 + 2. * P3 * w.inv_sw + cc;
             const double t6 = w.sw * t2;
             const double t4 = (double)mv * w.inv_sw + lin;
             const double rden = 1. / (t2 * t3 - t6 * t6);
@@ -618,8 +638,9 @@ __global__ void __launch_bounds__(WALK_NT, WALK_MINB) table_walk_kernel(WalkPara
     }
 #endif
     const float4 s = __ldg(w.auxS + (size_t)(w.oy + ty) * w.pitch + (w.ox + tx));
-    TableEval eval{w, ty, tx, (double)s.x + 2. * (double)s.y + w.sw * w.dd, (double)s.z,
-                   w.ktab ? w.ktab + n * (size_t)w.kstride : nullptr};
+    const double cd = __ldg(w.consts), cc = __ldg(w.consts + 1), dd = __ldg(w.consts + 2);
+    TableEval eval{w, ty, tx, (double)s.x + 2. * (double)s.y + w.sw * dd, (double)s.z,
+                   w.ktab ? w.ktab + n * (size_t)w.kstride : nullptr, cd, cc};
     FitArgs args{0., 0.};
     SharedGrid d{&d_sm[0][threadIdx.x]};
     double a[16], uv[2] = {roi.uv0[0], roi.uv0[1]}, f = 0.;
@@ -744,36 +765,54 @@ size_t plan_tiles(TableParams &p, int S, bool filter, int *nt)
 
 }  // namespace
 
-// FP64 device stacks -> per-frame means + centred FP32 stacks (pitch multiple of 4 floats)
+// FP64 device stacks -> centring constants + centred FP32 stacks (pitch multiple of 4 floats)
+int table_row_step(int H) { return std::max(1, H / 32); }
+
+static bool table_applicable(const umpa_model *m) { return m->uniform && !m->masked; }
+
+int table_alloc32(umpa_model *m)
+{
+    if (!table_applicable(m) || m->d_sam32) return UMPA_OK;
+    const int Na = m->Na;
+    m->pitch = 4 * ((m->W + 3) / 4);
+    const size_t n32 = (size_t)Na * m->H * m->pitch;
+    UMPA_CUDA(pool_malloc((void **)&m->d_sam32, n32 * sizeof(float)));
+    UMPA_CUDA(pool_malloc((void **)&m->d_ref32, n32 * sizeof(float)));
+    UMPA_CUDA(cudaMalloc(&m->d_mean_s, Na * sizeof(float)));
+    UMPA_CUDA(cudaMalloc(&m->d_mean_r, Na * sizeof(float)));
+    UMPA_CUDA(cudaMalloc(&m->d_means64, 2 * Na * sizeof(double)));
+    UMPA_CUDA(cudaMalloc(&m->d_consts, 3 * sizeof(double)));
+    UMPA_CUDA(cudaMalloc(&m->d_partials, (size_t)2 * Na * SUM_BLOCKS * sizeof(double)));
+    m->dev_bytes += 2 * n32 * sizeof(float);
+    return UMPA_OK;
+}
+
+int table_means(umpa_model *m, cudaStream_t st)
+{
+    if (!table_applicable(m)) return UMPA_OK;
+    const int Na = m->Na, H = m->H, W = m->W, rs = table_row_step(H);
+    const double count = (double)((H + rs - 1) / rs) * W;
+    frame_partial_sums<<<dim3(SUM_BLOCKS, 2 * Na), 256, 0, st>>>(m->d_sam64, m->d_ref64, H, W, rs, Na, m->d_partials);
+    finish_means<<<1, 256, 0, st>>>(m->d_partials, Na, 1. / count, m->d_means64, m->d_mean_s, m->d_mean_r, m->d_consts);
+    UMPA_CUDA(cudaGetLastError());
+    return UMPA_OK;
+}
+
+int table_center_rows(umpa_model *m, int y0, int y1, cudaStream_t st)
+{
+    if (!table_applicable(m) || y1 <= y0) return UMPA_OK;
+    center_frames<<<dim3((m->pitch + 255) / 256, y1 - y0, 2 * m->Na), 256, 0, st>>>(
+        m->d_sam64, m->d_ref64, m->d_means64, m->Na, m->H, m->W, m->pitch, y0, m->d_sam32, m->d_ref32);
+    UMPA_CUDA(cudaGetLastError());
+    return UMPA_OK;
+}
+
 int table_prepare_frames(umpa_model *m, cudaStream_t st)
 {
-    if (!m->uniform || m->masked) return UMPA_OK;
-    const int Na = m->Na, H = m->H, W = m->W;
-    m->pitch = 4 * ((W + 3) / 4);
-    const size_t n32 = (size_t)Na * H * m->pitch;
-    if (!m->d_sam32) {
-        UMPA_CUDA(pool_malloc((void **)&m->d_sam32, n32 * sizeof(float)));
-        UMPA_CUDA(pool_malloc((void **)&m->d_ref32, n32 * sizeof(float)));
-        UMPA_CUDA(cudaMalloc(&m->d_mean_s, Na * sizeof(float)));
-        UMPA_CUDA(cudaMalloc(&m->d_mean_r, Na * sizeof(float)));
-        UMPA_CUDA(cudaMalloc(&m->d_means64, 2 * Na * sizeof(double)));
-        UMPA_CUDA(cudaMalloc(&m->d_partials, (size_t)2 * Na * SUM_BLOCKS * sizeof(double)));
-        m->dev_bytes += 2 * n32 * sizeof(float);
-    }
-    const size_t fe = (size_t)H * W;
-    frame_partial_sums<<<dim3(SUM_BLOCKS, 2 * Na), 256, 0, st>>>(m->d_sam64, m->d_ref64, fe, Na, m->d_partials);
-    finish_means<<<(2 * Na + 63) / 64, 64, 0, st>>>(m->d_partials, 2 * Na, 1. / (double)fe, m->d_means64,
-                                                   m->d_mean_s, m->d_mean_r, Na);
-    center_frames<<<dim3((m->pitch + 255) / 256, H, 2 * Na), 256, 0, st>>>(m->d_sam64, m->d_ref64, m->d_means64, Na,
-                                                                          H, W, m->pitch, m->d_sam32, m->d_ref32);
-    UMPA_CUDA(cudaGetLastError());
-    std::vector<double> mu(2 * Na);
-    UMPA_CUDA(cudaMemcpyAsync(mu.data(), m->d_means64, 2 * Na * sizeof(double), cudaMemcpyDeviceToHost, st));
-    UMPA_CUDA(cudaStreamSynchronize(st));
-    m->mean_s.assign(mu.begin(), mu.begin() + Na);
-    m->mean_r.assign(mu.begin() + Na, mu.end());
-    m->moments_valid = false;
-    return UMPA_OK;
+    int rc;
+    if ((rc = table_alloc32(m))) return rc;
+    if ((rc = table_means(m, st))) return rc;
+    return table_center_rows(m, 0, m->H, st);
 }
 
 bool table_eligible(const umpa_model *m, const RoiView &roi, std::string *why)
@@ -925,13 +964,7 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         w.kind = m->kind; w.Na = Na; w.max_shift = m->max_shift; w.subpx = m->subpx;
         w.sw = m->win_sum; w.quad = m->d_quad;
         w.inv_sw = 1. / w.sw; w.inv_sw2 = 1. / (w.sw * w.sw); w.inv_Na = 1. / (double)Na;
-        double cd = 0., cc = 0., dd = 0.;
-        for (int k = 0; k < Na; k++) {
-            cd += m->mean_r[k] * m->mean_s[k];
-            cc += m->mean_r[k] * m->mean_r[k];
-            dd += m->mean_s[k] * m->mean_s[k];
-        }
-        w.cd = cd; w.cc = cc; w.dd = dd;
+        w.consts = m->d_consts;
         dim3 grid((roi.N1 + WALK_NT - 1) / WALK_NT, roi.N0);
         table_walk_kernel<<<grid, WALK_NT, 0, st>>>(w, roi, out);
         UMPA_CUDA(cudaGetLastError());

@@ -7,8 +7,9 @@ result dictionaries (UMPA/model.pyx:116-997); the work is done on the GPU by
 only as plumbing: device output buffers, pinned host buffers, the current stream.
 
 Differences from the reference that a caller can see (documented, deliberate):
-  * frames are copied to the GPU when the model is constructed -- later in-place
-    edits of the caller's arrays are not seen (the reference keeps raw pointers);
+  * host frames are copied to the GPU by the first match()/cost()/min() (pipelined with the
+    kernels); device (torch) frames when the model is constructed.  Later in-place edits of
+    the caller's arrays are not seen (the reference keeps raw pointers);
   * non-float64 inputs are converted (the reference reads them as garbage,
     model.pyx:236-237);
   * ``num_threads`` is accepted and ignored;
@@ -120,9 +121,13 @@ class UMPAModelBase:
             if self._on_device:
                 return _as_ptr_array([int(f.data_ptr()) for f in frames])
             return _as_ptr_array([f.ctypes.data for f in frames])
+        # host frames: the upload is deferred to the first match(), which pipelines it with the
+        # kernels in row bands (umpa_match_host).  Like the reference (model.pyx:242-262) the model
+        # keeps references to the caller's arrays until then.
+        self._frames_keepalive = (sams, refs, masks)
         _capi.check(L.umpa_set_frames(self._h, ptrs(sams), ptrs(refs),
                                       ptrs(masks) if masks is not None else None,
-                                      1 if self._on_device else 0, self._stream()))
+                                      1 if self._on_device else 2, self._stream()))
         self._geo.set_ROI(ROI)
 
     # ------------------------------------------------------------------ plumbing
@@ -320,21 +325,51 @@ class UMPAModelBase:
         return out
 
     def _match(self, step=None, dxdy=None, ROI=None, num_threads=None, quiet=False, abc=None, debug=None):
+        """Host-to-host match through umpa_match_host: result maps land in pinned host memory.  The
+        first call on host frames pipelines upload, kernels and download in row bands."""
         if (ROI is not None) and (step is not None):
             print("Warning: 'ROI' and 'step' parameters are set simultaneously. "
                   "'step' parameter is ignored.")
             step = None
         if debug is None:
             debug = DEBUG
-        dev = self.match_device(step=step, dxdy=dxdy, ROI=ROI, abc=abc, debug=debug)
-        dev.pop("_keepalive", None)
-        host = {}
-        for k, t in dev.items():       # device -> pinned host, one stream, one sync
-            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            h.copy_(t, non_blocking=True)
-            host[k] = h
-        torch.cuda.current_stream().synchronize()
-        return {k: h.numpy() for k, h in host.items()}
+        s0, s1 = self._convert_ROI_slice(ROI, step)
+        self._set_ROI((s0, s1))                       # sticky, like the reference (model.pyx:406)
+        N0, N1 = self._shape_of(s0, s1)
+        pin = torch.cuda.is_available()
+        f64 = dict(dtype=torch.float64, pin_memory=pin)
+        out = {k: torch.empty((N0, N1), **f64) for k in ("f", "T", "dx", "dy")}
+        if self._kind == _capi.DF:
+            out["df"] = torch.empty((N0, N1), **f64)
+        out["err"] = torch.empty((N0, N1), dtype=torch.int32, pin_memory=pin)
+        out["debug_Ncalls"] = torch.empty((N0, N1), dtype=torch.int32, pin_memory=pin)
+        if debug:
+            out["debug_d"] = torch.empty((N0, N1, 25), **f64)
+            out["debug_a"] = torch.empty((N0, N1, 16), **f64)
+        if N0 and N1:
+            abc_h = None
+            if self._kind == _capi.DFKERNEL:
+                if isinstance(abc, torch.Tensor):
+                    abc = abc.detach().cpu().numpy()
+                abc_h = np.ascontiguousarray(abc, dtype=np.float64)
+            cover_h, thr = None, 0.
+            if self._masked or not self._uniform:
+                cover_h = np.ascontiguousarray(self._coverage_device(s0, s1).cpu().numpy())
+                thr = .1 * float(cover_h.max()) / self._Na               # model.pyx:431
+            uv0 = None
+            if dxdy is not None:
+                uv0 = (C.c_double * 2)(float(dxdy[0]), float(dxdy[1]))   # model.pyx:463-465
+            o = _capi.Outputs()
+            o.f, o.T, o.dx, o.dy = (out[k].data_ptr() for k in ("f", "T", "dx", "dy"))
+            o.df = out["df"].data_ptr() if "df" in out else None
+            o.err, o.ncalls = out["err"].data_ptr(), out["debug_Ncalls"].data_ptr()
+            o.debug_d = out["debug_d"].data_ptr() if debug else None
+            o.debug_a = out["debug_a"].data_ptr() if debug else None
+            _capi.check(_capi.lib().umpa_match_host(
+                self._h, _capi.roi6((s0, s1)), uv0,
+                C.c_void_p(abc_h.ctypes.data) if abc_h is not None else None,
+                C.c_void_p(cover_h.ctypes.data) if cover_h is not None else None, thr, C.byref(o)))
+        return {k: h.numpy() for k, h in out.items()}
 
     # single-pixel hooks ----------------------------------------------------
     def _min(self, i, j, abc=None):
