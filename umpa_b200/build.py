@@ -8,7 +8,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libumpa_b200.so")
 SOURCES = ["capi.cu", "lazy_path.cu", "table_path.cu", "kernel_path.cu"]
-HEADERS = ["common.cuh", "walk.cuh", os.path.join("..", "..", "include", "umpa_b200.h")]
+# shift_table_inst.cu is compiled once per window half-width (-1 = unfiltered table) so that the
+# template instantiations build in parallel: (source, extra flags, object tag)
+INSTANCES = [("shift_table_inst.cu", ["-DUMPA_INST_NW=%d" % nw], "nw%s" % ("m1" if nw < 0 else nw)) for nw in range(-1, 7)]
+HEADERS = ["common.cuh", "walk.cuh", "shift_table.cuh", os.path.join("..", "..", "include", "umpa_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden", "-cudart", "static"]
 
@@ -24,7 +27,7 @@ def up_to_date():
     if not os.path.exists(LIB):
         return False
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, f) for f in SOURCES + [i[0] for i in INSTANCES] + HEADERS] + [os.path.abspath(__file__)]
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
@@ -35,9 +38,10 @@ def build(force=False, verbose=False, extra=(), dest=None):
     nvcc = nvcc_path()
     objs = []
     procs = []
-    for src in SOURCES:
-        obj = os.path.join(CSRC, src[:-3] + (".o" if dest is None else "." + os.path.basename(dest) + ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-c", os.path.join(CSRC, src), "-o", obj]
+    units = [(src, [], "") for src in SOURCES] + [(src, fl, "." + tag) for src, fl, tag in INSTANCES]
+    for src, flags, tag in units:
+        obj = os.path.join(CSRC, src[:-3] + tag + (".o" if dest is None else "." + os.path.basename(dest) + ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + list(extra) + flags + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

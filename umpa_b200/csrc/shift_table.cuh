@@ -1,0 +1,322 @@
+// shift_table.cuh -- the FP32 shift-table kernel of the table path (see table_path.cu for the
+// algebra) and its per-(S, Nw) launchers.  The kernel is instantiated for S = 3..19 and one window
+// half-width per translation unit: shift_table_inst.cu is compiled once per UMPA_INST_NW value
+// (-1 = plain table, 0..6 = filtered) so that the instantiations build in parallel.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace shift_table {
+
+constexpr int SMEM_CAP = 227 * 1024;
+
+// ------------------------------------------------------------------ shift tables
+//
+// table[s][p] = sum_k A_k(p+s) * B_k(p)   (FILTER: then window-filtered over p)
+//
+// One CTA owns an output tile TH x TW and produces ALL S*S shifts for it.  Work split:
+//   * the extended tile (TH + 2*halo rows, 32 columns = TW + 2*halo) is cut into strips of
+//     4 consecutive pixels; a thread owns one strip -> 8 strips per row, so every quarter
+//     warp reads one contiguous 128 B shared-memory line (conflict-free LDS.128);
+//   * G warp groups work on the same frame at the same time, group g accumulating shift rows
+//     [ (pass*G+g)*SH, +SH ): SH*S*4 FP32 accumulators per thread live in registers across all
+//     frames, so each frame tile is streamed through shared memory exactly once per pass;
+//   * frames arrive by TMA (cp.async.bulk.tensor, 3-D map over [Na][H][pitch], zero fill out
+//     of bounds) into a ring of NST stages guarded by full/empty mbarriers; thread 0 is the
+//     producer, nobody executes a per-frame __syncthreads();
+//   * epilogue (per shift row): accumulators -> shared, separable window filter (row pass in
+//     registers, column pass with 4-row register blocking), float4 stores to the table.
+
+struct TableParams {
+    float *table;                // [S*S][rows_p][cols_p]
+    const float *g;              // window factor (FILTER only)
+    int Na, Nw;
+    int oy, ox;                  // raw coordinates of table element (0,0)
+    int rows_p, cols_p;          // padded table plane
+    int TH, TW;                  // output tile
+    int EH;                      // extended tile rows (ext cols are EXT_W)
+    int AH, AP;                  // A tile rows, pitch (= TMA box width)
+    int G, npass, nstage;
+    int a_stage_floats, stage_floats;   // per-stage layout: A tile then B tile (128 B aligned)
+    int tiles_x, tiles_y;               // tile grid (the kernel is persistent over it)
+};
+
+constexpr int EXT_W = 32;          // extended tile width: one 128 B line per row
+constexpr int MAX_NT = 384;        // threads per CTA (3 groups x 16 rows x 8 strips)
+constexpr int MAX_STAGES = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 3-D tiled TMA load: box (c0.., c1.., c2) of the tensor map -> dense smem tile, completes on `bar`
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::
+            "r"(smem_u32(dst)), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// NWT: -1 = plain table (no window filter); >= 0 = window half-width, filter fully unrolled
+template <int S, int SH, int NWT>
+__global__ void __launch_bounds__(MAX_NT)
+shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TableParams p)
+{
+    extern __shared__ __align__(128) float sm[];
+    constexpr int HS = (S - 1) / 2;                  // max |shift|
+    // TMA needs the innermost box coordinate 16 B aligned (measured: unaligned -> illegal
+    // instruction).  The B tile origin is aligned by construction (host shifts the table
+    // origin); the A tile starts HS + DELTA columns to its left so that it is aligned too.
+    constexpr int DELTA = (4 - HS % 4) % 4;
+    constexpr int NA4 = (DELTA + S + 3 + 3) / 4;     // float4 loads covering DELTA+S+3 floats of an A row
+    constexpr bool FILTER = NWT >= 0;
+    constexpr int K = FILTER ? 2 * NWT + 1 : 1;
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
+
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int halo = FILTER ? NWT : 0;
+    const int TG = p.EH * (EXT_W / 4);               // threads per group
+    const int grp = tid / TG, lt = tid - grp * TG;
+    const int er = lt >> 3, ec = (lt & 7) << 2;      // strip: extended row, first extended column
+    float *cbuf = sm + (size_t)p.nstage * p.stage_floats;                // [G*S][EH][EXT_W] (FILTER only)
+    const uint32_t stage_bytes = (uint32_t)(p.AH * p.AP + p.EH * EXT_W) * sizeof(float);
+    const size_t plane_sz = (size_t)p.rows_p * p.cols_p;
+
+    float gk[K];
+#pragma unroll
+    for (int v = 0; v < K; v++) gk[v] = FILTER ? __ldg(p.g + v) : 1.f;
+    if (tid == 0) {
+        for (int s = 0; s < p.nstage; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], nt / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    // ---- persistent CTA: tiles blockIdx.x, +gridDim.x, ... ; the frame ring runs across tiles ----
+    const int ntiles = p.tiles_x * p.tiles_y;
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int per_tile = p.npass * p.Na;
+    const int total = my_tiles * per_tile;
+
+    // producer state (thread 0): next (tile, frame) to request, and where
+    int pr_issued = 0, pr_tile = blockIdx.x, pr_left = per_tile, pr_frame = 0, pr_stage = 0;
+    int pr_ax = 0, pr_ay = 0, pr_bx = 0, pr_by = 0;
+    auto pr_coords = [&]() {
+        const int tyi = pr_tile / p.tiles_x, txi = pr_tile - tyi * p.tiles_x;
+        pr_by = p.oy + tyi * p.TH - halo; pr_bx = p.ox + txi * p.TW - halo;
+        pr_ay = pr_by - HS; pr_ax = pr_bx - HS - DELTA;
+    };
+    auto issue_next = [&]() {
+        float *As = sm + (size_t)pr_stage * p.stage_floats, *Bs = As + p.a_stage_floats;
+        mbar_expect_tx(&full_bar[pr_stage], stage_bytes);
+        tma_load_3d(As, &mapA, pr_ax, pr_ay, pr_frame, &full_bar[pr_stage]);
+        tma_load_3d(Bs, &mapB, pr_bx, pr_by, pr_frame, &full_bar[pr_stage]);
+        pr_issued++;
+        if (++pr_stage == p.nstage) pr_stage = 0;
+        if (++pr_frame == p.Na) pr_frame = 0;
+        if (--pr_left == 0) { pr_left = per_tile; pr_tile += gridDim.x; pr_coords(); }
+    };
+    if (tid == 0) {
+        pr_coords();
+        for (int n = 0; n < p.nstage && n < total; n++) issue_next();
+    }
+
+    int stage = 0, phase = 0;                        // consumer ring position
+    int prev_stage = 0, prev_phase = 0;
+    bool first = true;
+    float acc[SH][S][4];
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tyi = tile / p.tiles_x, txi = tile - tyi * p.tiles_x;
+        const int ty0 = tyi * p.TH, tx0 = txi * p.TW;                    // table coords of the tile
+        for (int pass = 0; pass < p.npass; pass++) {
+            const int si0 = (pass * p.G + grp) * SH; // first shift row of this thread in this pass
+            const bool work = si0 < S;
+#pragma unroll
+            for (int a = 0; a < SH; a++)
+#pragma unroll
+                for (int b = 0; b < S; b++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[a][b][c] = 0.f;
+
+            for (int frame = 0; frame < p.Na; frame++) {
+                if (tid == 0 && !first && pr_issued < total) {           // refill the stage the previous frame used
+                    mbar_wait(&empty_bar[prev_stage], prev_phase);
+                    issue_next();
+                }
+                first = false;
+                mbar_wait(&full_bar[stage], phase);
+                if (work) {
+                    const float *As = sm + (size_t)stage * p.stage_floats;
+                    const float *Bs = As + p.a_stage_floats;
+                    const float4 b4 = *reinterpret_cast<const float4 *>(Bs + er * EXT_W + ec);
+                    const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+                    const float *arow0 = As + (er + si0) * p.AP + ec;
+#pragma unroll
+                    for (int sh = 0; sh < SH; sh++) {
+                        if (si0 + sh < S) {
+                            const float *arow = arow0 + sh * p.AP;
+                            float av[4 * NA4];
+#pragma unroll
+                            for (int v = 0; v < NA4; v++) {
+                                const float4 t = *reinterpret_cast<const float4 *>(arow + 4 * v);
+                                av[4 * v] = t.x; av[4 * v + 1] = t.y; av[4 * v + 2] = t.z; av[4 * v + 3] = t.w;
+                            }
+#pragma unroll
+                            for (int sj = 0; sj < S; sj++)
+#pragma unroll
+                                for (int x = 0; x < 4; x++)
+                                    acc[sh][sj][x] = fmaf(bv[x], av[DELTA + sj + x], acc[sh][sj][x]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);     // this warp is done with the stage
+                prev_stage = stage; prev_phase = phase;
+                if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+            }
+
+            // ---------------- epilogue of this pass ----------------
+            if (!FILTER) {
+                if (work) {
+#pragma unroll
+                    for (int sh = 0; sh < SH; sh++) {
+                        const int si = si0 + sh;
+                        if (si < S && ec < p.TW) {
+                            float *dst = p.table + (size_t)(si * S) * plane_sz + (size_t)(ty0 + er) * p.cols_p + tx0 + ec;
+#pragma unroll
+                            for (int sj = 0; sj < S; sj++)
+                                *reinterpret_cast<float4 *>(dst + sj * plane_sz) =
+                                    make_float4(acc[sh][sj][0], acc[sh][sj][1], acc[sh][sj][2], acc[sh][sj][3]);
+                        }
+                    }
+                }
+            } else {
+                // Separable window filter, one shift row (S planes per group) at a time.
+                //  row pass: in registers; the 8 lanes of a quarter warp hold one extended row, output x
+                //            needs columns x .. x+2Nw = own strip + the next NSH strips (shuffles; lanes past
+                //            the row end only feed outputs x >= TW, which are never stored);
+                //  column pass: through the group's slice of cbuf (conflict-free float4 lines), each thread
+                //            filters its own strip over rows er .. er+2Nw and stores one float4 of the table.
+                // Only the 128 threads of a group share data: named barrier per group, no __syncthreads.
+                constexpr int NSH = (K - 1 + 3) / 4;
+                const int plane = p.EH * EXT_W;
+                float *cg = cbuf + (size_t)grp * S * plane + er * EXT_W + ec;
+                const bool store = er < p.TH && ec < p.TW;
+#pragma unroll
+                for (int sh = 0; sh < SH; sh++) {
+                    const int si = si0 + sh;
+                    if (!work || si >= S) continue;              // uniform per group
+#pragma unroll
+                    for (int sj = 0; sj < S; sj++) {
+                        float c[4 + 4 * NSH];
+#pragma unroll
+                        for (int x = 0; x < 4; x++) c[x] = acc[sh][sj][x];
+#pragma unroll
+                        for (int d = 1; d <= NSH; d++)
+#pragma unroll
+                            for (int x = 0; x < 4; x++) c[4 * d + x] = __shfl_down_sync(0xffffffffu, acc[sh][sj][x], d, 8);
+                        float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int v = 0; v < K; v++)
+#pragma unroll
+                            for (int x = 0; x < 4; x++) o[x] = fmaf(gk[v], c[x + v], o[x]);
+                        *reinterpret_cast<float4 *>(cg + sj * plane) = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(TG) : "memory");
+                    if (store) {
+                        float *dst = p.table + (size_t)(si * S) * plane_sz + (size_t)(ty0 + er) * p.cols_p + tx0 + ec;
+#pragma unroll
+                        for (int sj = 0; sj < S; sj++) {
+                            float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                            for (int u = 0; u < K; u++) {
+                                const float4 t = *reinterpret_cast<const float4 *>(cg + sj * plane + u * EXT_W);
+                                o[0] = fmaf(gk[u], t.x, o[0]); o[1] = fmaf(gk[u], t.y, o[1]);
+                                o[2] = fmaf(gk[u], t.z, o[2]); o[3] = fmaf(gk[u], t.w, o[3]);
+                            }
+                            *reinterpret_cast<float4 *>(dst + sj * plane_sz) = make_float4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(TG) : "memory");
+                }
+            }
+        }
+    }
+}
+
+// compile-time choice of the per-thread shift-row block: keeps SH*S*4 accumulators <= ~120
+template <int S> struct RowBlock { static constexpr int SH = S <= 9 ? 3 : (S <= 17 ? 2 : 1); };
+
+template <int S, int NWT>
+int launch_shift_table(const CUtensorMap &mapA, const CUtensorMap &mapB, const TableParams &p, dim3 grid, int nt,
+                       size_t smem, cudaStream_t st)
+{
+    auto kern = shift_table_kernel<S, RowBlock<S>::SH, NWT>;
+    static size_t attr_set = 0;
+    if (smem > attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { umpa_set_error("cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e)); return UMPA_ERR_CUDA; }
+        attr_set = smem;
+    }
+    kern<<<grid, nt, smem, st>>>(mapA, mapB, p);
+    UMPA_CUDA(cudaGetLastError());
+    return UMPA_OK;
+}
+
+template <int NWT>
+int dispatch_shift_table_s(int S, const CUtensorMap &a, const CUtensorMap &b, const TableParams &p, dim3 grid, int nt,
+                           size_t smem, cudaStream_t st)
+{
+    switch (S) {
+        case 3: return launch_shift_table<3, NWT>(a, b, p, grid, nt, smem, st);
+        case 5: return launch_shift_table<5, NWT>(a, b, p, grid, nt, smem, st);
+        case 7: return launch_shift_table<7, NWT>(a, b, p, grid, nt, smem, st);
+        case 9: return launch_shift_table<9, NWT>(a, b, p, grid, nt, smem, st);
+        case 11: return launch_shift_table<11, NWT>(a, b, p, grid, nt, smem, st);
+        case 13: return launch_shift_table<13, NWT>(a, b, p, grid, nt, smem, st);
+        case 15: return launch_shift_table<15, NWT>(a, b, p, grid, nt, smem, st);
+        case 17: return launch_shift_table<17, NWT>(a, b, p, grid, nt, smem, st);
+        case 19: return launch_shift_table<19, NWT>(a, b, p, grid, nt, smem, st);
+    }
+    umpa_set_error("table path: max_shift %d not instantiated", (S + 1) / 2);
+    return UMPA_ERR_UNSUPPORTED;
+}
+
+}  // namespace shift_table
+
+// one entry point per translation unit of shift_table_inst.cu
+#define UMPA_ST_ARGS int S, const CUtensorMap &a, const CUtensorMap &b, const shift_table::TableParams &p, dim3 grid, int nt, \
+                     size_t smem, cudaStream_t st
+int shift_table_launch_plain(UMPA_ST_ARGS);
+int shift_table_launch_nw0(UMPA_ST_ARGS);
+int shift_table_launch_nw1(UMPA_ST_ARGS);
+int shift_table_launch_nw2(UMPA_ST_ARGS);
+int shift_table_launch_nw3(UMPA_ST_ARGS);
+int shift_table_launch_nw4(UMPA_ST_ARGS);
+int shift_table_launch_nw5(UMPA_ST_ARGS);
+int shift_table_launch_nw6(UMPA_ST_ARGS);

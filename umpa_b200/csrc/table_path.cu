@@ -33,11 +33,12 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "shift_table.cuh"
 #include "walk.cuh"
 
 namespace {
 
-constexpr int SMEM_CAP = 227 * 1024;
+using namespace shift_table;
 
 // ------------------------------------------------------------------ frame conversion
 
@@ -258,278 +259,6 @@ bool moments_pick(int Nw, MomentsKernel *k, size_t *smem)
     return false;
 }
 
-// ------------------------------------------------------------------ shift tables
-//
-// table[s][p] = sum_k A_k(p+s) * B_k(p)   (FILTER: then window-filtered over p)
-//
-// One CTA owns an output tile TH x TW and produces ALL S*S shifts for it.  Work split:
-//   * the extended tile (TH + 2*halo rows, 32 columns = TW + 2*halo) is cut into strips of
-//     4 consecutive pixels; a thread owns one strip -> 8 strips per row, so every quarter
-//     warp reads one contiguous 128 B shared-memory line (conflict-free LDS.128);
-//   * G warp groups work on the same frame at the same time, group g accumulating shift rows
-//     [ (pass*G+g)*SH, +SH ): SH*S*4 FP32 accumulators per thread live in registers across all
-//     frames, so each frame tile is streamed through shared memory exactly once per pass;
-//   * frames arrive by TMA (cp.async.bulk.tensor, 3-D map over [Na][H][pitch], zero fill out
-//     of bounds) into a ring of NST stages guarded by full/empty mbarriers; thread 0 is the
-//     producer, nobody executes a per-frame __syncthreads();
-//   * epilogue (per shift row): accumulators -> shared, separable window filter (row pass in
-//     registers, column pass with 4-row register blocking), float4 stores to the table.
-
-struct TableParams {
-    float *table;                // [S*S][rows_p][cols_p]
-    const float *g;              // window factor (FILTER only)
-    int Na, Nw;
-    int oy, ox;                  // raw coordinates of table element (0,0)
-    int rows_p, cols_p;          // padded table plane
-    int TH, TW;                  // output tile
-    int EH;                      // extended tile rows (ext cols are EXT_W)
-    int AH, AP;                  // A tile rows, pitch (= TMA box width)
-    int G, npass, nstage;
-    int a_stage_floats, stage_floats;   // per-stage layout: A tile then B tile (128 B aligned)
-    int tiles_x, tiles_y;               // tile grid (the kernel is persistent over it)
-};
-
-constexpr int EXT_W = 32;          // extended tile width: one 128 B line per row
-constexpr int MAX_NT = 384;        // threads per CTA (3 groups x 16 rows x 8 strips)
-constexpr int MAX_STAGES = 8;
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// 3-D tiled TMA load: box (c0.., c1.., c2) of the tensor map -> dense smem tile, completes on `bar`
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::
-            "r"(smem_u32(dst)), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-        : "memory");
-}
-
-template <int S, int SH, bool FILTER>
-__global__ void __launch_bounds__(MAX_NT)
-shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TableParams p)
-{
-    extern __shared__ __align__(128) float sm[];
-    constexpr int HS = (S - 1) / 2;                  // max |shift|
-    // TMA needs the innermost box coordinate 16 B aligned (measured: unaligned -> illegal
-    // instruction).  The B tile origin is aligned by construction (host shifts the table
-    // origin); the A tile starts HS + DELTA columns to its left so that it is aligned too.
-    constexpr int DELTA = (4 - HS % 4) % 4;
-    constexpr int NA4 = (DELTA + S + 3 + 3) / 4;     // float4 loads covering DELTA+S+3 floats of an A row
-    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
-    __shared__ float gs[UMPA_MAX_K];
-
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int K = 2 * p.Nw + 1;
-    const int halo = FILTER ? p.Nw : 0;
-    const int TG = p.EH * (EXT_W / 4);               // threads per group
-    const int grp = tid / TG, lt = tid - grp * TG;
-    const int er = lt >> 3, ec = (lt & 7) << 2;      // strip: extended row, first extended column
-    float *cbuf = sm + (size_t)p.nstage * p.stage_floats;                // [G*S][EH][EXT_W] (FILTER only)
-    const uint32_t stage_bytes = (uint32_t)(p.AH * p.AP + p.EH * EXT_W) * sizeof(float);
-    const size_t plane_sz = (size_t)p.rows_p * p.cols_p;
-
-    if (FILTER && tid < K) gs[tid] = p.g[tid];
-    if (tid == 0) {
-        for (int s = 0; s < p.nstage; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], nt / 32); }
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    }
-    __syncthreads();
-
-    // ---- persistent CTA: tiles blockIdx.x, +gridDim.x, ... ; the frame ring runs across tiles ----
-    const int ntiles = p.tiles_x * p.tiles_y;
-    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int per_tile = p.npass * p.Na;
-    const int total = my_tiles * per_tile;
-
-    // producer state (thread 0): next (tile, frame) to request, and where
-    int pr_issued = 0, pr_tile = blockIdx.x, pr_left = per_tile, pr_frame = 0, pr_stage = 0;
-    int pr_ax = 0, pr_ay = 0, pr_bx = 0, pr_by = 0;
-    auto pr_coords = [&]() {
-        const int tyi = pr_tile / p.tiles_x, txi = pr_tile - tyi * p.tiles_x;
-        pr_by = p.oy + tyi * p.TH - halo; pr_bx = p.ox + txi * p.TW - halo;
-        pr_ay = pr_by - HS; pr_ax = pr_bx - HS - DELTA;
-    };
-    auto issue_next = [&]() {
-        float *As = sm + (size_t)pr_stage * p.stage_floats, *Bs = As + p.a_stage_floats;
-        mbar_expect_tx(&full_bar[pr_stage], stage_bytes);
-        tma_load_3d(As, &mapA, pr_ax, pr_ay, pr_frame, &full_bar[pr_stage]);
-        tma_load_3d(Bs, &mapB, pr_bx, pr_by, pr_frame, &full_bar[pr_stage]);
-        pr_issued++;
-        if (++pr_stage == p.nstage) pr_stage = 0;
-        if (++pr_frame == p.Na) pr_frame = 0;
-        if (--pr_left == 0) { pr_left = per_tile; pr_tile += gridDim.x; pr_coords(); }
-    };
-    if (tid == 0) {
-        pr_coords();
-        for (int n = 0; n < p.nstage && n < total; n++) issue_next();
-    }
-
-    int stage = 0, phase = 0;                        // consumer ring position
-    int prev_stage = 0, prev_phase = 0;
-    bool first = true;
-    float acc[SH][S][4];
-
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int tyi = tile / p.tiles_x, txi = tile - tyi * p.tiles_x;
-        const int ty0 = tyi * p.TH, tx0 = txi * p.TW;                    // table coords of the tile
-        for (int pass = 0; pass < p.npass; pass++) {
-            const int si0 = (pass * p.G + grp) * SH; // first shift row of this thread in this pass
-            const bool work = si0 < S;
-#pragma unroll
-            for (int a = 0; a < SH; a++)
-#pragma unroll
-                for (int b = 0; b < S; b++)
-#pragma unroll
-                    for (int c = 0; c < 4; c++) acc[a][b][c] = 0.f;
-
-            for (int frame = 0; frame < p.Na; frame++) {
-                if (tid == 0 && !first && pr_issued < total) {           // refill the stage the previous frame used
-                    mbar_wait(&empty_bar[prev_stage], prev_phase);
-                    issue_next();
-                }
-                first = false;
-                mbar_wait(&full_bar[stage], phase);
-                if (work) {
-                    const float *As = sm + (size_t)stage * p.stage_floats;
-                    const float *Bs = As + p.a_stage_floats;
-                    const float4 b4 = *reinterpret_cast<const float4 *>(Bs + er * EXT_W + ec);
-                    const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
-                    const float *arow0 = As + (er + si0) * p.AP + ec;
-#pragma unroll
-                    for (int sh = 0; sh < SH; sh++) {
-                        if (si0 + sh < S) {
-                            const float *arow = arow0 + sh * p.AP;
-                            float av[4 * NA4];
-#pragma unroll
-                            for (int v = 0; v < NA4; v++) {
-                                const float4 t = *reinterpret_cast<const float4 *>(arow + 4 * v);
-                                av[4 * v] = t.x; av[4 * v + 1] = t.y; av[4 * v + 2] = t.z; av[4 * v + 3] = t.w;
-                            }
-#pragma unroll
-                            for (int sj = 0; sj < S; sj++)
-#pragma unroll
-                                for (int x = 0; x < 4; x++)
-                                    acc[sh][sj][x] = fmaf(bv[x], av[DELTA + sj + x], acc[sh][sj][x]);
-                        }
-                    }
-                }
-                __syncwarp();
-                if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);     // this warp is done with the stage
-                prev_stage = stage; prev_phase = phase;
-                if (++stage == p.nstage) { stage = 0; phase ^= 1; }
-            }
-
-            // ---------------- epilogue of this pass ----------------
-            if (!FILTER) {
-                if (work) {
-#pragma unroll
-                    for (int sh = 0; sh < SH; sh++) {
-                        const int si = si0 + sh;
-                        if (si < S && ec < p.TW) {
-                            float *dst = p.table + (size_t)(si * S) * plane_sz + (size_t)(ty0 + er) * p.cols_p + tx0 + ec;
-#pragma unroll
-                            for (int sj = 0; sj < S; sj++)
-                                *reinterpret_cast<float4 *>(dst + sj * plane_sz) =
-                                    make_float4(acc[sh][sj][0], acc[sh][sj][1], acc[sh][sj][2], acc[sh][sj][3]);
-                        }
-                    }
-                }
-            } else {
-                const int plane = p.EH * EXT_W;      // one shift's row-filtered extended tile in cbuf
-                const int ostrips = p.TW / 4;        // output strips per row
-                const int rblocks = (p.TH + 3) / 4;
-                const int per_plane = rblocks * ostrips;
-                const int citems = p.G * S * per_plane;
-#pragma unroll
-                for (int sh = 0; sh < SH; sh++) {
-                    // shift rows handled in this round: si(g) = (pass*G+g)*SH + sh for g < G.
-                    // Row pass in registers: the 8 lanes of a quarter warp hold one extended row
-                    // (32 columns); output x needs columns x .. x+2Nw, fetched from the lanes to the
-                    // right with shuffles (lanes past the row end only feed unused outputs x >= TW).
-                    if (work && si0 + sh < S) {
-#pragma unroll
-                        for (int sj = 0; sj < S; sj++) {
-                            const float a0 = acc[sh][sj][0], a1 = acc[sh][sj][1], a2 = acc[sh][sj][2], a3 = acc[sh][sj][3];
-                            float w0 = a0, w1 = a1, w2 = a2, w3;
-                            float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-                            for (int v = 0; v < K; v++) {
-                                const int e = v + 3, c = e & 3;
-                                const float mine = c == 0 ? a0 : (c == 1 ? a1 : (c == 2 ? a2 : a3));
-                                w3 = __shfl_down_sync(0xffffffffu, mine, e >> 2, 8);
-                                const float gv = gs[v];
-                                o0 = fmaf(gv, w0, o0); o1 = fmaf(gv, w1, o1);
-                                o2 = fmaf(gv, w2, o2); o3 = fmaf(gv, w3, o3);
-                                w0 = w1; w1 = w2; w2 = w3;
-                            }
-                            *reinterpret_cast<float4 *>(cbuf + (grp * S + sj) * plane + er * EXT_W + ec) =
-                                make_float4(o0, o1, o2, o3);
-                        }
-                    }
-                    __syncthreads();
-                    // column pass: item = (plane q, block of 4 output rows, strip c)
-                    for (int item = tid; item < citems; item += nt) {
-                        const int q = item / per_plane, rem = item - q * per_plane;
-                        const int rb = rem / ostrips, c4 = 4 * (rem - rb * ostrips);
-                        const int g_of_q = q / S, sj = q - g_of_q * S;
-                        const int si = (pass * p.G + g_of_q) * SH + sh;
-                        if (si >= S) continue;
-                        const float *src = cbuf + q * plane + (4 * rb) * EXT_W + c4;
-                        float o[4][4];
-#pragma unroll
-                        for (int a = 0; a < 4; a++)
-#pragma unroll
-                            for (int b = 0; b < 4; b++) o[a][b] = 0.f;
-                        const int nrows = min(K + 3, p.EH - 4 * rb);
-                        for (int u = 0; u < nrows; u++) {        // input row 4*rb + u feeds output rows u-K+1 .. u
-                            const float4 t = *reinterpret_cast<const float4 *>(src + u * EXT_W);
-#pragma unroll
-                            for (int a = 0; a < 4; a++) {
-                                const int tap = u - a;
-                                if (tap >= 0 && tap < K) {
-                                    const float gu = gs[tap];
-                                    o[a][0] = fmaf(gu, t.x, o[a][0]); o[a][1] = fmaf(gu, t.y, o[a][1]);
-                                    o[a][2] = fmaf(gu, t.z, o[a][2]); o[a][3] = fmaf(gu, t.w, o[a][3]);
-                                }
-                            }
-                        }
-                        float *dst = p.table + (size_t)(si * S + sj) * plane_sz + (size_t)(ty0 + 4 * rb) * p.cols_p + tx0 + c4;
-#pragma unroll
-                        for (int a = 0; a < 4; a++)
-                            if (4 * rb + a < p.TH)
-                                *reinterpret_cast<float4 *>(dst + (size_t)a * p.cols_p) = make_float4(o[a][0], o[a][1], o[a][2], o[a][3]);
-                    }
-                    __syncthreads();
-                }
-            }
-        }
-    }
-}
-
 // ------------------------------------------------------------------ table-driven walk
 
 struct WalkParams {
@@ -690,41 +419,21 @@ int make_stack_map(CUtensorMap *map, const float *base, int Na, int H, int W, in
     return UMPA_OK;
 }
 
-// compile-time choice of the per-thread shift-row block: keeps SH*S*4 accumulators <= ~120
-template <int S> struct RowBlock { static constexpr int SH = S <= 9 ? 3 : (S <= 17 ? 2 : 1); };
-
-template <int S, bool FILTER>
-int launch_shift_table(const CUtensorMap &mapA, const CUtensorMap &mapB, const TableParams &p, dim3 grid, int nt,
-                       size_t smem, cudaStream_t st)
+// filter = false: plain table; true: window filter of half-width p.Nw (0..6)
+int dispatch_shift_table(bool filter, int S, const CUtensorMap &a, const CUtensorMap &b, const TableParams &p, dim3 grid,
+                         int nt, size_t smem, cudaStream_t st)
 {
-    auto kern = shift_table_kernel<S, RowBlock<S>::SH, FILTER>;
-    static size_t attr_set = 0;
-    if (smem > attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { umpa_set_error("cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e)); return UMPA_ERR_CUDA; }
-        attr_set = smem;
+    if (!filter) return shift_table_launch_plain(S, a, b, p, grid, nt, smem, st);
+    switch (p.Nw) {
+        case 0: return shift_table_launch_nw0(S, a, b, p, grid, nt, smem, st);
+        case 1: return shift_table_launch_nw1(S, a, b, p, grid, nt, smem, st);
+        case 2: return shift_table_launch_nw2(S, a, b, p, grid, nt, smem, st);
+        case 3: return shift_table_launch_nw3(S, a, b, p, grid, nt, smem, st);
+        case 4: return shift_table_launch_nw4(S, a, b, p, grid, nt, smem, st);
+        case 5: return shift_table_launch_nw5(S, a, b, p, grid, nt, smem, st);
+        case 6: return shift_table_launch_nw6(S, a, b, p, grid, nt, smem, st);
     }
-    kern<<<grid, nt, smem, st>>>(mapA, mapB, p);
-    UMPA_CUDA(cudaGetLastError());
-    return UMPA_OK;
-}
-
-template <bool FILTER>
-int dispatch_shift_table(int S, const CUtensorMap &a, const CUtensorMap &b, const TableParams &p, dim3 grid, int nt,
-                         size_t smem, cudaStream_t st)
-{
-    switch (S) {
-        case 3: return launch_shift_table<3, FILTER>(a, b, p, grid, nt, smem, st);
-        case 5: return launch_shift_table<5, FILTER>(a, b, p, grid, nt, smem, st);
-        case 7: return launch_shift_table<7, FILTER>(a, b, p, grid, nt, smem, st);
-        case 9: return launch_shift_table<9, FILTER>(a, b, p, grid, nt, smem, st);
-        case 11: return launch_shift_table<11, FILTER>(a, b, p, grid, nt, smem, st);
-        case 13: return launch_shift_table<13, FILTER>(a, b, p, grid, nt, smem, st);
-        case 15: return launch_shift_table<15, FILTER>(a, b, p, grid, nt, smem, st);
-        case 17: return launch_shift_table<17, FILTER>(a, b, p, grid, nt, smem, st);
-        case 19: return launch_shift_table<19, FILTER>(a, b, p, grid, nt, smem, st);
-    }
-    umpa_set_error("table path: max_shift %d not instantiated", (S + 1) / 2);
+    umpa_set_error("table path: Nw %d not instantiated", p.Nw);
     return UMPA_ERR_UNSUPPORTED;
 }
 
@@ -927,7 +636,7 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         px.table = (float *)m->tabX.p;
         px.tiles_x = px.cols_p / px.TW; px.tiles_y = px.rows_p / px.TH;
         dim3 grid(std::min(px.tiles_x * px.tiles_y, m->sm_count * ctas_per_sm()));
-        if ((rc = dispatch_shift_table<true>(S, ma, mb, px, grid, ntx, smx, st))) return rc;
+        if ((rc = dispatch_shift_table(true, S, ma, mb, px, grid, ntx, smx, st))) return rc;
         m->last_launches++;
         if ((rc = stage_check("cross table", st))) return rc;
     }
@@ -941,7 +650,7 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         pm.table = (float *)m->tabM.p;
         pm.tiles_x = pm.cols_p / pm.TW; pm.tiles_y = pm.rows_p / pm.TH;
         dim3 grid(std::min(pm.tiles_x * pm.tiles_y, m->sm_count * ctas_per_sm()));
-        if ((rc = dispatch_shift_table<false>(S, ma, mb, pm, grid, ntm, smm, st))) return rc;
+        if ((rc = dispatch_shift_table(false, S, ma, mb, pm, grid, ntm, smm, st))) return rc;
         m->last_launches++;
         if ((rc = stage_check("mean table", st))) return rc;
     }
