@@ -310,9 +310,12 @@ def ours(args, cfg):
         steps_e = max(2, min(args.steps, 10))
         d2h = 0
 
+        stream_info = {}
+
         def one():
             m = cls(list(sam_np), list(ref_np), window_size=cfg["Nw"], max_shift=cfg["ms"])
             r = m.match(quiet=True, debug=False, **kw_h)
+            stream_info.update(m.last_stream_info)
             return sum(v.nbytes for v in r.values())
         for _ in range(2):
             d2h = one()
@@ -328,7 +331,11 @@ def ours(args, cfg):
                "h2d_bytes_per_step": int(sum_over_ranks(float(sam_np.nbytes + ref_np.nbytes))),
                "d2h_bytes_per_step": int(sum_over_ranks(float(d2h))), "steps": steps_e,
                "api": "%s(sam, ref, window_size, max_shift).match(debug=False) on pinned host float64 arrays"
-                      % cls.__name__}
+                      % cls.__name__,
+               "pipeline": dict(stream_info, note="upload / kernels / download overlapped in row bands; host_threads "
+                                "convert the lower host_rows_per_frame rows of every frame to centred FP32 in pinned "
+                                "staging while the DMA engine uploads the upper rows as FP64 (UMPA_HOST_THREADS=0 "
+                                "disables the host part)")}
 
     # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------------------
     cpu = None
@@ -352,19 +359,29 @@ def ours(args, cfg):
         px_rank = band_rows * N1                         # rank 0's launch processes its band
         t_cross = stage_ms[1] * 1e-3
         f_alg = algorithmic_flops_per_px(cfg)
-        f_exe = 2. * executed_fma_per_px_cross(cfg)
+        dfk = cfg["kind"] == "DFKernel"
+        if dfk:     # the blur-table kernel executes the direct form: patch blur + t5 partials + q3 (kernel_path.cu)
+            S_, K_ = 2 * cfg["ms"] - 1, 2 * cfg["Nw"] + 1
+            f_exe = 2. * cfg["Na"] * ((K_ + S_ - 1) ** 2 * 17 ** 2 + (K_ + S_ - 1) * K_ * K_ * S_ + (K_ + S_ - 1) ** 2)
+            kname = "ktable_kernel<Nw=%d,S=%d> (per-pixel blur tables)" % (cfg["Nw"], S_)
+            note = ("achieved = SURVEY 8d direct-form flop/px x px / kernel time; the kernel executes that form "
+                    "(blur of the (K+S-1)^2 patch per frame), executed/algorithmic = %.2f")
+        else:
+            f_exe = 2. * executed_fma_per_px_cross(cfg)
+            kname = "shift_table_kernel<S=%d,Nw=%d> (cross table)" % (2 * cfg["ms"] - 1, cfg["Nw"])
+            note = ("achieved = 2*S^2*Na*K^2 flop/px (SURVEY 8d, direct form) x px / kernel time; the kernel "
+                    "sums over frames first and filters once, so it executes %.0fx fewer FMAs")
         ach = f_alg * px_rank / t_cross / 1e12
         exe = f_exe * px_rank / t_cross / 1e12
-        roof = {"bound": "fp32_fma", "kernel": "shift_table_kernel<S=%d,FILTER> (cross table)" % (2 * cfg["ms"] - 1),
+        roof = {"bound": "fp32_fma", "kernel": kname,
                 "achieved": ach, "peak": peak.value, "unit": "TFLOP/s", "frac": ach / peak.value,
                 "peak_source": "FFMA probe measured in this run on this GPU (umpa_fma_peak); nominal %.1f"
                                % (sms.value * 128 * 2 * (peaks.get("sm_max_mhz", 1965.) * 1e6) / 1e12),
                 "traffic": None, "kernel_ms": stage_ms[1],
                 "executed_tflops": exe, "executed_frac": exe / peak.value,
-                "note": "achieved = 2*S^2*Na*K^2 flop/px (SURVEY 8d, direct form) x px / kernel time; the kernel "
-                        "sums over frames first and filters once, so it executes %.0fx fewer FMAs" % (f_alg / f_exe),
-                "stage_ms": {"moments": stage_ms[0], "cross_table": stage_ms[1], "mean_table": stage_ms[2],
-                             "walk": stage_ms[3]}}
+                "note": note % ((f_exe / f_alg) if dfk else (f_alg / f_exe)),
+                "stage_ms": {"moments": stage_ms[0], "blur_table" if dfk else "cross_table": stage_ms[1],
+                             "mean_table": stage_ms[2], "walk": stage_ms[3]}}
     alg_bytes = 2. * cfg["Na"] * cfg["H"] * cfg["W"] * 4 + 6 * 4. * total_px
     line = {"metric": "output pixels/s", "value": value, "unit": "output pixels/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,

@@ -95,12 +95,18 @@ UMPA_API void umpa_destroy(umpa_model *m);
 /* ---- inputs --------------------------------------------------------------
  * The reference keeps raw double* into the caller's numpy arrays
  * (vector<T*> sam/ref/mask, UMPA/model.pyx:235-262).  Here the frames are staged
- * once into device memory owned by the handle: FP64 copies (LAZY path) and,
- * when the TABLE path is eligible, mean-centred FP32 stacks.
+ * into device memory owned by the handle: FP64 copies (LAZY path, cost/min hooks)
+ * and, when a TABLE path is eligible, centred FP32 stacks.
  *   sam, ref : Na pointers to row-major float64 frames of shape dim[k]
  *   mask     : Na pointers or NULL (no masks)
- *   on_device: 0 = host pointers (pageable or pinned), 1 = device pointers
- * The caller's buffers are not referenced after the call returns. */
+ *   on_device: 0 = host pointers (pageable or pinned), copied before the call returns;
+ *              1 = device pointers, copied before the call returns;
+ *              2 = host pointers, copy DEFERRED: like the reference, the handle keeps the
+ *                  pointers and the buffers must stay valid and unchanged for its lifetime.
+ *                  The first umpa_match_host() then pipelines upload, kernels and download
+ *                  in row bands (host threads convert part of the rows to centred FP32 on the
+ *                  way, see UMPA_HOST_THREADS in INTEGRATION.md); any other entry point
+ *                  uploads whatever it needs first. */
 UMPA_API int umpa_set_frames(umpa_model *m, const double *const *sam, const double *const *ref,
                     const double *const *mask, int on_device, void *stream);
 
@@ -151,6 +157,9 @@ UMPA_API int umpa_coverage(umpa_model *m, const int32_t roi[6], double *out, int
 /* which path the last umpa_match used (UMPA_PATH_TABLE / UMPA_PATH_LAZY) and how
  * many kernels it launched */
 UMPA_API int umpa_last_match_info(const umpa_model *m, int *path, int *kernel_launches);
+/* how the last pipelined umpa_match_host ran: row bands, host conversion threads, rows per
+ * frame that crossed PCIe as host-converted FP32 (all 0 when the match was not pipelined) */
+UMPA_API int umpa_last_stream_info(const umpa_model *m, int *bands, int *host_threads, int *host_rows);
 /* device time of the stages of the last TABLE-path match, measured with CUDA events on the
  * launching stream when profiling is enabled via umpa_set_profiling(m, 1):
  * ms[0] moments, ms[1] cross table, ms[2] mean table, ms[3] walk; returns count written */

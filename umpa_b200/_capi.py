@@ -13,7 +13,7 @@ PATH_NAMES = {0: "none", 1: "table", 2: "lazy"}
 
 EXPORTS = ("umpa_create", "umpa_destroy", "umpa_set_frames", "umpa_set_window", "umpa_set_option",
            "umpa_get_option", "umpa_match", "umpa_match_host", "umpa_cost", "umpa_min", "umpa_coverage",
-           "umpa_last_match_info", "umpa_set_profiling", "umpa_last_stage_ms", "umpa_device_bytes",
+           "umpa_last_match_info", "umpa_last_stream_info", "umpa_set_profiling", "umpa_last_stage_ms", "umpa_device_bytes",
            "umpa_fma_peak", "umpa_last_error", "umpa_version")
 
 
@@ -65,6 +65,8 @@ def lib():
     L.umpa_coverage.argtypes = [vp, ip, vp, C.c_int, vp]
     L.umpa_last_match_info.restype = C.c_int
     L.umpa_last_match_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.umpa_last_stream_info.restype = C.c_int
+    L.umpa_last_stream_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.umpa_set_profiling.restype = C.c_int
     L.umpa_set_profiling.argtypes = [vp, C.c_int]
     L.umpa_last_stage_ms.restype = C.c_int

@@ -6,8 +6,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 
 #include "common.cuh"
 
@@ -224,7 +227,7 @@ void free_frames(umpa_model *m)
         if (p) cudaFree(p);
     m->d_consts = nullptr;
     m->h_sam.clear(); m->h_ref.clear(); m->h_mask.clear();
-    m->host_pending = false;
+    m->host_pending = false; m->fp64_missing = false;
     m->d_sam64 = m->d_ref64 = m->d_mask64 = nullptr;
     m->d_sam_ptrs = m->d_ref_ptrs = m->d_mask_ptrs = nullptr;
     m->d_sam32 = m->d_ref32 = nullptr;
@@ -247,10 +250,11 @@ int zero_outputs(const umpa_outputs &o, size_t n, cudaStream_t st)
     return UMPA_OK;
 }
 
-// Deferred host frames (umpa_set_frames on_device = 2): copy everything now, on `st`.
+// Deferred host frames (umpa_set_frames on_device = 2): bring the FP64 stacks (and, if they are not
+// there yet, the centred FP32 stacks) to the device now, on `st`.
 int ensure_resident(umpa_model *m, cudaStream_t st)
 {
-    if (!m->host_pending) return UMPA_OK;
+    if (!m->host_pending && !m->fp64_missing) return UMPA_OK;
     const std::vector<const double *> *srcs[3] = {&m->h_sam, &m->h_ref, &m->h_mask};
     double *dsts[3] = {m->d_sam64, m->d_ref64, m->d_mask64};
     for (int a = 0; a < 3; a++)
@@ -258,12 +262,17 @@ int ensure_resident(umpa_model *m, cudaStream_t st)
             const size_t n = (size_t)m->dim[2 * k] * m->dim[2 * k + 1];
             UMPA_CUDA(cudaMemcpyAsync(dsts[a] + m->frame_off[k], (*srcs[a])[k], n * sizeof(double), cudaMemcpyHostToDevice, st));
         }
-    int rc = table_prepare_frames(m, st);
-    if (rc) return rc;
+    if (m->host_pending) {
+        int rc = table_prepare_frames(m, st);
+        if (rc) return rc;
+    }
     UMPA_CUDA(cudaStreamSynchronize(st));
-    m->host_pending = false;
+    m->host_pending = false; m->fp64_missing = false;
     return UMPA_OK;
 }
+
+// the table paths read the centred FP32 stacks only
+int ensure_fp32(umpa_model *m, cudaStream_t st) { return m->host_pending ? ensure_resident(m, st) : UMPA_OK; }
 
 int ensure_streams(umpa_model *m)
 {
@@ -275,7 +284,7 @@ int ensure_streams(umpa_model *m)
 }
 
 // path selection + launch for one (sub-)ROI; everything is resident (or being streamed in by the caller)
-int match_view(umpa_model *m, const RoiView &v, const umpa_outputs &out, cudaStream_t st)
+int match_view(umpa_model *m, const RoiView &v, const umpa_outputs &out, cudaStream_t st, bool streaming = false)
 {
     const size_t n = (size_t)v.N0 * v.N1;
     int rc;
@@ -290,8 +299,13 @@ int match_view(umpa_model *m, const RoiView &v, const umpa_outputs &out, cudaStr
             return UMPA_ERR_UNSUPPORTED;
         }
     }
-    if (use_table) { m->last_path = UMPA_PATH_TABLE; return table_match(m, v, out, st); }
+    if (use_table) {
+        m->last_path = UMPA_PATH_TABLE;
+        if (!streaming && (rc = ensure_fp32(m, st))) return rc;
+        return table_match(m, v, out, st);
+    }
     m->last_path = UMPA_PATH_LAZY;
+    if ((rc = ensure_resident(m, st))) return rc;
     return lazy_match(m, v, out, st);
 }
 
@@ -328,16 +342,34 @@ int download_outputs(const umpa_outputs &host, const umpa_outputs &dev, size_t n
     return UMPA_OK;
 }
 
-// The pipelined host-to-host match: frames still in host memory are uploaded in row bands on a
-// copy stream while the kernels of the previous band run and the maps of the band before that go
-// back to the host.  Band b needs input rows below off0 + step0*(r1-1) + padding only, so its
-// kernels start as soon as those rows (and the sampled rows that define the centring constants)
-// have landed.  Pixels are independent: the result is the one the unpipelined path gives.
+// Pinned FP32 staging for the rows the host converts (grow-only, shared by all models of the process).
+struct HostStage {
+    std::mutex mu;
+    float *p = nullptr;
+    size_t bytes = 0;
+} g_stage;
+
+int host_threads()
+{
+    if (const char *e = getenv("UMPA_HOST_THREADS")) return std::max(0, atoi(e));
+    const int hw = (int)std::thread::hardware_concurrency();
+    return std::max(0, std::min(12, hw - 4));
+}
+
+// The pipelined host-to-host match.  Frames still in host memory go up in row bands on a copy stream
+// while the kernels of the previous band run and the maps of the band before that go back to the host.
+// Band b needs input rows below off0 + step0*(r1-1) + padding only, so its kernels start as soon as
+// those rows have landed.  PCIe is the critical path (1.68 GB of FP64 for config 2 against ~4 ms of
+// kernels), so host threads shorten it: they take the centring constants from the sampled rows and
+// convert the LOWER part of every frame to centred FP32 in pinned staging (same arithmetic as
+// center_frames: FP64 subtract, one rounding) while the DMA engine is busy with the upper part in
+// FP64; the converted rows then cross at half the bytes, straight into the FP32 stacks.
+// Pixels are independent: the result is the one the unpipelined path gives for the same constants.
 int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, const umpa_outputs &host)
 {
-    const int Na = m->Na, H = m->H, W = m->W;
+    const int Na = m->Na, H = m->H, W = m->W, pitch = m->pitch;
     // bands: equal slices of the output rows, the last one halved twice so that little work is left
-    // when the final rows arrive (the upload is the critical path; kernels and download hide behind it)
+    // when the final rows arrive (kernels and download hide behind the upload)
     std::vector<int> edge;                      // band b = output rows [edge[b], edge[b+1])
     {
         int nu = std::max(1, std::min(12, v.N0 / 256));
@@ -352,6 +384,42 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
         }
     }
     const int nb = (int)edge.size() - 1;
+    std::vector<int> need(nb);                  // band b needs input rows [0, need[b])
+    for (int b = 0; b < nb; b++)
+        need[b] = b == nb - 1 ? H : std::min(H, v.off0 + v.step0 * (edge[b + 1] - 1) + m->padding + 1);
+
+    // host conversion: rows [Yc, H) of every frame are converted by nthr host threads
+    int nthr = nb > 1 ? host_threads() : 0;
+    int Yc = H;
+    if (nthr > 0) {
+        // balance: DMA time (1 - x/2) D / B  ==  host time x D / Rc   (x = converted fraction)
+        const double Rc = std::min(85., 6.5 * nthr), Bp = 55.;
+        double x = 1. / (Bp / Rc + .5);
+        // pageable frames go through the driver's own staging at a fraction of the pinned rate: convert everything
+        cudaPointerAttributes pa{};
+        if (cudaPointerGetAttributes(&pa, m->h_sam[0]) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered) x = 1.;
+        cudaGetLastError();
+        if (const char *e = getenv("UMPA_HOST_FRAC")) x = atof(e);
+        x = std::max(0., std::min(1., x));
+        Yc = H - (int)(x * H);
+        if (Yc >= H) nthr = 0;
+    }
+    const int HC = H - Yc;                      // converted rows per frame
+    std::unique_lock<std::mutex> stage_lock(g_stage.mu, std::defer_lock);
+    if (nthr > 0) {
+        stage_lock.lock();
+        const size_t want = (size_t)2 * Na * HC * pitch * sizeof(float);
+        if (g_stage.bytes < want) {
+            if (g_stage.p) cudaFreeHost(g_stage.p);
+            g_stage.p = nullptr; g_stage.bytes = 0;
+            if (cudaHostAlloc((void **)&g_stage.p, want, cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                nthr = 0; Yc = H;                // no pinned memory: plain DMA path
+                stage_lock.unlock();
+            } else g_stage.bytes = want;
+        }
+    }
+
     // frames that are equally spaced slices of one host stack go up with one 2-D copy per stack and band
     auto spacing = [&](const std::vector<const double *> &h) -> ptrdiff_t {
         if (Na < 2) return (ptrdiff_t)H * W;
@@ -361,9 +429,52 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
         return d;
     };
     const ptrdiff_t gap_s = spacing(m->h_sam), gap_r = spacing(m->h_ref);
+
+    // ---- host workers: constants first, then conversion jobs in the order the bands need them ----
+    struct Job { int band, stack, frame, y0, y1; };
+    std::vector<Job> jobs;
+    std::vector<int> cy0(nb, 0), cy1(nb, 0);    // converted rows that band b waits for: [cy0, cy1)
+    {
+        int hi = Yc;
+        for (int b = 0; b < nb && nthr > 0; b++) {
+            cy0[b] = hi; cy1[b] = std::max(hi, need[b]);
+            hi = cy1[b];
+            for (int k = 0; k < Na && cy1[b] > cy0[b]; k++)
+                for (int a = 0; a < 2; a++) jobs.push_back({b, a, k, cy0[b], cy1[b]});
+        }
+    }
+    std::vector<double> mu(2 * Na, 0.);
+    std::unique_ptr<std::atomic<int>[]> left(new std::atomic<int>[nb]);
+    for (int b = 0; b < nb; b++) left[b].store(nthr > 0 && cy1[b] > cy0[b] ? 2 * Na : 0);
+    std::atomic<int> next_mean{0}, means_done{0}, next_job{0};
+    std::atomic<bool> abort_flag{false};
+    const int rs = table_row_step(H);
+    auto worker = [&]() {
+        for (;;) {
+            const int f = next_mean.fetch_add(1);
+            if (f >= 2 * Na) break;
+            mu[f] = host_sampled_mean(f < Na ? m->h_sam[f] : m->h_ref[f - Na], H, W, rs);
+        }
+        means_done.fetch_add(1, std::memory_order_acq_rel);
+        while (means_done.load(std::memory_order_acquire) < nthr) std::this_thread::yield();
+        for (;;) {
+            const int j = next_job.fetch_add(1);
+            if (j >= (int)jobs.size() || abort_flag.load()) break;
+            const Job &q = jobs[j];
+            const double *src = (q.stack == 0 ? m->h_sam[q.frame] : m->h_ref[q.frame]) + (size_t)q.y0 * W;
+            float *dst = g_stage.p + ((size_t)(q.stack * Na + q.frame) * HC + (q.y0 - Yc)) * pitch;
+            host_center_rows(dst, src, q.y1 - q.y0, W, pitch, mu[q.stack == 0 ? q.frame : Na + q.frame]);
+            left[q.band].fetch_sub(1, std::memory_order_acq_rel);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthr; t++) pool.emplace_back(worker);
+
     std::vector<cudaEvent_t> ev(2 * nb + 1, nullptr);
     int rc = UMPA_OK;
     auto fail = [&](int code) {
+        abort_flag.store(true);
+        for (auto &t : pool) t.join();
         cudaStreamSynchronize(m->s_copy); cudaStreamSynchronize(m->s_comp); cudaStreamSynchronize(m->s_out);
         for (auto e : ev) if (e) cudaEventDestroy(e);
         return code;
@@ -372,7 +483,7 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
         umpa_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return fail(UMPA_ERR_CUDA); } } while (0)
     const bool trace = getenv("UMPA_STREAM_TRACE") != nullptr;     // timeline of the three streams on stderr
     for (auto &e : ev) ST_CUDA(cudaEventCreateWithFlags(&e, trace ? cudaEventDefault : cudaEventDisableTiming));
-    std::vector<cudaEvent_t> tev;                // trace only: [start, sampled rows, then per band: copy, comp, out]
+    std::vector<cudaEvent_t> tev;                // trace only: [start, constants, then per band: copy, comp, out]
     auto mark = [&](cudaStream_t st) {
         if (!trace) return;
         cudaEvent_t e = nullptr;
@@ -383,18 +494,9 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
     if (trace) { cudaStreamSynchronize(m->s_copy); cudaStreamSynchronize(m->s_comp); }
     mark(m->s_copy);
 
-    // 0. the sampled rows first: they define the centring constants
-    const int rs = table_row_step(H), nrs = (H + rs - 1) / rs;
     const size_t rowb = (size_t)W * sizeof(double);
-    if (nb > 1)                                 // (one band: everything is up before the constants are taken)
-        for (int k = 0; k < Na; k++) {
-            ST_CUDA(cudaMemcpy2DAsync(m->d_sam64 + m->frame_off[k], rs * rowb, m->h_sam[k], rs * rowb, rowb, nrs,
-                                      cudaMemcpyHostToDevice, m->s_copy));
-            ST_CUDA(cudaMemcpy2DAsync(m->d_ref64 + m->frame_off[k], rs * rowb, m->h_ref[k], rs * rowb, rowb, nrs,
-                                      cudaMemcpyHostToDevice, m->s_copy));
-        }
-    // rows [y0, y1) of every frame of one stack
-    auto upload_rows = [&](double *dst, const std::vector<const double *> &h, ptrdiff_t gap, int y0, int y1) -> cudaError_t {
+    // FP64 rows [y0, y1) of every frame of one stack -> FP64 device stack
+    auto upload64 = [&](double *dst, const std::vector<const double *> &h, ptrdiff_t gap, int y0, int y1) -> cudaError_t {
         const size_t bytes = (size_t)(y1 - y0) * rowb;
         if (gap > 0)
             return cudaMemcpy2DAsync(dst + (size_t)y0 * W, (size_t)H * rowb, h[0] + (size_t)y0 * W, (size_t)gap * sizeof(double),
@@ -406,16 +508,44 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
         }
         return cudaSuccess;
     };
+    // converted rows [y0, y1) (>= Yc) of every frame of one stack: staging -> centred FP32 device stack
+    auto upload32 = [&](float *dst, int stack, int y0, int y1) -> cudaError_t {
+        const size_t rb = (size_t)pitch * sizeof(float);
+        return cudaMemcpy2DAsync(dst + (size_t)y0 * pitch, (size_t)H * rb, g_stage.p + ((size_t)stack * Na * HC + (y0 - Yc)) * pitch,
+                                 (size_t)HC * rb, (size_t)(y1 - y0) * rb, Na, cudaMemcpyHostToDevice, m->s_copy);
+    };
+
+    // 0. constants: from the host workers, or (no workers) from the sampled rows uploaded ahead of the bands
+    if (nthr == 0 && nb > 1) {
+        const int nrs = (H + rs - 1) / rs;
+        for (int k = 0; k < Na; k++) {
+            ST_CUDA(cudaMemcpy2DAsync(m->d_sam64 + m->frame_off[k], rs * rowb, m->h_sam[k], rs * rowb, rowb, nrs,
+                                      cudaMemcpyHostToDevice, m->s_copy));
+            ST_CUDA(cudaMemcpy2DAsync(m->d_ref64 + m->frame_off[k], rs * rowb, m->h_ref[k], rs * rowb, rowb, nrs,
+                                      cudaMemcpyHostToDevice, m->s_copy));
+        }
+    }
     mark(m->s_copy);
-    int up_hi = 0;                              // rows [0, up_hi) are uploaded and centred
+    int up_hi = 0;                              // rows [0, up_hi) are on the device and centred
     bool have_means = false;
     int launches = 0;
     for (int b = 0; b < nb; b++) {
         const int r0 = edge[b], r1 = edge[b + 1];
-        const int need_hi = b == nb - 1 ? H : std::min(H, v.off0 + v.step0 * (r1 - 1) + m->padding + 1);
-        if (need_hi > up_hi) {
-            ST_CUDA(upload_rows(m->d_sam64, m->h_sam, gap_s, up_hi, need_hi));
-            ST_CUDA(upload_rows(m->d_ref64, m->h_ref, gap_r, up_hi, need_hi));
+        const int hi = std::max(up_hi, need[b]);
+        const int d1 = std::min(hi, Yc);         // FP64 part [up_hi, d1), converted part [max(up_hi, Yc), hi)
+        if (d1 > up_hi) {
+            ST_CUDA(upload64(m->d_sam64, m->h_sam, gap_s, up_hi, d1));
+            ST_CUDA(upload64(m->d_ref64, m->h_ref, gap_r, up_hi, d1));
+        }
+        if (!have_means && nthr > 0) {           // the first FP64 rows are on their way; now the constants
+            while (means_done.load(std::memory_order_acquire) < nthr) std::this_thread::yield();
+            if ((rc = table_set_means(m, mu.data(), m->s_comp))) return fail(rc);
+            have_means = true;
+        }
+        if (hi > std::max(up_hi, Yc)) {
+            while (left[b].load(std::memory_order_acquire) > 0) std::this_thread::yield();
+            ST_CUDA(upload32(m->d_sam32, 0, std::max(up_hi, Yc), hi));
+            ST_CUDA(upload32(m->d_ref32, 1, std::max(up_hi, Yc), hi));
         }
         ST_CUDA(cudaEventRecord(ev[2 * b], m->s_copy));
         mark(m->s_copy);
@@ -424,8 +554,8 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
             if ((rc = table_means(m, m->s_comp))) return fail(rc);
             have_means = true;
         }
-        if ((rc = table_center_rows(m, up_hi, std::max(up_hi, need_hi), m->s_comp))) return fail(rc);
-        up_hi = std::max(up_hi, need_hi);
+        if ((rc = table_center_rows(m, up_hi, std::max(up_hi, d1), m->s_comp))) return fail(rc);
+        up_hi = hi;
         RoiView vb = v;
         vb.off0 = v.off0 + v.step0 * r0; vb.N0 = r1 - r0;
         const size_t px0 = (size_t)r0 * v.N1;
@@ -433,7 +563,7 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
         if (v.cover) vb.cover = v.cover + px0;
         const umpa_outputs db = offset_outputs(dev, px0);
         m->last_launches = 0;
-        if ((rc = match_view(m, vb, db, m->s_comp))) return fail(rc);
+        if ((rc = match_view(m, vb, db, m->s_comp, true))) return fail(rc);
         launches += m->last_launches;
         ST_CUDA(cudaEventRecord(ev[2 * b + 1], m->s_comp));
         mark(m->s_comp);
@@ -442,6 +572,8 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
         mark(m->s_out);
     }
     m->last_launches = launches;
+    for (auto &t : pool) t.join();
+    pool.clear();
     ST_CUDA(cudaStreamSynchronize(m->s_out));
     ST_CUDA(cudaStreamSynchronize(m->s_comp));
     ST_CUDA(cudaStreamSynchronize(m->s_copy));
@@ -449,7 +581,7 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
     if (trace) {
         float t = 0.f;
         cudaEventElapsedTime(&t, tev[0], tev[1]);
-        fprintf(stderr, "[umpa stream] %d bands; sampled rows up at %.2f ms\n", nb, t);
+        fprintf(stderr, "[umpa stream] %d bands, %d host threads convert rows >= %d of %d; sampled rows up at %.2f ms\n", nb, nthr, Yc, H, t);
         for (int b = 0; b < nb; b++) {
             float tc = 0.f, tk = 0.f, to = 0.f;
             cudaEventElapsedTime(&tc, tev[0], tev[2 + 3 * b]);
@@ -461,6 +593,8 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
     }
     for (auto e : ev) if (e) cudaEventDestroy(e);
     m->host_pending = false;
+    m->fp64_missing = Yc < H;
+    m->stream_bands = nb; m->stream_threads = nthr; m->stream_host_rows = HC;
     return UMPA_OK;
 }
 
@@ -520,6 +654,7 @@ void umpa_destroy(umpa_model *m)
         if (s->p) pool_free(s->p, s->bytes);
     for (cudaStream_t st : {m->s_copy, m->s_comp, m->s_out})
         if (st) cudaStreamDestroy(st);
+    if (m->h_small) cudaFreeHost(m->h_small);
     for (void *p : {(void *)m->d_dim, (void *)m->d_pos, (void *)m->d_win, (void *)m->d_quad, (void *)m->d_g})
         if (p) cudaFree(p);
     for (int i = 0; i < 5; i++)
@@ -623,7 +758,6 @@ int umpa_match(umpa_model *m, const int32_t roi[6], const double uv0[2], const d
     if ((rc = check_roi_bounds(m, v))) return rc;
     v.abc = abc; v.cover = cover; v.cover_threshold = cover_threshold;
     if (m->kind == UMPA_DFKERNEL && !abc) { umpa_set_error("abc array has to be provided"); return UMPA_ERR_ARG; }   // model.pyx:973-974
-    if ((rc = ensure_resident(m, st))) return rc;
     return match_view(m, v, *out, st);
 }
 
@@ -662,7 +796,6 @@ int umpa_match_host(umpa_model *m, const int32_t roi[6], const double uv0[2], co
     if (m->host_pending && m->path_opt != UMPA_PATH_LAZY && !getenv("UMPA_NO_STREAMING") && table_eligible(m, v, nullptr))
         return streamed_match(m, v, d, *out);
 
-    if ((rc = ensure_resident(m, m->s_comp))) return rc;
     if ((rc = match_view(m, v, d, m->s_comp))) return rc;
     if ((rc = download_outputs(*out, d, n, m->s_comp))) return rc;
     cudaError_t e = cudaStreamSynchronize(m->s_comp);
@@ -717,6 +850,15 @@ int umpa_last_match_info(const umpa_model *m, int *path, int *kernel_launches)
     if (!m) { umpa_set_error("NULL model"); return UMPA_ERR_ARG; }
     if (path) *path = m->last_path;
     if (kernel_launches) *kernel_launches = m->last_launches;
+    return UMPA_OK;
+}
+
+int umpa_last_stream_info(const umpa_model *m, int *bands, int *host_threads, int *host_rows)
+{
+    if (!m) { umpa_set_error("NULL model"); return UMPA_ERR_ARG; }
+    if (bands) *bands = m->stream_bands;
+    if (host_threads) *host_threads = m->stream_threads;
+    if (host_rows) *host_rows = m->stream_host_rows;
     return UMPA_OK;
 }
 

@@ -92,9 +92,12 @@ struct umpa_model {
     // host frames whose upload is deferred to the first match (umpa_set_frames with on_device = 2):
     // umpa_match_host then pipelines upload, kernels and download in row bands
     std::vector<const double *> h_sam, h_ref, h_mask;
-    bool host_pending = false;
+    bool host_pending = false;                   // nothing of the host frames is on the device yet
+    bool fp64_missing = false;                   // FP32 stacks complete, FP64 stacks not (rows the host converted)
     cudaStream_t s_copy = nullptr, s_comp = nullptr, s_out = nullptr;
     Scratch outbuf;
+    int stream_bands = 0, stream_threads = 0, stream_host_rows = 0;   // how the last pipelined match ran
+    void *h_small = nullptr;                     // pinned: constants on their way to the device
 
     // TABLE-path scratch (grow-only)
     Scratch filtA, filtB, auxS, auxR, tabX, tabM;
@@ -123,9 +126,14 @@ int table_prepare_frames(umpa_model *m, cudaStream_t st);      // FP64 stacks ->
 int table_alloc32(umpa_model *m);                              // 1. FP32 stacks + constants (no-op when not applicable)
 int table_means(umpa_model *m, cudaStream_t st);               // 2. centring constants from the sampled rows (see table_row_step)
 int table_center_rows(umpa_model *m, int y0, int y1, cudaStream_t st);   // 3. rows [y0,y1) of every frame -> centred FP32
+int table_set_means(umpa_model *m, const double *mu, cudaStream_t st);   // 2'. constants computed by the host (mu: 2*Na)
 int table_row_step(int H);                                     // rows y = 0, step, 2 step, ... define the centring constants
 bool table_eligible(const umpa_model *m, const RoiView &roi, std::string *why);
 int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st);
+
+// implemented in hoststage.cu (host code)
+double host_sampled_mean(const double *frame, int H, int W, int step);
+void host_center_rows(float *dst, const double *src, int rows, int W, int pitch, double c);
 
 // implemented in kernel_path.cu: per-pixel FP32 tables of UMPAModelDFKernel (blur fused into the window pass)
 bool ktable_supported(int Nw, int max_shift, int step0);

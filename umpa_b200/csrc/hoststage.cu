@@ -1,0 +1,64 @@
+// hoststage.cu -- host-side helpers of the pipelined upload (capi.cu, streamed_match): the centring
+// constants of a frame from its sampled rows, and the FP64 -> centred FP32 conversion that lets part
+// of a stack cross PCIe at half the bytes.  Plain host code (no device code in this unit).
+#include <immintrin.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+// mean of rows 0, step, 2 step, ... of one H x W frame (fixed summation order: row by row, 4 lanes)
+double host_sampled_mean(const double *frame, int H, int W, int step)
+{
+    double s = 0.;
+    size_t count = 0;
+    for (int y = 0; y < H; y += step) {
+        const double *row = frame + (size_t)y * W;
+        double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
+        int x = 0;
+        for (; x + 4 <= W; x += 4) { a0 += row[x]; a1 += row[x + 1]; a2 += row[x + 2]; a3 += row[x + 3]; }
+        for (; x < W; x++) a0 += row[x];
+        s += (a0 + a1) + (a2 + a3);
+        count += (size_t)W;
+    }
+    return s / (double)count;
+}
+
+namespace {
+
+void convert_scalar(float *dst, const double *src, size_t n, double c)
+{
+    for (size_t i = 0; i < n; i++) dst[i] = (float)(src[i] - c);
+}
+
+__attribute__((target("avx2"))) void convert_avx2(float *dst, const double *src, size_t n, double c)
+{
+    const __m256d vc = _mm256_set1_pd(c);
+    size_t i = 0;
+    for (; i < n && ((uintptr_t)(dst + i) & 31); i++) dst[i] = (float)(src[i] - c);
+    for (; i + 8 <= n; i += 8) {
+        const __m128 lo = _mm256_cvtpd_ps(_mm256_sub_pd(_mm256_loadu_pd(src + i), vc));
+        const __m128 hi = _mm256_cvtpd_ps(_mm256_sub_pd(_mm256_loadu_pd(src + i + 4), vc));
+        _mm256_stream_ps(dst + i, _mm256_set_m128(hi, lo));      // the staging buffer is write-only for the CPU
+    }
+    for (; i < n; i++) dst[i] = (float)(src[i] - c);
+    _mm_sfence();
+}
+
+}  // namespace
+
+// dst[y][x] = (float)(src[y][x] - c) for `rows` rows of W doubles -> rows of `pitch` floats (zero padded).
+// Same arithmetic as center_frames (table_path.cu): FP64 subtraction, one rounding to FP32.
+void host_center_rows(float *dst, const double *src, int rows, int W, int pitch, double c)
+{
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (pitch == W) {
+        if (avx2) convert_avx2(dst, src, (size_t)rows * W, c); else convert_scalar(dst, src, (size_t)rows * W, c);
+        return;
+    }
+    for (int y = 0; y < rows; y++) {
+        float *d = dst + (size_t)y * pitch;
+        if (avx2) convert_avx2(d, src + (size_t)y * W, W, c); else convert_scalar(d, src + (size_t)y * W, W, c);
+        for (int x = W; x < pitch; x++) d[x] = 0.f;
+    }
+}

@@ -507,6 +507,29 @@ int table_means(umpa_model *m, cudaStream_t st)
     return UMPA_OK;
 }
 
+int table_set_means(umpa_model *m, const double *mu, cudaStream_t st)
+{
+    if (!table_applicable(m)) return UMPA_OK;
+    const int Na = m->Na;
+    const size_t nd = 2 * (size_t)Na + 3;
+    if (!m->h_small) UMPA_CUDA(cudaHostAlloc(&m->h_small, nd * sizeof(double) + 2 * Na * sizeof(float), cudaHostAllocDefault));
+    double *hd = (double *)m->h_small;
+    float *hf = (float *)(hd + nd);
+    double cd = 0., cc = 0., dd = 0.;
+    for (int k = 0; k < Na; k++) {
+        const double d = mu[k], c = mu[Na + k];
+        hd[k] = d; hd[Na + k] = c;
+        hf[k] = (float)d; hf[Na + k] = (float)c;
+        cd += c * d; cc += c * c; dd += d * d;
+    }
+    hd[2 * Na] = cd; hd[2 * Na + 1] = cc; hd[2 * Na + 2] = dd;
+    UMPA_CUDA(cudaMemcpyAsync(m->d_means64, hd, 2 * Na * sizeof(double), cudaMemcpyHostToDevice, st));
+    UMPA_CUDA(cudaMemcpyAsync(m->d_consts, hd + 2 * Na, 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    UMPA_CUDA(cudaMemcpyAsync(m->d_mean_s, hf, Na * sizeof(float), cudaMemcpyHostToDevice, st));
+    UMPA_CUDA(cudaMemcpyAsync(m->d_mean_r, hf + Na, Na * sizeof(float), cudaMemcpyHostToDevice, st));
+    return UMPA_OK;
+}
+
 int table_center_rows(umpa_model *m, int y0, int y1, cudaStream_t st)
 {
     if (!table_applicable(m) || y1 <= y0) return UMPA_OK;

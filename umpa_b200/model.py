@@ -260,6 +260,13 @@ class UMPAModelBase:
         _capi.check(_capi.lib().umpa_last_match_info(self._h, C.byref(p), C.byref(n)))
         return {"path": _capi.PATH_NAMES[p.value], "kernel_launches": n.value}
 
+    @property
+    def last_stream_info(self):
+        """How the last host-to-host match was pipelined (zeros: it was not)."""
+        b, t, r = C.c_int(0), C.c_int(0), C.c_int(0)
+        _capi.check(_capi.lib().umpa_last_stream_info(self._h, C.byref(b), C.byref(t), C.byref(r)))
+        return {"bands": b.value, "host_threads": t.value, "host_rows_per_frame": r.value}
+
     def test(self):
         return float(self._Na)
 
