@@ -352,8 +352,11 @@ struct HostStage {
 int host_threads()
 {
     if (const char *e = getenv("UMPA_HOST_THREADS")) return std::max(0, atoi(e));
-    const int hw = (int)std::thread::hardware_concurrency();
-    return std::max(0, std::min(12, hw - 4));
+    // default: leave a few cores to the caller; processes launched side by side (one rank per GPU:
+    // torchrun exports LOCAL_WORLD_SIZE) share the box's cores
+    int hw = (int)std::thread::hardware_concurrency(), ranks = 1;
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+    return std::max(0, std::min(12, hw / ranks - (ranks > 1 ? 2 : 4)));
 }
 
 // The pipelined host-to-host match.  Frames still in host memory go up in row bands on a copy stream

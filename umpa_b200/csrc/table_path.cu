@@ -278,12 +278,18 @@ struct WalkParams {
     double swk;                     // exact sum of the FP32 2-D window kernel_path.cu applies
 };
 
+// RS = reference_shift (assign_coordinates = 'ref', Model.cpp:408-421 / 688-701): the SAMPLE window
+// moves by -s and the reference window stays at the pixel.  The tables are the same sums with the
+// roles of the stacks swapped (table_match feeds the sample stack as the moving operand) and the shift
+// negated; in the assembly the reference-derived aux image is then read at the pixel and the
+// sample-derived one at p - s.
+template <bool RS>
 struct TableEval {
     const WalkParams &w;
     int ty, tx;                     // table coords of this pixel
-    double t1, V;                   // pixel-only terms
+    double c0, c1, c2;              // pixel-only terms: (t1, V, -) or, RS, (t3, U, t2)
     const float *krow;              // DFKernel: this pixel's table row
-    double cd, cc;
+    double cd, cc, dd;
 
     __device__ int operator()(int si, int sj, double &cost, FitArgs &args) const
     {
@@ -292,28 +298,37 @@ struct TableEval {
         if (sj <= -ms) return UMPA_ST_BOUND | UMPA_ST_DIM;
         if (sj >= ms) return UMPA_ST_BOUND | UMPA_ST_DIM | UMPA_ST_POS;
         const int S = 2 * ms - 1;
-        const size_t sidx = (size_t)((si + ms - 1) * S + (sj + ms - 1));
-        if (w.kind == UMPA_DFKERNEL) {
+        const int ti = RS ? -si : si, tj = RS ? -sj : sj;
+        const size_t sidx = (size_t)((ti + ms - 1) * S + (tj + ms - 1));
+        if (!RS && w.kind == UMPA_DFKERNEL) {
             // t3 = sum w B^2, t5 = sum w B S with B = k_p (*) R (Model.cpp:1076-1099), rebuilt from the
             // centred FP32 sums: B = B' + sigma c_k
             const double sig = 1. + (double)__ldg(krow + 2 * S * S);
-            const double t5 = (double)__ldg(krow + sidx) + sig * (V + w.swk * cd);
+            const double t5 = (double)__ldg(krow + sidx) + sig * (c1 + w.swk * cd);
             const double t3 = (double)__ldg(krow + S * S + sidx) + sig * sig * w.swk * cc;
             args.t = t5 / t3;
-            cost = (t1 - t5 * args.t) * w.inv_Na;
+            cost = (c0 - t5 * args.t) * w.inv_Na;
             return UMPA_ST_OK;
         }
-        const float4 r = __ldg(w.auxR + (size_t)(w.oy + ty + si) * w.pitch + (w.ox + tx + sj));
+        const float4 mv = __ldg((RS ? w.auxS : w.auxR) + (size_t)(w.oy + ty + ti) * w.pitch + (w.ox + tx + tj));
         const float xv = __ldg(w.tabX + (sidx * w.rowsX + ty) * w.colsX + tx + w.dxX);
-        const double T3 = r.x, P3 = r.y, U = r.z, M2 = r.w;
-        const double t3 = T3 + 2. * P3 + w.sw * cc;
-        const double lin = U + V + w.sw * cd;
+        double t1, t2, t3, lin;
+        if (!RS) {                  // mv = (T3, P3, U, M2) of the reference at p + s
+            t1 = c0;
+            t3 = (double)mv.x + 2. * (double)mv.y + w.sw * cc;
+            lin = (double)mv.z + c1 + w.sw * cd;
+            t2 = (double)mv.w * w.inv_sw2 + 2. * (double)mv.y * w.inv_sw + cc;
+        } else {                    // mv = (T1, P1, V, -) of the sample at p - s
+            t1 = (double)mv.x + 2. * (double)mv.y + w.sw * dd;
+            t3 = c0;
+            lin = c1 + (double)mv.z + w.sw * cd;
+            t2 = c2;
+        }
         const double t5 = (double)xv + lin;
         if (w.kind == UMPA_DF) {
-            const float mv = __ldg(w.tabM + (sidx * w.rowsM + ty) * w.colsM + tx + w.dxM);
-            const double t2 = M2 * w.inv_sw2 + 2. * P3 * w.inv_sw + cc;
+            const float tm = __ldg(w.tabM + (sidx * w.rowsM + ty) * w.colsM + tx + w.dxM);
             const double t6 = w.sw * t2;
-            const double t4 = (double)mv * w.inv_sw + lin;
+            const double t4 = (double)tm * w.inv_sw + lin;
             const double rden = 1. / (t2 * t3 - t6 * t6);
             const double Kc = (t2 * t5 - t4 * t6) * rden;
             const double beta = (t3 * t4 - t5 * t6) * rden;
@@ -332,9 +347,6 @@ constexpr int WALK_NT = 128;
 #ifndef WALK_MINB
 #define WALK_MINB 8
 #endif
-#ifndef WALK_PREFETCH
-#define WALK_PREFETCH 0          // radius of the L2 prefetch around the start shift (0 = off)
-#endif
 
 // d (the 5x5 cost cache) lives in shared memory, one column per thread: dynamic indexing
 // without local-memory traffic.
@@ -343,6 +355,7 @@ struct SharedGrid {
     __device__ __forceinline__ double &operator[](int n) const { return base[n * WALK_NT]; }
 };
 
+template <bool RS>
 __global__ void __launch_bounds__(WALK_NT, WALK_MINB) table_walk_kernel(WalkParams w, RoiView roi, umpa_outputs out)
 {
     __shared__ double d_sm[25][WALK_NT];
@@ -352,24 +365,12 @@ __global__ void __launch_bounds__(WALK_NT, WALK_MINB) table_walk_kernel(WalkPara
     const size_t n = (size_t)xi * roi.N1 + xj;
     if (roi.cover && roi.cover[n] < roi.cover_threshold) return;
     const int ty = roi.step0 * xi, tx = roi.step1 * xj;
-#if WALK_PREFETCH > 0
-    {   // pull the table lines around the start shift into L2 while the first evaluations run
-        const int S = 2 * w.max_shift - 1, hs = w.max_shift - 1;
-        const int c0 = (int)round(roi.uv0[0]), c1 = (int)round(roi.uv0[1]);
-        for (int a = -WALK_PREFETCH; a <= WALK_PREFETCH; a++)
-            for (int b = -WALK_PREFETCH; b <= WALK_PREFETCH; b++) {
-                const int si = c0 + a, sj = c1 + b;
-                if (si < -hs || si > hs || sj < -hs || sj > hs) continue;
-                const size_t sidx = (size_t)((si + hs) * S + (sj + hs));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(w.tabX + (sidx * w.rowsX + ty) * w.colsX + tx + w.dxX));
-                if (w.tabM) asm volatile("prefetch.global.L2 [%0];" ::"l"(w.tabM + (sidx * w.rowsM + ty) * w.colsM + tx + w.dxM));
-            }
-    }
-#endif
-    const float4 s = __ldg(w.auxS + (size_t)(w.oy + ty) * w.pitch + (w.ox + tx));
+    const float4 s = __ldg((RS ? w.auxR : w.auxS) + (size_t)(w.oy + ty) * w.pitch + (w.ox + tx));
     const double cd = __ldg(w.consts), cc = __ldg(w.consts + 1), dd = __ldg(w.consts + 2);
-    TableEval eval{w, ty, tx, (double)s.x + 2. * (double)s.y + w.sw * dd, (double)s.z,
-                   w.ktab ? w.ktab + n * (size_t)w.kstride : nullptr, cd, cc};
+    // pixel-only terms: (t1, V) from the sample's aux image, or (RS) (t3, U, t2) from the reference's
+    TableEval<RS> eval{w, ty, tx, (double)s.x + 2. * (double)s.y + w.sw * (RS ? cc : dd), (double)s.z,
+                       RS ? (double)s.w * w.inv_sw2 + 2. * (double)s.y * w.inv_sw + cc : 0.,
+                       w.ktab ? w.ktab + n * (size_t)w.kstride : nullptr, cd, cc, dd};
     FitArgs args{0., 0.};
     SharedGrid d{&d_sm[0][threadIdx.x]};
     double a[16], uv[2] = {roi.uv0[0], roi.uv0[1]}, f = 0.;
@@ -553,7 +554,7 @@ bool table_eligible(const umpa_model *m, const RoiView &roi, std::string *why)
     if (!m->uniform) return no("ragged frames or non-zero positions");
     if (m->masked) return no("masks");
     if (!m->separable) return no("window is not separable");
-    if (m->refshift) return no("reference_shift=1");
+    if (m->refshift && m->kind == UMPA_DFKERNEL) return no("DFKernel with reference_shift=1");
     if (m->kind == UMPA_DFKERNEL) {
         if (!ktable_supported(m->Nw, m->max_shift, roi.step0)) return no("DFKernel: (Nw, max_shift, step) outside the instantiated blur-table kernels");
         if (!m->d_sam32) return no("FP32 stacks not prepared");
@@ -654,8 +655,10 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
     // 2. cross table: A = centred reference (read at p+s), B = centred sample, window-filtered
     else {
         CUtensorMap ma, mb;
-        if ((rc = make_stack_map(&ma, m->d_ref32, Na, H, m->W, pitch, px.AP, px.AH))) return rc;
-        if ((rc = make_stack_map(&mb, m->d_sam32, Na, H, m->W, pitch, EXT_W, px.EH))) return rc;
+        // the moving operand (read at p + s): the reference, or (reference_shift) the sample
+        const float *mov = m->refshift ? m->d_sam32 : m->d_ref32, *fix = m->refshift ? m->d_ref32 : m->d_sam32;
+        if ((rc = make_stack_map(&ma, mov, Na, H, m->W, pitch, px.AP, px.AH))) return rc;
+        if ((rc = make_stack_map(&mb, fix, Na, H, m->W, pitch, EXT_W, px.EH))) return rc;
         px.table = (float *)m->tabX.p;
         px.tiles_x = px.cols_p / px.TW; px.tiles_y = px.rows_p / px.TH;
         dim3 grid(std::min(px.tiles_x * px.tiles_y, m->sm_count * ctas_per_sm()));
@@ -668,8 +671,10 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
     // 3. mean table (DF): A = a_k, B = b_k, no filter
     if (df) {
         CUtensorMap ma, mb;
-        if ((rc = make_stack_map(&ma, (const float *)m->filtA.p, Na, H, m->W, pitch, pm.AP, pm.AH))) return rc;
-        if ((rc = make_stack_map(&mb, (const float *)m->filtB.p, Na, H, m->W, pitch, EXT_W, pm.EH))) return rc;
+        const float *mov = (const float *)(m->refshift ? m->filtB.p : m->filtA.p);
+        const float *fix = (const float *)(m->refshift ? m->filtA.p : m->filtB.p);
+        if ((rc = make_stack_map(&ma, mov, Na, H, m->W, pitch, pm.AP, pm.AH))) return rc;
+        if ((rc = make_stack_map(&mb, fix, Na, H, m->W, pitch, EXT_W, pm.EH))) return rc;
         pm.table = (float *)m->tabM.p;
         pm.tiles_x = pm.cols_p / pm.TW; pm.tiles_y = pm.rows_p / pm.TH;
         dim3 grid(std::min(pm.tiles_x * pm.tiles_y, m->sm_count * ctas_per_sm()));
@@ -698,7 +703,8 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         w.inv_sw = 1. / w.sw; w.inv_sw2 = 1. / (w.sw * w.sw); w.inv_Na = 1. / (double)Na;
         w.consts = m->d_consts;
         dim3 grid((roi.N1 + WALK_NT - 1) / WALK_NT, roi.N0);
-        table_walk_kernel<<<grid, WALK_NT, 0, st>>>(w, roi, out);
+        if (m->refshift) table_walk_kernel<true><<<grid, WALK_NT, 0, st>>>(w, roi, out);
+        else table_walk_kernel<false><<<grid, WALK_NT, 0, st>>>(w, roi, out);
         UMPA_CUDA(cudaGetLastError());
         m->last_launches++;
         if ((rc = stage_check("walk", st))) return rc;
