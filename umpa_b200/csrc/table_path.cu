@@ -266,6 +266,7 @@ struct WalkParams {
     const float4 *auxS, *auxR;      // [H][pitch], raw coordinates
     int pitch;
     int rowsX, colsX, rowsM, colsM; // padded plane geometry of the two tables
+    unsigned planeX, planeM;        // rows * cols
     int oy, ox;                     // raw coords of output pixel (0,0) of the dense region
     int dxX, dxM;                   // column of that pixel inside the cross / mean table (TMA alignment shift)
     int kind, Na, max_shift, subpx;
@@ -290,28 +291,60 @@ struct TableEval {
     double c0, c1, c2;              // pixel-only terms: (t1, V, -) or, RS, (t3, U, t2)
     const float *krow;              // DFKernel: this pixel's table row
     double cd, cc, dd;
+    const float4 *pAux;             // moving aux image at this pixel (shift 0)
+    const float *pX, *pM;           // this pixel in plane 0 of the cross / mean table
 
-    __device__ int operator()(int si, int sj, double &cost, FitArgs &args) const
+    struct Raw { float4 aux; float x, m; };     // what one evaluation reads: three independent gathers
+
+    __device__ int operator()(int si, int sj, double &cst, FitArgs &args) const
+    {
+        const int se = status(si, sj);
+        if (se != UMPA_ST_OK) return se;
+        cst = cost(fetch(si, sj), args);
+        return UMPA_ST_OK;
+    }
+
+    __device__ int status(int si, int sj) const
     {
         const int ms = w.max_shift;
         if (si <= -ms || si >= ms) return UMPA_ST_BOUND;
         if (sj <= -ms) return UMPA_ST_BOUND | UMPA_ST_DIM;
         if (sj >= ms) return UMPA_ST_BOUND | UMPA_ST_DIM | UMPA_ST_POS;
-        const int S = 2 * ms - 1;
+        return UMPA_ST_OK;
+    }
+
+    // the three gathers of one evaluation (shift must be in bounds)
+    __device__ Raw fetch(int si, int sj) const
+    {
+        const int ms = w.max_shift, S = 2 * ms - 1;
         const int ti = RS ? -si : si, tj = RS ? -sj : sj;
-        const size_t sidx = (size_t)((ti + ms - 1) * S + (tj + ms - 1));
+        const unsigned sidx = (unsigned)((ti + ms - 1) * S + (tj + ms - 1));
+        Raw r;
+        if (!RS && w.kind == UMPA_DFKERNEL) {
+            r.x = __ldg(krow + sidx);
+            r.m = __ldg(krow + S * S + sidx);
+            r.aux = make_float4(__ldg(krow + 2 * S * S), 0.f, 0.f, 0.f);
+            return r;
+        }
+        // per-pixel base pointers + one 32x32->64 multiply per table (plane sizes fit 32 bits)
+        r.aux = __ldg(pAux + (ti * w.pitch + tj));
+        r.x = __ldg(pX + (size_t)sidx * w.planeX);
+        r.m = w.kind == UMPA_DF ? __ldg(pM + (size_t)sidx * w.planeM) : 0.f;
+        return r;
+    }
+
+    __device__ double cost(const Raw &r, FitArgs &args) const
+    {
         if (!RS && w.kind == UMPA_DFKERNEL) {
             // t3 = sum w B^2, t5 = sum w B S with B = k_p (*) R (Model.cpp:1076-1099), rebuilt from the
             // centred FP32 sums: B = B' + sigma c_k
-            const double sig = 1. + (double)__ldg(krow + 2 * S * S);
-            const double t5 = (double)__ldg(krow + sidx) + sig * (c1 + w.swk * cd);
-            const double t3 = (double)__ldg(krow + S * S + sidx) + sig * sig * w.swk * cc;
+            const double sig = 1. + (double)r.aux.x;
+            const double t5 = (double)r.x + sig * (c1 + w.swk * cd);
+            const double t3 = (double)r.m + sig * sig * w.swk * cc;
             args.t = t5 / t3;
-            cost = (c0 - t5 * args.t) * w.inv_Na;
-            return UMPA_ST_OK;
+            return (c0 - t5 * args.t) * w.inv_Na;
         }
-        const float4 mv = __ldg((RS ? w.auxS : w.auxR) + (size_t)(w.oy + ty + ti) * w.pitch + (w.ox + tx + tj));
-        const float xv = __ldg(w.tabX + (sidx * w.rowsX + ty) * w.colsX + tx + w.dxX);
+        const float4 mv = r.aux;
         double t1, t2, t3, lin;
         if (!RS) {                  // mv = (T3, P3, U, M2) of the reference at p + s
             t1 = c0;
@@ -324,28 +357,25 @@ struct TableEval {
             lin = c1 + (double)mv.z + w.sw * cd;
             t2 = c2;
         }
-        const double t5 = (double)xv + lin;
+        const double t5 = (double)r.x + lin;
         if (w.kind == UMPA_DF) {
-            const float tm = __ldg(w.tabM + (sidx * w.rowsM + ty) * w.colsM + tx + w.dxM);
             const double t6 = w.sw * t2;
-            const double t4 = (double)tm * w.inv_sw + lin;
+            const double t4 = (double)r.m * w.inv_sw + lin;
             const double rden = 1. / (t2 * t3 - t6 * t6);
             const double Kc = (t2 * t5 - t4 * t6) * rden;
             const double beta = (t3 * t4 - t5 * t6) * rden;
             args.t = beta + Kc;
-            args.v = Kc;                  // dark field = Kc / t, divided once at the end (finish())
-            cost = (t1 + beta * beta * t2 + Kc * Kc * t3 - 2. * beta * t4 - 2. * Kc * t5 + 2. * beta * Kc * t6) * w.inv_Na;
-        } else {
-            args.t = t5 / t3;
-            cost = (t1 - t5 * args.t) * w.inv_Na;
+            args.v = Kc;                  // dark field = Kc / t, divided once at the end
+            return (t1 + beta * beta * t2 + Kc * Kc * t3 - 2. * beta * t4 - 2. * Kc * t5 + 2. * beta * Kc * t6) * w.inv_Na;
         }
-        return UMPA_ST_OK;
+        args.t = t5 / t3;
+        return (t1 - t5 * args.t) * w.inv_Na;
     }
 };
 
 constexpr int WALK_NT = 128;
 #ifndef WALK_MINB
-#define WALK_MINB 8
+#define WALK_MINB 6
 #endif
 
 // d (the 5x5 cost cache) lives in shared memory, one column per thread: dynamic indexing
@@ -370,7 +400,10 @@ __global__ void __launch_bounds__(WALK_NT, WALK_MINB) table_walk_kernel(WalkPara
     // pixel-only terms: (t1, V) from the sample's aux image, or (RS) (t3, U, t2) from the reference's
     TableEval<RS> eval{w, ty, tx, (double)s.x + 2. * (double)s.y + w.sw * (RS ? cc : dd), (double)s.z,
                        RS ? (double)s.w * w.inv_sw2 + 2. * (double)s.y * w.inv_sw + cc : 0.,
-                       w.ktab ? w.ktab + n * (size_t)w.kstride : nullptr, cd, cc, dd};
+                       w.ktab ? w.ktab + n * (size_t)w.kstride : nullptr, cd, cc, dd,
+                       (RS ? w.auxS : w.auxR) + (size_t)(w.oy + ty) * w.pitch + (w.ox + tx),
+                       w.tabX + (size_t)ty * w.colsX + tx + w.dxX,
+                       w.tabM ? w.tabM + (size_t)ty * w.colsM + tx + w.dxM : nullptr};
     FitArgs args{0., 0.};
     SharedGrid d{&d_sm[0][threadIdx.x]};
     double a[16], uv[2] = {roi.uv0[0], roi.uv0[1]}, f = 0.;
@@ -468,7 +501,7 @@ size_t plan_tiles(TableParams &p, int S, bool filter, int *nt)
     int ns = MAX_STAGES;
     while (ns > 2 && (size_t)ns * p.stage_floats * sizeof(float) + cbuf > budget) ns--;
     if ((size_t)ns * p.stage_floats * sizeof(float) + cbuf > budget) return 0;
-    p.nstage = std::min(ns, 6);
+    p.nstage = std::min(ns, MAX_STAGES);
     if (const char *e = getenv("UMPA_TAB_NST")) p.nstage = std::max(2, std::min(ns, atoi(e)));
     return (size_t)p.nstage * p.stage_floats * sizeof(float) + cbuf;
 }
@@ -697,6 +730,7 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         }
         w.auxS = (const float4 *)m->auxS.p; w.auxR = (const float4 *)m->auxR.p;
         w.pitch = pitch; w.rowsX = px.rows_p; w.colsX = px.cols_p; w.rowsM = pm.rows_p; w.colsM = pm.cols_p;
+        w.planeX = (unsigned)px.rows_p * (unsigned)px.cols_p; w.planeM = (unsigned)pm.rows_p * (unsigned)pm.cols_p;
         w.oy = oy; w.ox = ox; w.dxX = dxX; w.dxM = dxM;
         w.kind = m->kind; w.Na = Na; w.max_shift = m->max_shift; w.subpx = m->subpx;
         w.sw = m->win_sum; w.quad = m->d_quad;

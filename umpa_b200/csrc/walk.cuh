@@ -257,6 +257,8 @@ __device__ __forceinline__ void store_pixel(const umpa_outputs &o, size_t n, int
     if (o.ncalls) o.ncalls[n] = ncalls;
     if (o.debug_d)
         for (int t = 0; t < 25; t++) o.debug_d[25 * n + t] = d[t];
-    if (o.debug_a)
+    if (o.debug_a) {
+#pragma unroll
         for (int t = 0; t < 16; t++) o.debug_a[16 * n + t] = have_a ? a[t] : 0.;
+    }
 }
