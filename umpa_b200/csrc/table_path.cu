@@ -119,144 +119,165 @@ struct MomentsParams {
     int ty0, tx0;                // first tile (in tile units) of the bounding box
 };
 
-constexpr int MO_TH = 16, MO_TW = 128, MO_NT = 256;
+constexpr int MO_TH = 16, MO_TW = 64, MO_NT = 256;
 
-__device__ __forceinline__ void cp_async4(float *dst, const float *src, bool valid)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-    const int sz = valid ? 4 : 0;                      // src-size 0 -> zero fill
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(src), "r"(sz));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-// One block filters a 16 x 128 tile of every frame of both stacks with the separable window
-// and accumulates the aux images.  256 threads = 2 halves x 128 columns; a thread owns one
-// column and 8 output rows: the row pass reads shared memory (conflict-free, K taps), the column
-// pass runs on registers.  Frames are double-buffered with cp.async (zero fill outside the frame).
-// The per-pixel sums of squares are accumulated in shared memory and filtered once at the end,
-// as an extra "frame".
+// One block filters a 16 x 64 tile of every frame of both stacks with the separable window and
+// accumulates the aux images.  Per frame:
+//   * both raw tiles (with their Nw halo) arrive by TMA into a two-stage ring (box start 16 B aligned:
+//     LPAD >= Nw columns are loaded left of the tile; zero fill outside the frame);
+//   * row pass: an item is 4 consecutive outputs of one extended row, float4 in / float4 out, result to
+//     a shared row buffer (the 8 lanes of a quarter warp cover one 128 B line: conflict free);
+//   * column pass: every thread owns ONE float4 of the output tile: K float4 loads per stack, the two
+//     filtered values a'_k, b'_k feed the five aux accumulators (registers) and go to the filtered stacks.
+// The per-pixel sums of squares are accumulated in registers (each thread owns three float4 of the raw
+// tiles) and filtered once at the end, as an extra "frame".
 template <int NW>
-__global__ void __launch_bounds__(MO_NT) moments_kernel(MomentsParams p)
+__global__ void __launch_bounds__(MO_NT)
+moments_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapS, MomentsParams p)
 {
-    constexpr int K = 2 * NW + 1;
-    constexpr int ER = MO_TH + 2 * NW, EC = MO_TW + 2 * NW;   // extended tile
-    constexpr int RH = MO_TH / 2 + 2 * NW;                    // extended rows one half walks over
-    extern __shared__ float sm[];
-    float *buf = sm;                                   // [2 buffers][2 stacks][ER*EC]
-    float *qs = sm + 4 * ER * EC;                      // [2 stacks][ER*EC] sums of squares
-    const int tid = threadIdx.x, h = tid >> 7, c = tid & 127;
+    constexpr int K = 2 * NW + 1, ER = MO_TH + 2 * NW;
+    constexpr int LPAD = (NW + 3) & ~3;                 // columns left of the tile in the TMA box
+    constexpr int BW = MO_TW + 2 * LPAD, OFF = LPAD - NW;
+    constexpr int NL4 = (OFF + 4 + 2 * NW + 3) / 4;     // float4 loads of one row-pass item
+    constexpr int RAW = ((ER * BW * 4 + 127) & ~127) / 4;    // floats per raw tile (128 B multiple)
+    constexpr int S4 = MO_TW / 4;                       // output strips per row
+    constexpr int NROW = 2 * ER * S4, NSQ = 2 * ER * (BW / 4);
+    constexpr int RIT = (NROW + MO_NT - 1) / MO_NT, QIT = (NSQ + MO_NT - 1) / MO_NT;
+    extern __shared__ __align__(128) float sm[];
+    float *raw = sm;                                    // [2 stages][2 stacks][RAW]
+    float *rowbuf = sm + 4 * RAW;                       // [2 stacks][ER][MO_TW]
+    __shared__ uint64_t full_bar[2];
+    const int tid = threadIdx.x;
     const int y0 = (blockIdx.y + p.ty0) * MO_TH, x0 = (blockIdx.x + p.tx0) * MO_TW;
     const size_t fstride = (size_t)p.H * p.pitch;
     float g[K];
 #pragma unroll
     for (int v = 0; v < K; v++) g[v] = __ldg(p.g + v);
-    for (int n = tid; n < 2 * ER * EC; n += MO_NT) qs[n] = 0.f;
 
-    auto load = [&](int k, int b) {
-        const float *R = p.ref + k * fstride, *S = p.sam + k * fstride;
-        float *dR = buf + (size_t)b * 2 * ER * EC, *dS = dR + ER * EC;
-        for (int n = tid; n < ER * EC; n += MO_NT) {
-            const int r = n / EC, cc = n - r * EC;
-            const int y = y0 - NW + r, x = x0 - NW + cc;
-            const bool ok = y >= 0 && y < p.H && x >= 0 && x < p.W;
-            const size_t off = ok ? (size_t)y * p.pitch + x : 0;
-            cp_async4(dR + n, R + off, ok);
-            cp_async4(dS + n, S + off, ok);
-        }
+    if (tid == 0) {
+        mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+    auto request = [&](int k) {                         // thread 0: both raw tiles of frame k -> stage k & 1
+        float *dst = raw + (k & 1) * 2 * RAW;
+        mbar_expect_tx(&full_bar[k & 1], 2u * ER * BW * sizeof(float));
+        tma_load_3d(dst, &mapR, x0 - LPAD, y0 - NW, k, &full_bar[k & 1]);
+        tma_load_3d(dst + RAW, &mapS, x0 - LPAD, y0 - NW, k, &full_bar[k & 1]);
     };
+    if (tid == 0) { request(0); if (p.Na > 1) request(1); }
 
-    float m2[8], p3[8], uu[8], p1[8], vv[8];
+    // row pass of the two tiles at `in` ([2][RAW]) -> rowbuf
+    auto row_pass = [&](const float *in) {
 #pragma unroll
-    for (int t = 0; t < 8; t++) m2[t] = p3[t] = uu[t] = p1[t] = vv[t] = 0.f;
-
-    // row pass of one stack for this thread's RH extended rows; optionally adds the squares of the
-    // rows this half owns to qs (centre column, plus the tile's edge columns for the edge threads)
-    auto rows_of = [&](const float *in, float *q, float (&row)[RH]) {
+        for (int n = 0; n < RIT; n++) {
+            const int it = tid + n * MO_NT;
+            if (it < NROW) {
+                const int st = it / (ER * S4), rem = it - st * (ER * S4);
+                const int er = rem / S4, c4 = rem - er * S4;
+                const float *src = in + st * RAW + er * BW + 4 * c4;
+                float r[4 * NL4];
 #pragma unroll
-        for (int j = 0; j < RH; j++) {
-            const float *src = in + (8 * h + j) * EC + c;
-            float v[K];
+                for (int v = 0; v < NL4; v++) {
+                    const float4 t = *reinterpret_cast<const float4 *>(src + 4 * v);
+                    r[4 * v] = t.x; r[4 * v + 1] = t.y; r[4 * v + 2] = t.z; r[4 * v + 3] = t.w;
+                }
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int t = 0; t < K; t++) v[t] = src[t];
-            float acc = 0.f;
+                for (int v = 0; v < K; v++)
 #pragma unroll
-            for (int t = 0; t < K; t++) acc = fmaf(g[t], v[t], acc);
-            row[j] = acc;
-            if (q != nullptr && (h == 0 ? j < 8 + NW : j >= NW)) {
-                float *qd = q + (8 * h + j) * EC + c;
-                qd[NW] += v[NW] * v[NW];
-                if (NW > 0 && c < NW) qd[0] += v[0] * v[0];
-                if (NW > 0 && c >= MO_TW - NW) qd[K - 1] += v[K - 1] * v[K - 1];
+                    for (int x = 0; x < 4; x++) o[x] = fmaf(g[v], r[OFF + x + v], o[x]);
+                *reinterpret_cast<float4 *>(rowbuf + (st * ER + er) * MO_TW + 4 * c4) = make_float4(o[0], o[1], o[2], o[3]);
             }
         }
     };
+    // column pass of this thread's float4 (output row orow, strip c4) of stack st
+    const int orow = tid / S4, oc4 = tid - orow * S4;
+    auto col_pass = [&](int st, float (&o)[4]) {
+        o[0] = o[1] = o[2] = o[3] = 0.f;
+        const float *src = rowbuf + (st * ER + orow) * MO_TW + 4 * oc4;
+#pragma unroll
+        for (int u = 0; u < K; u++) {
+            const float4 t = *reinterpret_cast<const float4 *>(src + u * MO_TW);
+            o[0] = fmaf(g[u], t.x, o[0]); o[1] = fmaf(g[u], t.y, o[1]);
+            o[2] = fmaf(g[u], t.z, o[2]); o[3] = fmaf(g[u], t.w, o[3]);
+        }
+    };
 
-    load(0, 0);
-    cp_async_commit();
+    float m2[4], p3[4], uu[4], p1[4], vv[4], sq[QIT][4];
+#pragma unroll
+    for (int x = 0; x < 4; x++) m2[x] = p3[x] = uu[x] = p1[x] = vv[x] = 0.f;
+#pragma unroll
+    for (int n = 0; n < QIT; n++)
+#pragma unroll
+        for (int x = 0; x < 4; x++) sq[n][x] = 0.f;
+    const int oy = y0 + orow, ox = x0 + 4 * oc4;
+    const bool inside = oy < p.H && ox < p.pitch;
+    const size_t opix = (size_t)oy * p.pitch + ox;
+
     for (int k = 0; k < p.Na; k++) {
-        if (k + 1 < p.Na) load(k + 1, (k + 1) & 1);
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
-        const float *inR = buf + (size_t)(k & 1) * 2 * ER * EC, *inS = inR + ER * EC;
-        float rowR[RH], rowS[RH];
-        rows_of(inR, qs, rowR);
-        rows_of(inS, qs + ER * EC, rowS);
-        const float ck = __ldg(p.mean_r + k), dk = __ldg(p.mean_s + k);
-        const int x = x0 + c;
+        mbar_wait(&full_bar[k & 1], (k >> 1) & 1);
+        const float *in = raw + (k & 1) * 2 * RAW;
+        row_pass(in);
 #pragma unroll
-        for (int t = 0; t < 8; t++) {
-            float a = 0.f, b = 0.f;
-#pragma unroll
-            for (int u = 0; u < K; u++) { a = fmaf(g[u], rowR[t + u], a); b = fmaf(g[u], rowS[t + u], b); }
-            m2[t] = fmaf(a, a, m2[t]);
-            p3[t] = fmaf(ck, a, p3[t]);
-            uu[t] = fmaf(dk, a, uu[t]);
-            p1[t] = fmaf(dk, b, p1[t]);
-            vv[t] = fmaf(ck, b, vv[t]);
-            const int y = y0 + 8 * h + t;
-            if (p.fa && y < p.H && x < p.pitch) {
-                p.fa[k * fstride + (size_t)y * p.pitch + x] = a;
-                p.fb[k * fstride + (size_t)y * p.pitch + x] = b;
+        for (int n = 0; n < QIT; n++) {                  // squares of the raw float4s this thread owns
+            const int it = tid + n * MO_NT;
+            if (it < NSQ) {
+                const int st = it / (ER * (BW / 4)), rem = it - st * (ER * (BW / 4));
+                const float4 t = *reinterpret_cast<const float4 *>(in + st * RAW + 4 * rem);
+                sq[n][0] = fmaf(t.x, t.x, sq[n][0]); sq[n][1] = fmaf(t.y, t.y, sq[n][1]);
+                sq[n][2] = fmaf(t.z, t.z, sq[n][2]); sq[n][3] = fmaf(t.w, t.w, sq[n][3]);
             }
         }
-        __syncthreads();                               // buffer (k & 1) is free for frame k + 2
+        __syncthreads();                                 // row buffer complete, stage k & 1 consumed
+        if (tid == 0 && k + 2 < p.Na) request(k + 2);
+        float a[4], b[4];
+        col_pass(0, a);
+        col_pass(1, b);
+        const float ck = __ldg(p.mean_r + k), dk = __ldg(p.mean_s + k);
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+            m2[x] = fmaf(a[x], a[x], m2[x]);
+            p3[x] = fmaf(ck, a[x], p3[x]);
+            uu[x] = fmaf(dk, a[x], uu[x]);
+            p1[x] = fmaf(dk, b[x], p1[x]);
+            vv[x] = fmaf(ck, b[x], vv[x]);
+        }
+        if (p.fa && inside) {
+            *reinterpret_cast<float4 *>(p.fa + k * fstride + opix) = make_float4(a[0], a[1], a[2], a[3]);
+            *reinterpret_cast<float4 *>(p.fb + k * fstride + opix) = make_float4(b[0], b[1], b[2], b[3]);
+        }
+        __syncthreads();                                 // row buffer free for the next frame
     }
     // the sums of squares as one more frame: T3 = w (*) sum_k R'^2, T1 = w (*) sum_k S'^2
-    {
-        float rowR[RH], rowS[RH];
-        rows_of(qs, nullptr, rowR);
-        rows_of(qs + ER * EC, nullptr, rowS);
-        const int x = x0 + c;
 #pragma unroll
-        for (int t = 0; t < 8; t++) {
-            float t3 = 0.f, t1 = 0.f;
+    for (int n = 0; n < QIT; n++) {
+        const int it = tid + n * MO_NT;
+        if (it < NSQ) {
+            const int st = it / (ER * (BW / 4)), rem = it - st * (ER * (BW / 4));
+            *reinterpret_cast<float4 *>(raw + st * RAW + 4 * rem) = make_float4(sq[n][0], sq[n][1], sq[n][2], sq[n][3]);
+        }
+    }
+    __syncthreads();
+    row_pass(raw);
+    __syncthreads();
+    float t3[4], t1[4];
+    col_pass(0, t3);
+    col_pass(1, t1);
+    if (inside) {
 #pragma unroll
-            for (int u = 0; u < K; u++) { t3 = fmaf(g[u], rowR[t + u], t3); t1 = fmaf(g[u], rowS[t + u], t1); }
-            const int y = y0 + 8 * h + t;
-            if (y < p.H && x < p.pitch) {
-                p.auxR[(size_t)y * p.pitch + x] = make_float4(t3, p3[t], uu[t], m2[t]);
-                p.auxS[(size_t)y * p.pitch + x] = make_float4(t1, p1[t], vv[t], 0.f);
-            }
+        for (int x = 0; x < 4; x++) {
+            p.auxR[opix + x] = make_float4(t3[x], p3[x], uu[x], m2[x]);
+            p.auxS[opix + x] = make_float4(t1[x], p1[x], vv[x], 0.f);
         }
     }
 }
 
-typedef void (*MomentsKernel)(MomentsParams);
-template <int NW> size_t moments_smem() { return (size_t)6 * (MO_TH + 2 * NW) * (MO_TW + 2 * NW) * sizeof(float); }
-bool moments_pick(int Nw, MomentsKernel *k, size_t *smem)
+template <int NW> size_t moments_smem()
 {
-    switch (Nw) {
-        case 0: *k = moments_kernel<0>; *smem = moments_smem<0>(); return true;
-        case 1: *k = moments_kernel<1>; *smem = moments_smem<1>(); return true;
-        case 2: *k = moments_kernel<2>; *smem = moments_smem<2>(); return true;
-        case 3: *k = moments_kernel<3>; *smem = moments_smem<3>(); return true;
-        case 4: *k = moments_kernel<4>; *smem = moments_smem<4>(); return true;
-        case 5: *k = moments_kernel<5>; *smem = moments_smem<5>(); return true;
-        case 6: *k = moments_kernel<6>; *smem = moments_smem<6>(); return true;
-    }
-    return false;
+    constexpr int ER = MO_TH + 2 * NW, LPAD = (NW + 3) & ~3, BW = MO_TW + 2 * LPAD;
+    return (size_t)4 * ((ER * BW * 4 + 127) & ~127) + (size_t)2 * ER * MO_TW * sizeof(float);
 }
 
 // ------------------------------------------------------------------ table-driven walk
@@ -453,6 +474,36 @@ int make_stack_map(CUtensorMap *map, const float *base, int Na, int H, int W, in
     return UMPA_OK;
 }
 
+template <int NW>
+int launch_moments_nw(const MomentsParams &mp, const float *ref32, const float *sam32, dim3 grid, cudaStream_t st)
+{
+    constexpr int ER = MO_TH + 2 * NW, LPAD = (NW + 3) & ~3, BW = MO_TW + 2 * LPAD;
+    CUtensorMap mr, ms;
+    int rc;
+    if ((rc = make_stack_map(&mr, ref32, mp.Na, mp.H, mp.W, mp.pitch, BW, ER))) return rc;
+    if ((rc = make_stack_map(&ms, sam32, mp.Na, mp.H, mp.W, mp.pitch, BW, ER))) return rc;
+    const size_t smem = moments_smem<NW>();
+    UMPA_CUDA(cudaFuncSetAttribute(moments_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    moments_kernel<NW><<<grid, MO_NT, smem, st>>>(mr, ms, mp);
+    UMPA_CUDA(cudaGetLastError());
+    return UMPA_OK;
+}
+
+int launch_moments(int Nw, const MomentsParams &mp, const float *ref32, const float *sam32, dim3 grid, cudaStream_t st)
+{
+    switch (Nw) {
+        case 0: return launch_moments_nw<0>(mp, ref32, sam32, grid, st);
+        case 1: return launch_moments_nw<1>(mp, ref32, sam32, grid, st);
+        case 2: return launch_moments_nw<2>(mp, ref32, sam32, grid, st);
+        case 3: return launch_moments_nw<3>(mp, ref32, sam32, grid, st);
+        case 4: return launch_moments_nw<4>(mp, ref32, sam32, grid, st);
+        case 5: return launch_moments_nw<5>(mp, ref32, sam32, grid, st);
+        case 6: return launch_moments_nw<6>(mp, ref32, sam32, grid, st);
+    }
+    umpa_set_error("table path: Nw %d not instantiated", Nw);
+    return UMPA_ERR_UNSUPPORTED;
+}
+
 // filter = false: plain table; true: window filter of half-width p.Nw (0..6)
 int dispatch_shift_table(bool filter, int S, const CUtensorMap &a, const CUtensorMap &b, const TableParams &p, dim3 grid,
                          int nt, size_t smem, cudaStream_t st)
@@ -501,7 +552,7 @@ size_t plan_tiles(TableParams &p, int S, bool filter, int *nt)
     int ns = MAX_STAGES;
     while (ns > 2 && (size_t)ns * p.stage_floats * sizeof(float) + cbuf > budget) ns--;
     if ((size_t)ns * p.stage_floats * sizeof(float) + cbuf > budget) return 0;
-    p.nstage = std::min(ns, MAX_STAGES);
+    p.nstage = std::min(ns, p.Na >= 8 ? MAX_STAGES : 6);     // measured: 8 stages help Na = 25 (+2 %), hurt Na = 4 (-14 %)
     if (const char *e = getenv("UMPA_TAB_NST")) p.nstage = std::max(2, std::min(ns, atoi(e)));
     return (size_t)p.nstage * p.stage_floats * sizeof(float) + cbuf;
 }
@@ -669,12 +720,7 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         const int xlo = std::max(0, ox - HS), xhi = std::min(m->W, ox + cols + HS);
         mp.ty0 = ylo / MO_TH; mp.tx0 = xlo / MO_TW;
         dim3 grid((xhi + MO_TW - 1) / MO_TW - mp.tx0, (yhi + MO_TH - 1) / MO_TH - mp.ty0);
-        MomentsKernel mk = nullptr;
-        size_t smem = 0;
-        if (!moments_pick(m->Nw, &mk, &smem)) { umpa_set_error("table path: Nw %d not instantiated", m->Nw); return UMPA_ERR_UNSUPPORTED; }
-        UMPA_CUDA(cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mk<<<grid, MO_NT, smem, st>>>(mp);
-        UMPA_CUDA(cudaGetLastError());
+        if ((rc = launch_moments(m->Nw, mp, m->d_ref32, m->d_sam32, grid, st))) return rc;
         m->last_launches++;
         if ((rc = stage_check("moments", st))) return rc;
     }
