@@ -134,8 +134,6 @@ void quad_matrix(double *Q /*6x16*/)
         }
 }
 
-int nparam(int kind) { return kind == UMPA_NODF ? 4 : (kind == UMPA_DF ? 5 : 7); }
-
 // window bookkeeping: copy, separability test (w == r c^T / total), device copies
 int install_window(umpa_model *m, int Nw, const double *win)
 {
@@ -250,6 +248,27 @@ int zero_outputs(const umpa_outputs &o, size_t n, cudaStream_t st)
     return UMPA_OK;
 }
 
+// Centring constants of host frames, by host threads (hoststage.cu): the same values whether the
+// frames then go up in one piece, in bands, or partly converted.
+void host_means(const umpa_model *m, std::vector<double> &mu)
+{
+    const int Na = m->Na, rs = table_row_step(m->H);
+    mu.assign(2 * Na, 0.);
+    std::atomic<int> next{0};
+    auto work = [&]() {
+        for (;;) {
+            const int f = next.fetch_add(1);
+            if (f >= 2 * Na) break;
+            mu[f] = host_sampled_mean(f < Na ? m->h_sam[f] : m->h_ref[f - Na], m->H, m->W, rs);
+        }
+    };
+    const int nt = std::max(1, std::min(8, std::min(2 * Na, (int)std::thread::hardware_concurrency() - 1)));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; t++) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+}
+
 // Deferred host frames (umpa_set_frames on_device = 2): bring the FP64 stacks (and, if they are not
 // there yet, the centred FP32 stacks) to the device now, on `st`.
 int ensure_resident(umpa_model *m, cudaStream_t st)
@@ -262,8 +281,12 @@ int ensure_resident(umpa_model *m, cudaStream_t st)
             const size_t n = (size_t)m->dim[2 * k] * m->dim[2 * k + 1];
             UMPA_CUDA(cudaMemcpyAsync(dsts[a] + m->frame_off[k], (*srcs[a])[k], n * sizeof(double), cudaMemcpyHostToDevice, st));
         }
-    if (m->host_pending) {
-        int rc = table_prepare_frames(m, st);
+    if (m->host_pending && m->uniform && !m->masked) {
+        std::vector<double> mu;
+        host_means(m, mu);
+        int rc = table_alloc32(m);
+        if (!rc) rc = table_set_means(m, mu.data(), st);
+        if (!rc) rc = table_center_rows(m, 0, m->H, st);
         if (rc) return rc;
     }
     UMPA_CUDA(cudaStreamSynchronize(st));
@@ -446,7 +469,7 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
                 for (int a = 0; a < 2; a++) jobs.push_back({b, a, k, cy0[b], cy1[b]});
         }
     }
-    std::vector<double> mu(2 * Na, 0.);
+    std::vector<double> mu(2 * Na, 0.);      // centring constants (host_sampled_mean of every frame)
     std::unique_ptr<std::atomic<int>[]> left(new std::atomic<int>[nb]);
     for (int b = 0; b < nb; b++) left[b].store(nthr > 0 && cy1[b] > cy0[b] ? 2 * Na : 0);
     std::atomic<int> next_mean{0}, means_done{0}, next_job{0};
@@ -518,16 +541,6 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
                                  (size_t)HC * rb, (size_t)(y1 - y0) * rb, Na, cudaMemcpyHostToDevice, m->s_copy);
     };
 
-    // 0. constants: from the host workers, or (no workers) from the sampled rows uploaded ahead of the bands
-    if (nthr == 0 && nb > 1) {
-        const int nrs = (H + rs - 1) / rs;
-        for (int k = 0; k < Na; k++) {
-            ST_CUDA(cudaMemcpy2DAsync(m->d_sam64 + m->frame_off[k], rs * rowb, m->h_sam[k], rs * rowb, rowb, nrs,
-                                      cudaMemcpyHostToDevice, m->s_copy));
-            ST_CUDA(cudaMemcpy2DAsync(m->d_ref64 + m->frame_off[k], rs * rowb, m->h_ref[k], rs * rowb, rowb, nrs,
-                                      cudaMemcpyHostToDevice, m->s_copy));
-        }
-    }
     mark(m->s_copy);
     int up_hi = 0;                              // rows [0, up_hi) are on the device and centred
     bool have_means = false;
@@ -540,8 +553,9 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
             ST_CUDA(upload64(m->d_sam64, m->h_sam, gap_s, up_hi, d1));
             ST_CUDA(upload64(m->d_ref64, m->h_ref, gap_r, up_hi, d1));
         }
-        if (!have_means && nthr > 0) {           // the first FP64 rows are on their way; now the constants
-            while (means_done.load(std::memory_order_acquire) < nthr) std::this_thread::yield();
+        if (!have_means) {                       // the first FP64 rows are on their way; now the constants
+            if (nthr > 0) while (means_done.load(std::memory_order_acquire) < nthr) std::this_thread::yield();
+            else host_means(m, mu);
             if ((rc = table_set_means(m, mu.data(), m->s_comp))) return fail(rc);
             have_means = true;
         }
@@ -553,10 +567,6 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
         ST_CUDA(cudaEventRecord(ev[2 * b], m->s_copy));
         mark(m->s_copy);
         ST_CUDA(cudaStreamWaitEvent(m->s_comp, ev[2 * b], 0));
-        if (!have_means) {
-            if ((rc = table_means(m, m->s_comp))) return fail(rc);
-            have_means = true;
-        }
         if ((rc = table_center_rows(m, up_hi, std::max(up_hi, d1), m->s_comp))) return fail(rc);
         up_hi = hi;
         RoiView vb = v;
