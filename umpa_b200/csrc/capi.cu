@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <chrono>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -372,6 +373,16 @@ struct HostStage {
     size_t bytes = 0;
 } g_stage;
 
+// Measured rates of the two sides of the pipelined upload (this process, exponential average): how
+// fast the host threads convert while the DMA engine runs, and how fast the DMA engine moves FP64
+// rows.  They set the share of rows the host converts in the next call, so the split follows the
+// machine (cores and memory bandwidth left by other ranks / the caller) instead of a guess.
+struct HostRates {
+    std::mutex mu;
+    double conv_gbs = 0., dma_gbs = 0.;          // while both run (0 = not measured yet)
+    double dma_alone_gbs = 0.;                   // DMA engine with no conversion running (probed once)
+} g_rates;
+
 int host_threads()
 {
     if (const char *e = getenv("UMPA_HOST_THREADS")) return std::max(0, atoi(e));
@@ -418,13 +429,52 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
     int nthr = nb > 1 ? host_threads() : 0;
     int Yc = H;
     if (nthr > 0) {
-        // balance: DMA time (1 - x/2) D / B  ==  host time x D / Rc   (x = converted fraction)
-        const double Rc = std::min(85., 6.5 * nthr), Bp = 55.;
-        double x = 1. / (Bp / Rc + .5);
-        // pageable frames go through the driver's own staging at a fraction of the pinned rate: convert everything
+        // Which share x of the rows should the host convert?  Per input byte a converted row costs the
+        // host memory system 2 bytes of traffic (read, write FP32, DMA read of the FP32) against 1 for a
+        // row that goes up as FP64, and PCIe half a byte against one.  With M = B_conc + 1.5 R_conc the
+        // memory bandwidth this process got while both sides ran, and B_alone the DMA rate with nobody
+        // converting:   PCIe time (1 - x/2) D / B_alone  ==  memory time (1 + x) D / M
+        //           =>  x = (M - B_alone) / (M/2 + B_alone).
+        // On an idle host (B_conc = B_alone = B) this is the CPU balance x = 1 / (B/R + 1/2); when several
+        // ranks saturate the host memory (measured: 2 ranks on one 24-vCPU box, DMA 53 -> 40 GB/s,
+        // conversion 73 -> 36 GB/s) it backs off, down to plain DMA.
         cudaPointerAttributes pa{};
-        if (cudaPointerGetAttributes(&pa, m->h_sam[0]) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered) x = 1.;
+        const bool pinned = cudaPointerGetAttributes(&pa, m->h_sam[0]) == cudaSuccess && pa.type != cudaMemoryTypeUnregistered;
         cudaGetLastError();
+        double Ba, Bc, Rc;
+        {
+            std::lock_guard<std::mutex> lk(g_rates.mu);
+            if (pinned && g_rates.dma_alone_gbs == 0.) {       // once per process: ~128 MB of real rows, nobody converting
+                const int pr = std::max(1, std::min(H, (int)(((size_t)128 << 20) / ((size_t)Na * W * sizeof(double)))));
+                const size_t bytes = (size_t)pr * W * sizeof(double);
+                ptrdiff_t gap = Na > 1 ? m->h_sam[1] - m->h_sam[0] : (ptrdiff_t)H * W;
+                for (int k = 2; k < Na; k++) if (m->h_sam[k] - m->h_sam[k - 1] != gap) gap = 0;
+                cudaEvent_t e0 = nullptr, e1 = nullptr;
+                cudaEventCreate(&e0); cudaEventCreate(&e1);
+                cudaEventRecord(e0, m->s_copy);
+                if (gap >= (ptrdiff_t)H * W)
+                    cudaMemcpy2DAsync(m->d_sam64, (size_t)H * W * sizeof(double), m->h_sam[0], (size_t)gap * sizeof(double), bytes, Na,
+                                      cudaMemcpyHostToDevice, m->s_copy);
+                else
+                    for (int k = 0; k < Na; k++)
+                        cudaMemcpyAsync(m->d_sam64 + m->frame_off[k], m->h_sam[k], bytes, cudaMemcpyHostToDevice, m->s_copy);
+                cudaEventRecord(e1, m->s_copy);
+                float ms = 0.f;
+                if (cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess && ms > 0.f)
+                    g_rates.dma_alone_gbs = (double)Na * bytes / (ms * 1e-3) / 1e9;
+                cudaEventDestroy(e0); cudaEventDestroy(e1);
+                cudaGetLastError();
+            }
+            Ba = g_rates.dma_alone_gbs > 0. ? g_rates.dma_alone_gbs : 55.;
+            Bc = g_rates.dma_gbs > 0. ? g_rates.dma_gbs : Ba;
+            Rc = g_rates.conv_gbs > 0. ? g_rates.conv_gbs : std::min(85., 6.5 * nthr);
+        }
+        const double Mem = Bc + 1.5 * Rc;
+        double x = (Mem - Ba) / (.5 * Mem + Ba);
+        if (x < .15) x = 0.;                               // not worth the threads
+        x = std::min(x, .9);
+        // pageable frames go through the driver's own staging at a fraction of the pinned rate: convert everything
+        if (!pinned) x = 1.;
         if (const char *e = getenv("UMPA_HOST_FRAC")) x = atof(e);
         x = std::max(0., std::min(1., x));
         Yc = H - (int)(x * H);
@@ -474,8 +524,10 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
     for (int b = 0; b < nb; b++) left[b].store(nthr > 0 && cy1[b] > cy0[b] ? 2 * Na : 0);
     std::atomic<int> next_mean{0}, means_done{0}, next_job{0};
     std::atomic<bool> abort_flag{false};
+    using clk = std::chrono::steady_clock;
+    std::vector<clk::time_point> conv_t0(std::max(nthr, 1)), conv_t1(std::max(nthr, 1));
     const int rs = table_row_step(H);
-    auto worker = [&]() {
+    auto worker = [&](int wid) {
         for (;;) {
             const int f = next_mean.fetch_add(1);
             if (f >= 2 * Na) break;
@@ -483,6 +535,7 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
         }
         means_done.fetch_add(1, std::memory_order_acq_rel);
         while (means_done.load(std::memory_order_acquire) < nthr) std::this_thread::yield();
+        conv_t0[wid] = conv_t1[wid] = clk::now();
         for (;;) {
             const int j = next_job.fetch_add(1);
             if (j >= (int)jobs.size() || abort_flag.load()) break;
@@ -491,18 +544,21 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
             float *dst = g_stage.p + ((size_t)(q.stack * Na + q.frame) * HC + (q.y0 - Yc)) * pitch;
             host_center_rows(dst, src, q.y1 - q.y0, W, pitch, mu[q.stack == 0 ? q.frame : Na + q.frame]);
             left[q.band].fetch_sub(1, std::memory_order_acq_rel);
+            conv_t1[wid] = clk::now();
         }
     };
     std::vector<std::thread> pool;
-    for (int t = 0; t < nthr; t++) pool.emplace_back(worker);
+    for (int t = 0; t < nthr; t++) pool.emplace_back(worker, t);
 
     std::vector<cudaEvent_t> ev(2 * nb + 1, nullptr);
+    cudaEvent_t rate_ev[2] = {nullptr, nullptr}; // around the first band's FP64 rows: the DMA rate
     int rc = UMPA_OK;
     auto fail = [&](int code) {
         abort_flag.store(true);
         for (auto &t : pool) t.join();
         cudaStreamSynchronize(m->s_copy); cudaStreamSynchronize(m->s_comp); cudaStreamSynchronize(m->s_out);
         for (auto e : ev) if (e) cudaEventDestroy(e);
+        for (auto e : rate_ev) if (e) cudaEventDestroy(e);
         return code;
     };
 #define ST_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -542,6 +598,8 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
     };
 
     mark(m->s_copy);
+    size_t rate_bytes = 0;
+    if (nthr > 0) { cudaEventCreate(&rate_ev[0]); cudaEventCreate(&rate_ev[1]); cudaEventRecord(rate_ev[0], m->s_copy); }
     int up_hi = 0;                              // rows [0, up_hi) are on the device and centred
     bool have_means = false;
     int launches = 0;
@@ -552,6 +610,7 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
         if (d1 > up_hi) {
             ST_CUDA(upload64(m->d_sam64, m->h_sam, gap_s, up_hi, d1));
             ST_CUDA(upload64(m->d_ref64, m->h_ref, gap_r, up_hi, d1));
+            if (b == 0 && rate_ev[1]) { cudaEventRecord(rate_ev[1], m->s_copy); rate_bytes = (size_t)2 * Na * (d1 - up_hi) * rowb; }
         }
         if (!have_means) {                       // the first FP64 rows are on their way; now the constants
             if (nthr > 0) while (means_done.load(std::memory_order_acquire) < nthr) std::this_thread::yield();
@@ -607,6 +666,21 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
     for (auto e : ev) if (e) cudaEventDestroy(e);
     m->host_pending = false;
     m->fp64_missing = Yc < H;
+    if (nthr > 0 && !jobs.empty()) {             // update the measured rates
+        clk::time_point a = conv_t0[0], z = conv_t1[0];
+        for (int t = 1; t < nthr; t++) { a = std::min(a, conv_t0[t]); z = std::max(z, conv_t1[t]); }
+        const double secs = std::chrono::duration<double>(z - a).count();
+        const double conv = secs > 0. ? (double)2 * Na * HC * rowb / secs / 1e9 : 0.;
+        float ms = 0.f;
+        double dma = 0.;
+        if (rate_bytes && cudaEventElapsedTime(&ms, rate_ev[0], rate_ev[1]) == cudaSuccess && ms > 0.f) dma = rate_bytes / (ms * 1e-3) / 1e9;
+        std::lock_guard<std::mutex> lk(g_rates.mu);
+        if (conv > 0.) g_rates.conv_gbs = g_rates.conv_gbs > 0. ? .5 * (g_rates.conv_gbs + conv) : conv;
+        if (dma > 0.) g_rates.dma_gbs = g_rates.dma_gbs > 0. ? .5 * (g_rates.dma_gbs + dma) : dma;
+        if (trace) fprintf(stderr, "[umpa stream] host conversion %.1f GB/s, DMA %.1f GB/s (averages %.1f / %.1f, DMA alone %.1f)\n",
+                           conv, dma, g_rates.conv_gbs, g_rates.dma_gbs, g_rates.dma_alone_gbs);
+    }
+    for (auto e : rate_ev) if (e) cudaEventDestroy(e);
     m->stream_bands = nb; m->stream_threads = nthr; m->stream_host_rows = HC;
     return UMPA_OK;
 }
