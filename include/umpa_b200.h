@@ -153,6 +153,18 @@ UMPA_API int umpa_min(umpa_model *m, int i, int j, double *values, double uv[2],
  * UMPA/lib/Model.cpp:273-314).  out: (N0, N1) float64, host (on_device=0) or device. */
 UMPA_API int umpa_coverage(umpa_model *m, const int32_t roi[6], double *out, int on_device, void *stream);
 
+/* ---- post-processing of the displacement maps -------------------------------
+ * umpa_correct_bad_pixels replaces correct_bad_pixels(img, th, iterations, dims=(-2,-1))
+ * (UMPA/align.py:661-732) as UMPA_normal / UMPA_nobias apply it to dx and dy right after
+ * match() (align.py:58-60, 111-114), with the bias subtraction of UMPA_nobias fused in:
+ *   out = correct(img - bias),  values outside [lo, hi] replaced by the median of their four
+ *   neighbours (reflected at the edges exactly as the reference indexes them).
+ * All pointers are DEVICE pointers to (nimg, N0, N1) float64; bias may be NULL; scratch (same
+ * size) is needed when bias is given, when img == out, or for iterations > 1.  Asynchronous on
+ * `stream`.  (NaNs: fmin/fmax skip them, numpy's median propagates them.) */
+UMPA_API int umpa_correct_bad_pixels(const double *img, const double *bias, double *out, double *scratch,
+                            int64_t nimg, int N0, int N1, double lo, double hi, int iterations, void *stream);
+
 /* ---- introspection --------------------------------------------------------- */
 /* which path the last umpa_match used (UMPA_PATH_TABLE / UMPA_PATH_LAZY) and how
  * many kernels it launched */

@@ -195,3 +195,26 @@ class OracleModel:
 
 def max_threads():
     return lib().uo_max_threads()
+
+
+def correct_bad_pixels(img_in, th=None, iterations=1, p=0.5):
+    """Restatement of UMPA/align.py:661-732 for dims=(-2, -1) (numpy, test infrastructure only).
+    Values outside [-th, th] (or the p / 100-p percentiles, align.py:702-705) are replaced by the
+    median of their four neighbours; |i-1| reflects at the low edge, N-2 replaces N at the high
+    edge (align.py:720-727); every iteration gathers all neighbours before it assigns (713-731) and
+    revisits the SAME pixels (the mask is taken once, align.py:707-708)."""
+    img = np.array(img_in, copy=True)
+    lims = [np.percentile(img, p), np.percentile(img, 100 - p)] if th is None else [-th, th]
+    bad = (img < min(lims)) | (img > max(lims))
+    if not bad.any():
+        return img
+    N0, N1 = img.shape[-2:]
+    idx = np.nonzero(bad)
+    i, j = idx[-2], idx[-1]
+    lead = idx[:-2]
+    for _ in range(iterations):
+        nb = np.stack([img[lead + (np.abs(i - 1), j)], img[lead + (np.where(i + 1 == N0, N0 - 2, i + 1), j)],
+                       img[lead + (i, np.abs(j - 1))], img[lead + (i, np.where(j + 1 == N1, N1 - 2, j + 1))]])
+        nb.sort(axis=0)
+        img[idx] = (nb[1] + nb[2]) / 2.
+    return img

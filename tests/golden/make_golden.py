@@ -94,6 +94,43 @@ def run_case(name, kind, sam, ref, mask=None, pos=None, Nw=2, max_shift=4, abc=N
           f"calls {res['debug_Ncalls'][ok].mean() if ok.any() else 0:.2f}")
 
 
+def load_reference_align():
+    """The reference's own UMPA/align.py, imported from its file with the modules it does not need for
+    correct_bad_pixels stubbed (matplotlib is absent here; `import UMPA` would pull the whole package)."""
+    import importlib.util
+    import types
+    for name in ("matplotlib", "matplotlib.pyplot", "UMPA"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    spec = importlib.util.spec_from_file_location("ref_align", "/root/reference/UMPA/align.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_post():
+    """correct_bad_pixels (align.py:661-732) on displacement-like maps with outliers on edges and corners."""
+    A = load_reference_align()
+    rng = np.random.default_rng(21)
+    out = {}
+    img = rng.normal(0., .8, (40, 44))
+    img[rng.random(img.shape) < .03] = 7.5
+    img[rng.random(img.shape) < .03] = -9.
+    img[0, 0], img[0, 43], img[39, 0], img[39, 43], img[0, 10], img[39, 11], img[12, 0], img[13, 43] = 8, -8, 9, -9, 6, -6, 5, -5
+    img[20:23, 20:23] = 11.                       # a cluster: neighbours are bad too
+    stack = rng.normal(0., 1., (3, 20, 22))
+    stack[rng.random(stack.shape) < .05] = 6.
+    out["img"], out["stack"] = img, stack
+    out["img_th3_it1"] = A.correct_bad_pixels(img, 3)
+    out["img_th3_it2"] = A.correct_bad_pixels(img, 3, iterations=2)
+    out["img_th3_it3"] = A.correct_bad_pixels(img, 3, iterations=3)
+    out["img_auto"] = A.correct_bad_pixels(img)
+    out["img_auto_p5"] = A.correct_bad_pixels(img, p=5.)
+    out["stack_th4"] = A.correct_bad_pixels(stack, 4)
+    out["clean"] = A.correct_bad_pixels(np.clip(img, -2, 2), 3)
+    np.savez_compressed(os.path.join(HERE, "post_badpix.npz"), **out)
+    print("post_badpix written")
+
+
 def main():
     clean = synth.speckle_stack(5, 40, 44, seed=11, max_shift=4, dark_field=False)
     clean_df = synth.speckle_stack(5, 40, 44, seed=12, max_shift=4, dark_field=True)
@@ -149,6 +186,8 @@ def main():
     run_case("df_roi", "DF", clean_df["sam"], clean_df["ref"], ROI=((2, 20, 2), (1, 25, 3)))
     run_case("df_dxdy", "DF", clean_df["sam"], clean_df["ref"], dxdy=(1., -1.))
 
+    if not ONLY or "post_badpix" in ONLY:
+        make_post()
     if ONLY and "hooks" not in ONLY:
         return
     # module-level hooks (model.pyx:31-114; note spm -> spmin_quad, spmq -> spmin)

@@ -17,7 +17,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def golden_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                  if not p.endswith("hooks.npz"))
+                  if not p.endswith("hooks.npz") and not os.path.basename(p).startswith("post_"))
 
 
 def load_case(name):

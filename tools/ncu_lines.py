@@ -4,6 +4,7 @@ Usage: python tools/ncu_lines.py REP KERNEL_SUBSTRING [top]"""
 import csv, subprocess, sys, collections
 rep, pat = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+skip = int(sys.argv[4]) if len(sys.argv) > 4 else 0      # skip this many matching blocks (one block per source file)
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
                      capture_output=True, text=True).stdout
 blocks = txt.split('"File Path",')
@@ -11,6 +12,9 @@ for blk in blocks[1:]:
     lines = blk.split("\n")
     fname = lines[1]
     if pat not in fname:
+        continue
+    if skip > 0:
+        skip -= 1
         continue
     rdr = csv.reader(lines[2:])
     h = next(rdr)

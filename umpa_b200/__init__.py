@@ -10,5 +10,6 @@ from . import model                                    # noqa: F401
 from .model import (UMPAModelBase, UMPAModelDF, UMPAModelDFKernel,   # noqa: F401
                     UMPAModelNoDF)
 from .speckle_matching import match, match_unbiased    # noqa: F401
+from . import align                                    # noqa: F401  (correct_bad_pixels, UMPA_normal, UMPA_nobias)
 
 __version__ = "0.1"

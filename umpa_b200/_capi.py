@@ -12,7 +12,7 @@ PATH_AUTO, PATH_TABLE, PATH_LAZY = 0, 1, 2
 PATH_NAMES = {0: "none", 1: "table", 2: "lazy"}
 
 EXPORTS = ("umpa_create", "umpa_destroy", "umpa_set_frames", "umpa_set_window", "umpa_set_option",
-           "umpa_get_option", "umpa_match", "umpa_match_host", "umpa_cost", "umpa_min", "umpa_coverage",
+           "umpa_get_option", "umpa_match", "umpa_match_host", "umpa_cost", "umpa_min", "umpa_coverage", "umpa_correct_bad_pixels",
            "umpa_last_match_info", "umpa_last_stream_info", "umpa_set_profiling", "umpa_last_stage_ms", "umpa_device_bytes",
            "umpa_fma_peak", "umpa_last_error", "umpa_version")
 
@@ -63,6 +63,8 @@ def lib():
     L.umpa_min.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.umpa_coverage.restype = C.c_int
     L.umpa_coverage.argtypes = [vp, ip, vp, C.c_int, vp]
+    L.umpa_correct_bad_pixels.restype = C.c_int
+    L.umpa_correct_bad_pixels.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, vp]
     L.umpa_last_match_info.restype = C.c_int
     L.umpa_last_match_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.umpa_last_stream_info.restype = C.c_int

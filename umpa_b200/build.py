@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libumpa_b200.so")
-SOURCES = ["capi.cu", "lazy_path.cu", "table_path.cu", "kernel_path.cu", "hoststage.cu"]
+SOURCES = ["capi.cu", "lazy_path.cu", "table_path.cu", "kernel_path.cu", "hoststage.cu", "post.cu"]
 # shift_table_inst.cu is compiled once per window half-width (-1 = unfiltered table) so that the
 # template instantiations build in parallel: (source, extra flags, object tag)
 INSTANCES = [("shift_table_inst.cu", ["-DUMPA_INST_NW=%d" % nw], "nw%s" % ("m1" if nw < 0 else nw)) for nw in range(-1, 7)]
