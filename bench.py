@@ -42,6 +42,11 @@ CONFIGS = {
     "cfg5": dict(kind="NoDF", Na=4, H=2048, W=2048, Nw=6, ms=4, desc="UMPAModelNoDF 4x2048^2 Nw=6 max_shift=4"),
 }
 SAFE_CROP = {"NoDF": 0, "DF": 0, "DFKernel": 8}
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+# `ncu --set full` capture of the same command (profiles/r01d_epilogue_v2_ncu_summary.txt): the cross-table
+# kernel reads the two FP32 stacks once (0.85 GB) and writes the 81-plane table (1.30 GB).
+NCU_TRAFFIC = {("cfg2", 1): 851.6e6 + 1.3024e9}
+NCU_TRAFFIC_SOURCE = "profiles/r01d_epilogue_v2_ncu_summary.txt (ncu --set full, shift_table_kernel<9,3,2>)"
 
 
 def algorithmic_flops_per_px(cfg):
@@ -377,7 +382,8 @@ def ours(args, cfg):
                 "achieved": ach, "peak": peak.value, "unit": "TFLOP/s", "frac": ach / peak.value,
                 "peak_source": "FFMA probe measured in this run on this GPU (umpa_fma_peak); nominal %.1f"
                                % (sms.value * 128 * 2 * (peaks.get("sm_max_mhz", 1965.) * 1e6) / 1e12),
-                "traffic": None, "kernel_ms": stage_ms[1],
+                "traffic": NCU_TRAFFIC.get((args.config, world)), "traffic_source": NCU_TRAFFIC_SOURCE
+                if (args.config, world) in NCU_TRAFFIC else None, "kernel_ms": stage_ms[1],
                 "executed_tflops": exe, "executed_frac": exe / peak.value,
                 "note": note % ((f_exe / f_alg) if dfk else (f_alg / f_exe)),
                 "stage_ms": {"moments": stage_ms[0], "blur_table" if dfk else "cross_table": stage_ms[1],
