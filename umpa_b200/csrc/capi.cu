@@ -409,7 +409,7 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
     // when the final rows arrive (kernels and download hide behind the upload)
     std::vector<int> edge;                      // band b = output rows [edge[b], edge[b+1])
     {
-        int nu = std::max(1, std::min(12, v.N0 / 256));
+        int nu = std::max(1, std::min(10, v.N0 / 128));
         if (const char *e = getenv("UMPA_BANDS")) nu = std::max(1, std::min(v.N0, atoi(e)));
         const int rows_per = (v.N0 + nu - 1) / nu;
         for (int r = 0; r < v.N0; r += rows_per) edge.push_back(r);
