@@ -61,7 +61,9 @@ enum {
  *  LAZY:  one thread per pixel evaluates the reference's cost() on demand in FP64,
  *         in the reference's summation order (all models, masks, positions).
  *  AUTO:  TABLE when eligible, else LAZY. */
-enum { UMPA_PATH_AUTO = 0, UMPA_PATH_TABLE = 1, UMPA_PATH_LAZY = 2 };
+enum { UMPA_PATH_AUTO = 0, UMPA_PATH_TABLE = 1, UMPA_PATH_LAZY = 2,
+       UMPA_PATH_MIXED = 3 /* reported only: masked NoDF/DF -- TABLE where every mask value within reach of the
+                              pixel is exactly 1 (the masked and the unmasked cost agree there), LAZY elsewhere */ };
 
 /* Output maps of umpa_match*, all row-major (N0, N1); any pointer may be NULL to
  * skip that map.  Replaces the `values`, `err`, `debug_*` arrays that

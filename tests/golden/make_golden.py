@@ -170,6 +170,17 @@ def main():
     mask_b = .5 + .5 * rng.random(big["sam"].shape)
     run_case("dfk_masked", "DFKernel", big["sam"], big["ref"], mask=mask_b, Nw=1, max_shift=3)
 
+    # sparse masks (what real masks look like: ones, a dead block, a dead pixel, a down-weighted corner):
+    # most pixels have no mask value != 1 within reach
+    sp = synth.speckle_stack(5, 72, 76, seed=18, max_shift=4, dark_field=True)
+    msp = np.ones(sp["sam"].shape)
+    msp[1, 30:33, 40:43] = 0.
+    msp[3, 10, 12] = 0.
+    msp[:, 58:, :9] = .5
+    run_case("df_masked_sparse", "DF", sp["sam"], sp["ref"], mask=msp)
+    run_case("nodf_masked_sparse", "NoDF", sp["sam"], sp["ref"], mask=msp)
+    run_case("df_masked_sparse_ref", "DF", sp["sam"], sp["ref"], mask=msp, assign="ref")
+
     # sample stepping: ragged frames at integer offsets (model.pyx:265-283)
     pos = [(0, 0), (3, 0), (0, 5), (2, 2), (5, 4)]
     shapes = [(40, 44), (38, 44), (40, 40), (36, 42), (35, 40)]

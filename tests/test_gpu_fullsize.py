@@ -144,3 +144,43 @@ def test_cfg5_large_window_vs_lazy():
     exp = m.match(ROI=((1, 2028, 32), (2, 2028, 32)), quiet=True)
     got = {k: v[1::32, 2::32] for k, v in full.items()}
     compare_fp32(got, exp, label="cfg5 table-vs-lazy")
+
+
+def test_cfg2_masked_mixed_path():
+    """Config 2 with a realistic mask stack (ones, a few dead pixels, a dead block): pixels with no mask value
+    != 1 within reach are bit-identical to the unmasked model (table kernels), the others equal the FP64 lazy
+    path (the reference's masked arithmetic)."""
+    import time
+    import torch
+    from umpa_b200 import UMPAModelDF
+    d = _stacks(25, 2048, 2048, 5, True)
+    sam, ref = list(d["sam"]), list(d["ref"])
+    mask = torch.ones((25, 2048, 2048), dtype=torch.float64, device="cuda")
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for _ in range(60):
+        k, y, x = (int(torch.randint(0, n, (1,), generator=g)) for n in (25, 2048, 2048))
+        mask[k, y, x] = 0.
+    mask[7, 900:920, 1100:1130] = 0.
+    plain = UMPAModelDF(sam, ref, window_size=2, max_shift=5).match(quiet=True, debug=False)
+    m = UMPAModelDF(sam, ref, mask_list=list(mask), window_size=2, max_shift=5)
+    got = m.match(quiet=True, debug=False)
+    assert m.last_match_info["path"] == "mixed"
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    got = m.match(quiet=True, debug=False)
+    t_mixed = time.perf_counter() - t0
+    bad = (mask != 1.).any(dim=0)[None, None].double()
+    reach = torch.nn.functional.max_pool2d(bad, 15, stride=1, padding=7)[0, 0][7:-7, 7:-7].cpu().numpy() > 0
+    assert 0.001 < reach.mean() < .05
+    for k in ("f", "T", "dx", "dy", "df", "err"):
+        assert np.array_equal(got[k][~reach], plain[k][~reach]), k
+    m.cuda_path = "lazy"
+    roi = ((880, 940, 1), (1080, 1150, 1))
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    exp = m.match(ROI=roi, quiet=True, debug=False)
+    t_lazy_roi = time.perf_counter() - t0
+    sub = reach[880:940, 1080:1150]
+    assert sub.mean() > .2
+    for k in ("f", "T", "dx", "dy", "df", "err"):
+        assert np.array_equal(got[k][880:940, 1080:1150][sub], exp[k][sub]), k
+    print("masked config 2: mixed path %.1f ms (host maps included); lazy path on a %d-pixel ROI %.1f ms"
+          % (1e3 * t_mixed, exp["err"].size, 1e3 * t_lazy_roi))

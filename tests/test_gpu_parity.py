@@ -39,6 +39,29 @@ def test_table_path_equals_reference(name):
     print(name, st)
 
 
+@pytest.mark.parametrize("name", ["df_masked_sparse", "nodf_masked_sparse", "df_masked_sparse_ref", "df_masked", "nodf_masked"])
+def test_masked_models_mixed_path(name):
+    """Masked NoDF/DF: table kernels where every mask value within reach is 1, FP64 lazy evaluation on the
+    rest -- against the reference's golden vectors (err and the integer walk equal everywhere; the lazy
+    pixels to 1e-9, the table pixels to the FP32 criteria)."""
+    case = load_case(name)
+    m, got = run_case(case, "auto")
+    assert m.last_match_info["path"] == "mixed", m.last_match_info
+    exp = case["expected"]
+    compare_fp32(got, exp, tol=1e-4, label=name)
+    # the pixels the lazy kernel owns carry the reference's FP64 arithmetic
+    m.cuda_path = "lazy"
+    kw = {k: case[k] for k in ("step", "ROI", "dxdy") if case[k] is not None}
+    lazy = m.match(quiet=True, **kw)
+    same = np.ones(exp["err"].shape, bool)
+    for k in ("dx", "dy", "T", "f"):
+        same &= got[k] == lazy[k]
+    frac = same.mean()
+    print(name, "lazy-owned fraction %.3f" % frac)
+    if "sparse" in name:
+        assert .05 < frac < .6, frac          # most pixels went through the tables
+
+
 @pytest.mark.parametrize("name", ["nodf_clean", "df_clean", "dfk_clean", "df_masked", "df_positions"])
 def test_cost_probes(name):
     case = load_case(name)

@@ -195,6 +195,7 @@ int make_roi(const umpa_model *m, const int32_t roi[6], const double uv0[2], Roi
     if (roi[4] <= roi[3]) v->N1 = 0;
     v->uv0[0] = uv0 ? uv0[0] : 0.; v->uv0[1] = uv0 ? uv0[1] : 0.;
     v->abc = nullptr; v->cover = nullptr; v->cover_threshold = 0.;
+    v->dirty = nullptr; v->dirty_want = 0;
     return UMPA_OK;
 }
 
@@ -226,6 +227,7 @@ void free_frames(umpa_model *m)
         if (p) cudaFree(p);
     m->d_consts = nullptr;
     m->h_sam.clear(); m->h_ref.clear(); m->h_mask.clear();
+    m->maskbad_valid = false;
     m->host_pending = false; m->fp64_missing = false;
     m->d_sam64 = m->d_ref64 = m->d_mask64 = nullptr;
     m->d_sam_ptrs = m->d_ref_ptrs = m->d_mask_ptrs = nullptr;
@@ -282,7 +284,7 @@ int ensure_resident(umpa_model *m, cudaStream_t st)
             const size_t n = (size_t)m->dim[2 * k] * m->dim[2 * k + 1];
             UMPA_CUDA(cudaMemcpyAsync(dsts[a] + m->frame_off[k], (*srcs[a])[k], n * sizeof(double), cudaMemcpyHostToDevice, st));
         }
-    if (m->host_pending && m->uniform && !m->masked) {
+    if (m->host_pending && m->uniform) {
         std::vector<double> mu;
         host_means(m, mu);
         int rc = table_alloc32(m);
@@ -316,6 +318,12 @@ int match_view(umpa_model *m, const RoiView &v, const umpa_outputs &out, cudaStr
     else if (out.df && m->kind != UMPA_DF) UMPA_CUDA(cudaMemsetAsync(out.df, 0, n * sizeof(double), st));
     std::string why;
     bool use_table = false;
+    if (m->path_opt != UMPA_PATH_LAZY && m->masked && m->kind != UMPA_DFKERNEL && table_eligible(m, v, nullptr, true)) {
+        // masks: table kernels where every mask value within reach is 1, FP64 lazy evaluation elsewhere
+        if ((rc = ensure_resident(m, st))) return rc;
+        m->last_path = UMPA_PATH_MIXED;
+        return mixed_match(m, v, out, st);
+    }
     if (m->path_opt != UMPA_PATH_LAZY) {
         use_table = table_eligible(m, v, &why);
         if (!use_table && m->path_opt == UMPA_PATH_TABLE) {
@@ -737,7 +745,7 @@ void umpa_destroy(umpa_model *m)
     if (!m) return;
     cudaDeviceSynchronize();      // blocks go back to the cache: nothing of this model may still be running
     free_frames(m);
-    for (Scratch *s : {&m->filtA, &m->filtB, &m->auxS, &m->auxR, &m->tabX, &m->tabM, &m->outbuf})
+    for (Scratch *s : {&m->filtA, &m->filtB, &m->auxS, &m->auxR, &m->tabX, &m->tabM, &m->outbuf, &m->maskbad, &m->dirty})
         if (s->p) pool_free(s->p, s->bytes);
     for (cudaStream_t st : {m->s_copy, m->s_comp, m->s_out})
         if (st) cudaStreamDestroy(st);

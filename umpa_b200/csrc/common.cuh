@@ -51,6 +51,10 @@ struct RoiView {
     const double *abc;           // (N0,N1,3) or nullptr
     const double *cover;         // (N0,N1) or nullptr
     double cover_threshold;
+    // masked models on the mixed path: dirty[n] != 0 where a mask value != 1 is within reach of the pixel;
+    // a kernel handles the pixel iff dirty == nullptr or (dirty[n] != 0) == dirty_want
+    const unsigned char *dirty;
+    int dirty_want;
 };
 
 // ---------------------------------------------------------------- the handle
@@ -101,6 +105,8 @@ struct umpa_model {
 
     // TABLE-path scratch (grow-only)
     Scratch filtA, filtB, auxS, auxR, tabX, tabM;
+    Scratch maskbad, dirty;                      // masked models: row-dilated "mask != 1" image [H][W], per-ROI dirty map
+    bool maskbad_valid = false;
     bool moments_valid = false;
 
     // bookkeeping
@@ -128,7 +134,8 @@ int table_means(umpa_model *m, cudaStream_t st);               // 2. centring co
 int table_center_rows(umpa_model *m, int y0, int y1, cudaStream_t st);   // 3. rows [y0,y1) of every frame -> centred FP32
 int table_set_means(umpa_model *m, const double *mu, cudaStream_t st);   // 2'. constants computed by the host (mu: 2*Na)
 int table_row_step(int H);                                     // rows y = 0, step, 2 step, ... define the centring constants
-bool table_eligible(const umpa_model *m, const RoiView &roi, std::string *why);
+bool table_eligible(const umpa_model *m, const RoiView &roi, std::string *why, bool ignore_masks = false);
+int mixed_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st);   // masked NoDF/DF
 int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st);
 
 // implemented in hoststage.cu (host code)

@@ -193,6 +193,7 @@ lazy_match_kernel(LazyView m, RoiView roi, umpa_outputs out, double *kern_ws, in
     if (xj >= roi.N1 || xi >= roi.N0) return;
     const size_t n = (size_t)xi * roi.N1 + xj;
     if (roi.cover && roi.cover[n] < roi.cover_threshold) return;   // model.pyx:480; outputs stay zero
+    if (roi.dirty && (roi.dirty[n] != 0) != (roi.dirty_want != 0)) return;   // mixed path: the table kernels own this pixel
 
     double *kern = nullptr;
     const size_t ks = (size_t)gridDim.x * gridDim.y * blockDim.x;

@@ -415,6 +415,7 @@ __global__ void __launch_bounds__(WALK_NT, WALK_MINB) table_walk_kernel(WalkPara
     if (xj >= roi.N1 || xi >= roi.N0) return;
     const size_t n = (size_t)xi * roi.N1 + xj;
     if (roi.cover && roi.cover[n] < roi.cover_threshold) return;
+    if (roi.dirty && (roi.dirty[n] != 0) != (roi.dirty_want != 0)) return;   // mixed path: the lazy kernel owns this pixel
     const int ty = roi.step0 * xi, tx = roi.step1 * xj;
     const float4 s = __ldg((RS ? w.auxR : w.auxS) + (size_t)(w.oy + ty) * w.pitch + (w.ox + tx));
     const double cd = __ldg(w.consts), cc = __ldg(w.consts + 1), dd = __ldg(w.consts + 2);
@@ -562,7 +563,7 @@ size_t plan_tiles(TableParams &p, int S, bool filter, int *nt)
 // FP64 device stacks -> centring constants + centred FP32 stacks (pitch multiple of 4 floats)
 int table_row_step(int H) { return std::max(1, H / 32); }
 
-static bool table_applicable(const umpa_model *m) { return m->uniform && !m->masked; }
+static bool table_applicable(const umpa_model *m) { return m->uniform; }
 
 int table_alloc32(umpa_model *m)
 {
@@ -632,11 +633,11 @@ int table_prepare_frames(umpa_model *m, cudaStream_t st)
     return table_center_rows(m, 0, m->H, st);
 }
 
-bool table_eligible(const umpa_model *m, const RoiView &roi, std::string *why)
+bool table_eligible(const umpa_model *m, const RoiView &roi, std::string *why, bool ignore_masks)
 {
     auto no = [&](const char *s) { if (why) *why = s; return false; };
     if (!m->uniform) return no("ragged frames or non-zero positions");
-    if (m->masked) return no("masks");
+    if (m->masked && !ignore_masks) return no("masks");
     if (!m->separable) return no("window is not separable");
     if (m->refshift && m->kind == UMPA_DFKERNEL) return no("DFKernel with reference_shift=1");
     if (m->kind == UMPA_DFKERNEL) {
@@ -790,5 +791,67 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         if ((rc = stage_check("walk", st))) return rc;
     }
     if (m->profiling) { UMPA_CUDA(cudaEventRecord(m->ev[4], st)); m->ev_valid = true; }
+    return UMPA_OK;
+}
+
+// ------------------------------------------------------------------ masked models: the mixed path
+//
+// With masks the weights g = m_r m_s / (m_r + m_s + 1e-8) (Utils.cpp:125-130) couple the two window
+// positions and do not factor, so the masked cost (Model.cpp:461-499, 775-847) is not a sum of
+// tables.  But where every mask value within reach of a pixel is exactly 1, g is the constant
+// 1/(2+1e-8) and every sum of the masked branch is that constant times the unmasked one: cost, T
+// and df are the unmasked ones (to 1e-16: sum w = 1 - 1e-16), and the coverage gate passes.  Real
+// masks are mostly ones (dead pixels, a beam stop), so: table kernels on the clean pixels, the FP64
+// lazy evaluation on the pixels with a mask value != 1 within +-padding.
+namespace {
+
+// any_k mask_k(y, x') != 1 for x' within +-pad of x  ->  bad[y][x]  (row-dilated; one pass over the mask stack)
+__global__ void mask_rows_kernel(const double *mask, int Na, int H, int W, int pad, unsigned char *bad)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const int x0 = max(0, x - pad), x1 = min(W - 1, x + pad);
+    unsigned char b = 0;
+    for (int k = 0; k < Na && !b; k++) {
+        const double *row = mask + ((size_t)k * H + y) * W;
+        for (int xx = x0; xx <= x1; xx++) b |= row[xx] != 1.;
+    }
+    bad[(size_t)y * W + x] = b;
+}
+
+// dirty[n] = any bad[y'][j] for y' within +-pad of the pixel's raw row
+__global__ void dirty_kernel(const unsigned char *bad, int H, int W, int pad, RoiView roi, unsigned char *dirty)
+{
+    const int xj = blockIdx.x * blockDim.x + threadIdx.x, xi = blockIdx.y;
+    if (xj >= roi.N1) return;
+    const int i = roi.off0 + roi.step0 * xi, j = roi.off1 + roi.step1 * xj;
+    unsigned char b = 0;
+    for (int y = max(0, i - pad); y <= min(H - 1, i + pad); y++) b |= bad[(size_t)y * W + j];
+    dirty[(size_t)xi * roi.N1 + xj] = b;
+}
+
+}  // namespace
+
+int mixed_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st)
+{
+    int rc;
+    const int H = m->H, W = m->W, pad = m->padding;
+    if (!m->maskbad_valid) {
+        if ((rc = scratch_reserve(m, m->maskbad, (size_t)H * W))) return rc;
+        mask_rows_kernel<<<dim3((W + 127) / 128, H), 128, 0, st>>>(m->d_mask64, m->Na, H, W, pad, (unsigned char *)m->maskbad.p);
+        UMPA_CUDA(cudaGetLastError());
+        m->maskbad_valid = true;
+    }
+    if ((rc = scratch_reserve(m, m->dirty, (size_t)roi.N0 * roi.N1))) return rc;
+    dirty_kernel<<<dim3((roi.N1 + 127) / 128, roi.N0), 128, 0, st>>>((const unsigned char *)m->maskbad.p, H, W, pad, roi,
+                                                                       (unsigned char *)m->dirty.p);
+    UMPA_CUDA(cudaGetLastError());
+    RoiView v = roi;
+    v.dirty = (const unsigned char *)m->dirty.p;
+    v.dirty_want = 0;
+    if ((rc = table_match(m, v, out, st))) return rc;
+    v.dirty_want = 1;
+    if ((rc = lazy_match(m, v, out, st))) return rc;
+    m->last_launches += 2;
     return UMPA_OK;
 }

@@ -340,6 +340,17 @@ class UMPAModelBase:
             step = None
         if debug is None:
             debug = DEBUG
+        if self._masked or not self._uniform:
+            # the coverage map gates pixels (model.pyx:427-431, 480): keep it on the device
+            dev = self.match_device(step=step, dxdy=dxdy, ROI=ROI, abc=abc, debug=debug)
+            dev.pop("_keepalive", None)
+            host = {}
+            for k, t in dev.items():       # device -> pinned host, one stream, one sync
+                h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                h.copy_(t, non_blocking=True)
+                host[k] = h
+            torch.cuda.current_stream().synchronize()
+            return {k: h.numpy() for k, h in host.items()}
         s0, s1 = self._convert_ROI_slice(ROI, step)
         self._set_ROI((s0, s1))                       # sticky, like the reference (model.pyx:406)
         N0, N1 = self._shape_of(s0, s1)
@@ -360,9 +371,6 @@ class UMPAModelBase:
                     abc = abc.detach().cpu().numpy()
                 abc_h = np.ascontiguousarray(abc, dtype=np.float64)
             cover_h, thr = None, 0.
-            if self._masked or not self._uniform:
-                cover_h = np.ascontiguousarray(self._coverage_device(s0, s1).cpu().numpy())
-                thr = .1 * float(cover_h.max()) / self._Na               # model.pyx:431
             uv0 = None
             if dxdy is not None:
                 uv0 = (C.c_double * 2)(float(dxdy[0]), float(dxdy[1]))   # model.pyx:463-465
