@@ -189,6 +189,16 @@ def main():
     run_case("df_positions", "DF", sam_p, ref_p, pos=pos)
     run_case("nodf_positions", "NoDF", sam_p, ref_p, pos=pos)
 
+    # larger sample-stepping set: 6 ragged frames at offsets up to 14 px (interior reached by all frames,
+    # rims reached by some, corners by none)
+    stp = synth.speckle_stack(6, 96, 100, seed=19, max_shift=4, dark_field=True)
+    pos6 = [(0, 0), (9, 0), (0, 14), (6, 7), (12, 3), (3, 11)]
+    shp6 = [(84, 86), (80, 90), (90, 80), (84, 84), (78, 88), (88, 82)]
+    sam6 = [stp["sam"][k][py:py + h, px:px + w].copy() for k, ((py, px), (h, w)) in enumerate(zip(pos6, shp6))]
+    ref6 = [stp["ref"][k][py:py + h, px:px + w].copy() for k, ((py, px), (h, w)) in enumerate(zip(pos6, shp6))]
+    run_case("df_positions_big", "DF", sam6, ref6, pos=pos6)
+    run_case("nodf_positions_big", "NoDF", sam6, ref6, pos=pos6, assign="ref")
+
     # options
     run_case("df_assign_ref", "DF", clean_df["sam"], clean_df["ref"], assign="ref")
     run_case("df_subpx0", "DF", clean_df["sam"], clean_df["ref"], subpx=0)

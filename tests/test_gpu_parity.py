@@ -62,6 +62,26 @@ def test_masked_models_mixed_path(name):
         assert .05 < frac < .6, frac          # most pixels went through the tables
 
 
+@pytest.mark.parametrize("name", ["df_positions", "nodf_positions", "df_positions_big", "nodf_positions_big"])
+def test_ragged_frames_mixed_path(name):
+    """Sample stepping (per-frame positions, ragged shapes): table kernels on the canvas where every frame either
+    contains the pixel's reach or misses it, FP64 lazy evaluation where a frame overlaps it partly."""
+    case = load_case(name)
+    m, got = run_case(case, "auto")
+    assert m.last_match_info["path"] == "mixed", m.last_match_info
+    exp = case["expected"]
+    st = compare_fp32(got, exp, tol=1e-4, label=name)
+    m.cuda_path = "lazy"
+    lazy = m.match(quiet=True)
+    same = np.ones(exp["err"].shape, bool)
+    for k in ("dx", "dy", "T", "f"):
+        same &= got[k] == lazy[k]
+    ok = exp["err"] == 1
+    print(name, st, "lazy-owned fraction of ok pixels %.3f, ok %.3f" % (same[ok].mean(), ok.mean()))
+    if "big" in name:
+        assert same[ok].mean() < .7
+
+
 @pytest.mark.parametrize("name", ["nodf_clean", "df_clean", "dfk_clean", "df_masked", "df_positions"])
 def test_cost_probes(name):
     case = load_case(name)

@@ -255,14 +255,15 @@ int zero_outputs(const umpa_outputs &o, size_t n, cudaStream_t st)
 // frames then go up in one piece, in bands, or partly converted.
 void host_means(const umpa_model *m, std::vector<double> &mu)
 {
-    const int Na = m->Na, rs = table_row_step(m->H);
+    const int Na = m->Na;
     mu.assign(2 * Na, 0.);
     std::atomic<int> next{0};
     auto work = [&]() {
         for (;;) {
             const int f = next.fetch_add(1);
             if (f >= 2 * Na) break;
-            mu[f] = host_sampled_mean(f < Na ? m->h_sam[f] : m->h_ref[f - Na], m->H, m->W, rs);
+            const int k = f < Na ? f : f - Na, fh = m->dim[2 * k], fw = m->dim[2 * k + 1];
+            mu[f] = host_sampled_mean(f < Na ? m->h_sam[k] : m->h_ref[k], fh, fw, table_row_step(fh));
         }
     };
     const int nt = std::max(1, std::min(8, std::min(2 * Na, (int)std::thread::hardware_concurrency() - 1)));
@@ -284,7 +285,7 @@ int ensure_resident(umpa_model *m, cudaStream_t st)
             const size_t n = (size_t)m->dim[2 * k] * m->dim[2 * k + 1];
             UMPA_CUDA(cudaMemcpyAsync(dsts[a] + m->frame_off[k], (*srcs[a])[k], n * sizeof(double), cudaMemcpyHostToDevice, st));
         }
-    if (m->host_pending && m->uniform) {
+    if (m->host_pending && (m->uniform || !m->masked)) {
         std::vector<double> mu;
         host_means(m, mu);
         int rc = table_alloc32(m);
@@ -318,8 +319,8 @@ int match_view(umpa_model *m, const RoiView &v, const umpa_outputs &out, cudaStr
     else if (out.df && m->kind != UMPA_DF) UMPA_CUDA(cudaMemsetAsync(out.df, 0, n * sizeof(double), st));
     std::string why;
     bool use_table = false;
-    if (m->path_opt != UMPA_PATH_LAZY && m->masked && m->kind != UMPA_DFKERNEL && table_eligible(m, v, nullptr, true)) {
-        // masks: table kernels where every mask value within reach is 1, FP64 lazy evaluation elsewhere
+    if (m->path_opt != UMPA_PATH_LAZY && (m->masked || !m->uniform) && m->kind != UMPA_DFKERNEL && table_eligible(m, v, nullptr, true)) {
+        // masks / ragged frames: table kernels on the pixels where they are exact, FP64 lazy evaluation elsewhere
         if ((rc = ensure_resident(m, st))) return rc;
         m->last_path = UMPA_PATH_MIXED;
         return mixed_match(m, v, out, st);
@@ -725,6 +726,13 @@ int umpa_create(umpa_model **out, int kind, int Na, const int32_t *dim, const in
         if (m->dim[2 * k] != m->dim[0] || m->dim[2 * k + 1] != m->dim[1] || m->pos[2 * k] || m->pos[2 * k + 1]) m->uniform = false;
     }
     m->H = m->dim[0]; m->W = m->dim[1];
+    if (!m->uniform) {                          // canvas: the rectangle circumscribing all frames (model.pyx:531-549)
+        m->H = m->W = 0;
+        for (int k = 0; k < Na; k++) {
+            m->H = std::max(m->H, m->pos[2 * k] + m->dim[2 * k]);
+            m->W = std::max(m->W, m->pos[2 * k + 1] + m->dim[2 * k + 1]);
+        }
+    }
     int rc = install_window(m, Nw, win);
     if (rc) { umpa_destroy(m); return rc; }
     double Q[96];

@@ -71,7 +71,7 @@ struct umpa_model {
     std::vector<int> dim, pos;                   // host copies
     std::vector<double> win;                     // K*K
     bool uniform = false;                        // equal shapes and zero positions
-    int H = 0, W = 0;                            // common shape when uniform
+    int H = 0, W = 0;                            // common shape when uniform, else the canvas circumscribing all frames
     bool separable = false;                      // win == g (x) g
     std::vector<double> g;                       // 1-D factor, K
     double win_sum = 0.;
@@ -134,8 +134,8 @@ int table_means(umpa_model *m, cudaStream_t st);               // 2. centring co
 int table_center_rows(umpa_model *m, int y0, int y1, cudaStream_t st);   // 3. rows [y0,y1) of every frame -> centred FP32
 int table_set_means(umpa_model *m, const double *mu, cudaStream_t st);   // 2'. constants computed by the host (mu: 2*Na)
 int table_row_step(int H);                                     // rows y = 0, step, 2 step, ... define the centring constants
-bool table_eligible(const umpa_model *m, const RoiView &roi, std::string *why, bool ignore_masks = false);
-int mixed_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st);   // masked NoDF/DF
+bool table_eligible(const umpa_model *m, const RoiView &roi, std::string *why, bool mixed = false);   // mixed: masks / ragged frames allowed
+int mixed_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st);   // masked or ragged NoDF/DF
 int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st);
 
 // implemented in hoststage.cu (host code)

@@ -49,13 +49,14 @@ constexpr int SUM_BLOCKS = 64;
 // they are), so they are defined as the mean over the rows y = 0, step, 2 step, ... : those
 // rows can be uploaded ahead of the rest (umpa_match_host pipelines the upload in row bands)
 // and the result does not depend on how the upload was split.
-// grid (SUM_BLOCKS, 2*Na): partial sums of the sampled rows of one FP64 frame (fixed order)
-__global__ void frame_partial_sums(const double *sam, const double *ref, int H, int W, int row_step, int Na,
+// grid (SUM_BLOCKS, 2*Na): partial sums of the sampled rows of one FP64 frame (fixed order).
+// Frames are addressed through the per-frame pointer / shape tables (they may be ragged).
+__global__ void frame_partial_sums(const double *const *sam, const double *const *ref, const int *dim, int Na,
                                    double *partials)
 {
-    const int f = blockIdx.y;
-    const size_t frame_elems = (size_t)H * W;
-    const double *src = (f < Na ? sam + (size_t)f * frame_elems : ref + (size_t)(f - Na) * frame_elems);
+    const int f = blockIdx.y, k = f < Na ? f : f - Na;
+    const double *src = f < Na ? sam[k] : ref[k];
+    const int H = dim[2 * k], W = dim[2 * k + 1], row_step = max(1, H / 32);     // table_row_step
     const int nrows = (H + row_step - 1) / row_step;
     double s = 0.;
     for (int r = blockIdx.x; r < nrows; r += SUM_BLOCKS) {
@@ -73,13 +74,14 @@ __global__ void frame_partial_sums(const double *sam, const double *ref, int H, 
 }
 
 // one block: constants of all 2*Na frames, then sum c_k d_k, sum c_k^2, sum d_k^2
-__global__ void finish_means(const double *partials, int Na, double inv_count, double *means64, float *mean_s,
+__global__ void finish_means(const double *partials, const int *dim, int Na, double *means64, float *mean_s,
                              float *mean_r, double *consts)
 {
     for (int f = threadIdx.x; f < 2 * Na; f += blockDim.x) {
+        const int k = f < Na ? f : f - Na, H = dim[2 * k], W = dim[2 * k + 1], rs = max(1, H / 32);
         double s = 0.;
         for (int b = 0; b < SUM_BLOCKS; b++) s += partials[(size_t)f * SUM_BLOCKS + b];
-        const double mu = s * inv_count;
+        const double mu = s / ((double)((H + rs - 1) / rs) * W);
         means64[f] = mu;
         if (f < Na) mean_s[f] = (float)mu; else mean_r[f - Na] = (float)mu;
     }
@@ -94,17 +96,22 @@ __global__ void finish_means(const double *partials, int Na, double inv_count, d
     }
 }
 
-// grid (ceil(pitch/256), y1-y0, 2*Na): x' = (float)(x - c) for rows [y0, y1)
-__global__ void center_frames(const double *sam, const double *ref, const double *means64, int Na, int H, int W,
-                              int pitch, int y0, float *sam32, float *ref32)
+// grid (ceil(pitch/256), y1-y0, 2*Na): rows [y0, y1) of the FP32 stacks, x' = (float)(x - c).
+// The FP32 stacks live on the common canvas (H x pitch per frame): frame k covers rows
+// [pos_k, pos_k + dim_k); outside its footprint the canvas holds the centred value of 0, so that a
+// window that does not touch the frame contributes exactly nothing to the uncentred sums.
+__global__ void center_frames(const double *const *sam, const double *const *ref, const int *dim, const int *pos,
+                              const double *means64, int Na, int H, int pitch, int y0, float *sam32, float *ref32)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = y0 + blockIdx.y, f = blockIdx.z;
     if (x >= pitch) return;
     const bool is_s = f < Na;
     const int k = is_s ? f : f - Na;
-    const double *src = (is_s ? sam : ref) + ((size_t)k * H + y) * W;
+    const int ly = y - pos[2 * k], lx = x - pos[2 * k + 1], fh = dim[2 * k], fw = dim[2 * k + 1];
+    const double *src = is_s ? sam[k] : ref[k];
     float *dst = (is_s ? sam32 : ref32) + ((size_t)k * H + y) * pitch;
-    dst[x] = x < W ? (float)(src[x] - means64[f]) : 0.f;
+    const double v = (ly >= 0 && ly < fh && lx >= 0 && lx < fw) ? src[(size_t)ly * fw + lx] : 0.;
+    dst[x] = (float)(v - means64[f]);
 }
 
 // ------------------------------------------------------------------ moments
@@ -563,7 +570,8 @@ size_t plan_tiles(TableParams &p, int S, bool filter, int *nt)
 // FP64 device stacks -> centring constants + centred FP32 stacks (pitch multiple of 4 floats)
 int table_row_step(int H) { return std::max(1, H / 32); }
 
-static bool table_applicable(const umpa_model *m) { return m->uniform; }
+// equal frames, or (unmasked) ragged frames / positions on the common canvas
+static bool table_applicable(const umpa_model *m) { return m->uniform || !m->masked; }
 
 int table_alloc32(umpa_model *m)
 {
@@ -585,10 +593,9 @@ int table_alloc32(umpa_model *m)
 int table_means(umpa_model *m, cudaStream_t st)
 {
     if (!table_applicable(m)) return UMPA_OK;
-    const int Na = m->Na, H = m->H, W = m->W, rs = table_row_step(H);
-    const double count = (double)((H + rs - 1) / rs) * W;
-    frame_partial_sums<<<dim3(SUM_BLOCKS, 2 * Na), 256, 0, st>>>(m->d_sam64, m->d_ref64, H, W, rs, Na, m->d_partials);
-    finish_means<<<1, 256, 0, st>>>(m->d_partials, Na, 1. / count, m->d_means64, m->d_mean_s, m->d_mean_r, m->d_consts);
+    const int Na = m->Na;
+    frame_partial_sums<<<dim3(SUM_BLOCKS, 2 * Na), 256, 0, st>>>(m->d_sam_ptrs, m->d_ref_ptrs, m->d_dim, Na, m->d_partials);
+    finish_means<<<1, 256, 0, st>>>(m->d_partials, m->d_dim, Na, m->d_means64, m->d_mean_s, m->d_mean_r, m->d_consts);
     UMPA_CUDA(cudaGetLastError());
     return UMPA_OK;
 }
@@ -620,7 +627,7 @@ int table_center_rows(umpa_model *m, int y0, int y1, cudaStream_t st)
 {
     if (!table_applicable(m) || y1 <= y0) return UMPA_OK;
     center_frames<<<dim3((m->pitch + 255) / 256, y1 - y0, 2 * m->Na), 256, 0, st>>>(
-        m->d_sam64, m->d_ref64, m->d_means64, m->Na, m->H, m->W, m->pitch, y0, m->d_sam32, m->d_ref32);
+        m->d_sam_ptrs, m->d_ref_ptrs, m->d_dim, m->d_pos, m->d_means64, m->Na, m->H, m->pitch, y0, m->d_sam32, m->d_ref32);
     UMPA_CUDA(cudaGetLastError());
     return UMPA_OK;
 }
@@ -633,11 +640,12 @@ int table_prepare_frames(umpa_model *m, cudaStream_t st)
     return table_center_rows(m, 0, m->H, st);
 }
 
-bool table_eligible(const umpa_model *m, const RoiView &roi, std::string *why, bool ignore_masks)
+bool table_eligible(const umpa_model *m, const RoiView &roi, std::string *why, bool mixed)
 {
     auto no = [&](const char *s) { if (why) *why = s; return false; };
-    if (!m->uniform) return no("ragged frames or non-zero positions");
-    if (m->masked && !ignore_masks) return no("masks");
+    if (!m->uniform && !mixed) return no("ragged frames or non-zero positions");
+    if (!m->uniform && m->masked) return no("masks together with ragged frames / positions");
+    if (m->masked && !mixed) return no("masks");
     if (!m->separable) return no("window is not separable");
     if (m->refshift && m->kind == UMPA_DFKERNEL) return no("DFKernel with reference_shift=1");
     if (m->kind == UMPA_DFKERNEL) {
@@ -830,12 +838,47 @@ __global__ void dirty_kernel(const unsigned char *bad, int H, int W, int pad, Ro
     dirty[(size_t)xi * roi.N1 + xj] = b;
 }
 
+// Ragged frames / per-frame positions (sample stepping, model.pyx:265-283): frame k takes part in a pixel's
+// cost only if the pixel +-padding lies inside it (Model.cpp:428-433, 716-719; wt stays Na).  On the canvas a
+// frame that does not overlap the pixel's reach contributes nothing, a frame that contains it contributes what
+// the reference reads: the table kernels are exact there.  A frame that overlaps the reach only PARTLY is
+// skipped by the reference but would leak into the tables: those pixels are dirty.
+__global__ void dirty_rect_kernel(const int *dim, const int *pos, int Na, int pad, RoiView roi, unsigned char *dirty)
+{
+    const int xj = blockIdx.x * blockDim.x + threadIdx.x, xi = blockIdx.y;
+    if (xj >= roi.N1) return;
+    const int i = roi.off0 + roi.step0 * xi, j = roi.off1 + roi.step1 * xj;
+    unsigned char b = 0;
+    for (int k = 0; k < Na; k++) {
+        const int py = pos[2 * k], px = pos[2 * k + 1], fh = dim[2 * k], fw = dim[2 * k + 1];
+        const int ri = i - py, rj = j - px;
+        const bool reach = !(ri - pad < 0 || ri + pad > fh || rj - pad < 0 || rj + pad > fw);
+        const bool overlap = i + pad >= py && i - pad < py + fh && j + pad >= px && j - pad < px + fw;
+        b |= !reach && overlap;
+    }
+    dirty[(size_t)xi * roi.N1 + xj] = b;
+}
+
 }  // namespace
 
 int mixed_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st)
 {
     int rc;
     const int H = m->H, W = m->W, pad = m->padding;
+    if (!m->masked) {
+        if ((rc = scratch_reserve(m, m->dirty, (size_t)roi.N0 * roi.N1))) return rc;
+        dirty_rect_kernel<<<dim3((roi.N1 + 127) / 128, roi.N0), 128, 0, st>>>(m->d_dim, m->d_pos, m->Na, pad, roi,
+                                                                            (unsigned char *)m->dirty.p);
+        UMPA_CUDA(cudaGetLastError());
+        RoiView v = roi;
+        v.dirty = (const unsigned char *)m->dirty.p;
+        v.dirty_want = 0;
+        if ((rc = table_match(m, v, out, st))) return rc;
+        v.dirty_want = 1;
+        if ((rc = lazy_match(m, v, out, st))) return rc;
+        m->last_launches += 1;
+        return UMPA_OK;
+    }
     if (!m->maskbad_valid) {
         if ((rc = scratch_reserve(m, m->maskbad, (size_t)H * W))) return rc;
         mask_rows_kernel<<<dim3((W + 127) / 128, H), 128, 0, st>>>(m->d_mask64, m->Na, H, W, pad, (unsigned char *)m->maskbad.p);
