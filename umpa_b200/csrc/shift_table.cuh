@@ -40,6 +40,8 @@ struct TableParams {
     int G, npass, nstage;
     int a_stage_floats, stage_floats;   // per-stage layout: A tile then B tile (128 B aligned)
     int tiles_x, tiles_y;               // tile grid (the kernel is persistent over it)
+    int FB;                             // frames per TMA box / ring stage
+    int dbg;                            // experiments only (UMPA_TAB_DBG): 1 = skip the epilogue, 2 = skip the FMA loop
 };
 
 constexpr int EXT_W = 32;          // extended tile width: one 128 B line per row
@@ -103,7 +105,8 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     const int grp = tid / TG, lt = tid - grp * TG;
     const int er = lt >> 3, ec = (lt & 7) << 2;      // strip: extended row, first extended column
     float *cbuf = sm + (size_t)p.nstage * p.stage_floats;                // [G*S][EH][EXT_W] (FILTER only)
-    const uint32_t stage_bytes = (uint32_t)(p.AH * p.AP + p.EH * EXT_W) * sizeof(float);
+    const uint32_t stage_bytes = (uint32_t)(p.FB * (p.AH * p.AP + p.EH * EXT_W)) * sizeof(float);
+    const int a_frame = p.AH * p.AP, b_frame = p.EH * EXT_W;             // one frame inside a stage
     const size_t plane_sz = (size_t)p.rows_p * p.cols_p;
 
     float gk[K];
@@ -119,7 +122,11 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     // ---- persistent CTA: tiles blockIdx.x, +gridDim.x, ... ; the frame ring runs across tiles ----
     const int ntiles = p.tiles_x * p.tiles_y;
     const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int per_tile = p.npass * p.Na;
+    // A ring stage holds FB consecutive frames (one TMA box per stack): a box costs ~450-500 cycles of
+    // TMA-unit time whatever its size (measured: A only, B only and both take the same time with the FMA
+    // loop and the epilogue switched off), so one box per frame capped the kernel at ~515 cycles per frame.
+    const int nbox = (p.Na + p.FB - 1) / p.FB;       // boxes per pass over the frames (the last one may run past Na: zero fill)
+    const int per_tile = p.npass * nbox;
     const int total = my_tiles * per_tile;
 
     // producer state (thread 0): next (tile, frame) to request, and where
@@ -137,7 +144,8 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         tma_load_3d(Bs, &mapB, pr_bx, pr_by, pr_frame, &full_bar[pr_stage]);
         pr_issued++;
         if (++pr_stage == p.nstage) pr_stage = 0;
-        if (++pr_frame == p.Na) pr_frame = 0;
+        pr_frame += p.FB;
+        if (pr_frame >= p.Na) pr_frame = 0;
         if (--pr_left == 0) { pr_left = per_tile; pr_tile += gridDim.x; pr_coords(); }
     };
     if (tid == 0) {
@@ -163,16 +171,18 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
                     for (int c = 0; c < 4; c++) acc[a][b][c] = 0.f;
 
-            for (int frame = 0; frame < p.Na; frame++) {
-                if (tid == 0 && !first && pr_issued < total) {           // refill the stage the previous frame used
+            for (int box = 0; box < nbox; box++) {
+                if (tid == 0 && !first && pr_issued < total) {           // refill the stage the previous box used
                     mbar_wait(&empty_bar[prev_stage], prev_phase);
                     issue_next();
                 }
                 first = false;
                 mbar_wait(&full_bar[stage], phase);
-                if (work) {
-                    const float *As = sm + (size_t)stage * p.stage_floats;
-                    const float *Bs = As + p.a_stage_floats;
+                const int nfr = min(p.FB, p.Na - box * p.FB);
+                if (work && !(p.dbg & 2))
+                  for (int fr = 0; fr < nfr; fr++) {
+                    const float *As = sm + (size_t)stage * p.stage_floats + fr * a_frame;
+                    const float *Bs = sm + (size_t)stage * p.stage_floats + p.a_stage_floats + fr * b_frame;
                     const float4 b4 = *reinterpret_cast<const float4 *>(Bs + er * EXT_W + ec);
                     const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
                     const float *arow0 = As + (er + si0) * p.AP + ec;
@@ -193,7 +203,7 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                                     acc[sh][sj][x] = fmaf(bv[x], av[DELTA + sj + x], acc[sh][sj][x]);
                         }
                     }
-                }
+                  }
                 __syncwarp();
                 if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);     // this warp is done with the stage
                 prev_stage = stage; prev_phase = phase;
@@ -201,7 +211,9 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             }
 
             // ---------------- epilogue of this pass ----------------
-            if (!FILTER) {
+            if (p.dbg & 1) {
+                if (work && tid == 0x7fffffff) p.table[0] = acc[0][0][0];      // keeps the accumulators alive
+            } else if (!FILTER) {
                 if (work) {
 #pragma unroll
                     for (int sh = 0; sh < SH; sh++) {

@@ -464,13 +464,13 @@ EncodeTiledFn encode_tiled_fn()
 }
 
 // 3-D map over a stack [Na][H][pitch] of floats, box (bw, bh, 1), zero fill outside [0,W)x[0,H)
-int make_stack_map(CUtensorMap *map, const float *base, int Na, int H, int W, int pitch, int bw, int bh)
+int make_stack_map(CUtensorMap *map, const float *base, int Na, int H, int W, int pitch, int bw, int bh, int bd = 1)
 {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) { umpa_set_error("cuTensorMapEncodeTiled is not available from the driver"); return UMPA_ERR_CUDA; }
     const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Na};
     const cuuint64_t strides[2] = {(cuuint64_t)pitch * sizeof(float), (cuuint64_t)pitch * H * sizeof(float)};
-    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -553,14 +553,25 @@ size_t plan_tiles(TableParams &p, int S, bool filter, int *nt)
     p.AP = EXT_W - 4 + 4 * NA4;
     *nt = p.G * p.EH * 8;
     auto up32 = [](int floats) { return (floats + 31) & ~31; };      // 128 B
-    p.a_stage_floats = up32(p.AH * p.AP);
-    p.stage_floats = p.a_stage_floats + up32(p.EH * EXT_W);
     const size_t cbuf = filter ? (size_t)p.G * S * p.EH * EXT_W * sizeof(float) : 0;
     const size_t budget = SMEM_CAP - 2048;
-    int ns = MAX_STAGES;
-    while (ns > 2 && (size_t)ns * p.stage_floats * sizeof(float) + cbuf > budget) ns--;
-    if ((size_t)ns * p.stage_floats * sizeof(float) + cbuf > budget) return 0;
-    p.nstage = std::min(ns, p.Na >= 8 ? MAX_STAGES : 6);     // measured: 8 stages help Na = 25 (+2 %), hurt Na = 4 (-14 %)
+    // frames per TMA box = per ring stage (see shift_table.cuh: a box costs the same TMA time whatever its
+    // size): split the Na frames into the fewest boxes of at most 9 frames, as long as 3 stages fit
+    // (2 at least).  Measured on config 2: FB 1 / 2 / 5 / 9 -> cross table 1.51 / 1.22 / 1.08 / 1.04 ms.
+    const int nboxes = (p.Na + 8) / 9;
+    p.FB = (p.Na + nboxes - 1) / nboxes;
+    if (const char *e = getenv("UMPA_TAB_FB")) p.FB = std::max(1, std::min(32, atoi(e)));
+    p.FB = std::max(1, std::min(p.FB, p.Na));
+    int ns = 0;
+    for (;; p.FB--) {
+        p.a_stage_floats = up32(p.FB * p.AH * p.AP);
+        p.stage_floats = p.a_stage_floats + up32(p.FB * p.EH * EXT_W);
+        ns = budget > cbuf ? (int)((budget - cbuf) / ((size_t)p.stage_floats * sizeof(float))) : 0;
+        if (ns >= 3 || p.FB == 1 || (ns >= 2 && p.FB <= 4)) break;
+    }
+    if (ns < 2) return 0;
+    p.nstage = std::min(ns, p.FB >= 4 ? 4 : MAX_STAGES);
+    if (const char *e = getenv("UMPA_TAB_DBG")) p.dbg = atoi(e);
     if (const char *e = getenv("UMPA_TAB_NST")) p.nstage = std::max(2, std::min(ns, atoi(e)));
     return (size_t)p.nstage * p.stage_floats * sizeof(float) + cbuf;
 }
@@ -745,8 +756,8 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         CUtensorMap ma, mb;
         // the moving operand (read at p + s): the reference, or (reference_shift) the sample
         const float *mov = m->refshift ? m->d_sam32 : m->d_ref32, *fix = m->refshift ? m->d_ref32 : m->d_sam32;
-        if ((rc = make_stack_map(&ma, mov, Na, H, m->W, pitch, px.AP, px.AH))) return rc;
-        if ((rc = make_stack_map(&mb, fix, Na, H, m->W, pitch, EXT_W, px.EH))) return rc;
+        if ((rc = make_stack_map(&ma, mov, Na, H, m->W, pitch, px.AP, px.AH, px.FB))) return rc;
+        if ((rc = make_stack_map(&mb, fix, Na, H, m->W, pitch, EXT_W, px.EH, px.FB))) return rc;
         px.table = (float *)m->tabX.p;
         px.tiles_x = px.cols_p / px.TW; px.tiles_y = px.rows_p / px.TH;
         dim3 grid(std::min(px.tiles_x * px.tiles_y, m->sm_count * ctas_per_sm()));
@@ -761,8 +772,8 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         CUtensorMap ma, mb;
         const float *mov = (const float *)(m->refshift ? m->filtB.p : m->filtA.p);
         const float *fix = (const float *)(m->refshift ? m->filtA.p : m->filtB.p);
-        if ((rc = make_stack_map(&ma, mov, Na, H, m->W, pitch, pm.AP, pm.AH))) return rc;
-        if ((rc = make_stack_map(&mb, fix, Na, H, m->W, pitch, EXT_W, pm.EH))) return rc;
+        if ((rc = make_stack_map(&ma, mov, Na, H, m->W, pitch, pm.AP, pm.AH, pm.FB))) return rc;
+        if ((rc = make_stack_map(&mb, fix, Na, H, m->W, pitch, EXT_W, pm.EH, pm.FB))) return rc;
         pm.table = (float *)m->tabM.p;
         pm.tiles_x = pm.cols_p / pm.TW; pm.tiles_y = pm.rows_p / pm.TH;
         dim3 grid(std::min(pm.tiles_x * pm.tiles_y, m->sm_count * ctas_per_sm()));
