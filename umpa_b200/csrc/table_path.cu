@@ -126,7 +126,7 @@ struct MomentsParams {
     int ty0, tx0;                // first tile (in tile units) of the bounding box
 };
 
-constexpr int MO_TH = 16, MO_TW = 64, MO_NT = 256;
+constexpr int MO_TH = 16, MO_TW = 64, MO_NT = 256, MO_FB = 2;     // MO_FB: frames per TMA box
 
 // One block filters a 16 x 64 tile of every frame of both stacks with the separable window and
 // accumulates the aux images.  Per frame:
@@ -146,7 +146,8 @@ moments_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_constant__
     constexpr int LPAD = (NW + 3) & ~3;                 // columns left of the tile in the TMA box
     constexpr int BW = MO_TW + 2 * LPAD, OFF = LPAD - NW;
     constexpr int NL4 = (OFF + 4 + 2 * NW + 3) / 4;     // float4 loads of one row-pass item
-    constexpr int RAW = ((ER * BW * 4 + 127) & ~127) / 4;    // floats per raw tile (128 B multiple)
+    constexpr int FR = ER * BW;                         // floats per raw frame tile (dense inside a TMA box)
+    constexpr int RAW = ((MO_FB * FR * 4 + 127) & ~127) / 4; // floats per stack and ring stage: MO_FB frames (128 B multiple)
     constexpr int S4 = MO_TW / 4;                       // output strips per row
     constexpr int NROW = 2 * ER * S4, NSQ = 2 * ER * (BW / 4);
     constexpr int RIT = (NROW + MO_NT - 1) / MO_NT, QIT = (NSQ + MO_NT - 1) / MO_NT;
@@ -167,15 +168,16 @@ moments_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_constant__
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     }
     __syncthreads();
-    auto request = [&](int k) {                         // thread 0: both raw tiles of frame k -> stage k & 1
-        float *dst = raw + (k & 1) * 2 * RAW;
-        mbar_expect_tx(&full_bar[k & 1], 2u * ER * BW * sizeof(float));
-        tma_load_3d(dst, &mapR, x0 - LPAD, y0 - NW, k, &full_bar[k & 1]);
-        tma_load_3d(dst + RAW, &mapS, x0 - LPAD, y0 - NW, k, &full_bar[k & 1]);
+    const int nbox = (p.Na + MO_FB - 1) / MO_FB;
+    auto request = [&](int b) {                         // thread 0: frames [b MO_FB, +MO_FB) of both stacks -> stage b & 1
+        float *dst = raw + (b & 1) * 2 * RAW;           // (one box per stack: a TMA box costs the same whatever its depth)
+        mbar_expect_tx(&full_bar[b & 1], 2u * MO_FB * FR * sizeof(float));
+        tma_load_3d(dst, &mapR, x0 - LPAD, y0 - NW, b * MO_FB, &full_bar[b & 1]);
+        tma_load_3d(dst + RAW, &mapS, x0 - LPAD, y0 - NW, b * MO_FB, &full_bar[b & 1]);
     };
-    if (tid == 0) { request(0); if (p.Na > 1) request(1); }
+    if (tid == 0) { request(0); if (nbox > 1) request(1); }
 
-    // row pass of the two tiles at `in` ([2][RAW]) -> rowbuf
+    // row pass of the two tiles at `in` (reference) and `in + RAW` (sample) -> rowbuf
     auto row_pass = [&](const float *in) {
 #pragma unroll
         for (int n = 0; n < RIT; n++) {
@@ -224,8 +226,9 @@ moments_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_constant__
     const size_t opix = (size_t)oy * p.pitch + ox;
 
     for (int k = 0; k < p.Na; k++) {
-        mbar_wait(&full_bar[k & 1], (k >> 1) & 1);
-        const float *in = raw + (k & 1) * 2 * RAW;
+        const int box = k / MO_FB, fr = k - box * MO_FB;
+        if (fr == 0) mbar_wait(&full_bar[box & 1], (box >> 1) & 1);
+        const float *in = raw + (box & 1) * 2 * RAW + fr * FR;
         row_pass(in);
 #pragma unroll
         for (int n = 0; n < QIT; n++) {                  // squares of the raw float4s this thread owns
@@ -237,8 +240,8 @@ moments_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_constant__
                 sq[n][2] = fmaf(t.z, t.z, sq[n][2]); sq[n][3] = fmaf(t.w, t.w, sq[n][3]);
             }
         }
-        __syncthreads();                                 // row buffer complete, stage k & 1 consumed
-        if (tid == 0 && k + 2 < p.Na) request(k + 2);
+        __syncthreads();                                 // row buffer complete; after a box's last frame its stage is consumed
+        if (tid == 0 && (fr == MO_FB - 1 || k == p.Na - 1) && box + 2 < nbox) request(box + 2);
         float a[4], b[4];
         col_pass(0, a);
         col_pass(1, b);
@@ -284,7 +287,7 @@ moments_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_constant__
 template <int NW> size_t moments_smem()
 {
     constexpr int ER = MO_TH + 2 * NW, LPAD = (NW + 3) & ~3, BW = MO_TW + 2 * LPAD;
-    return (size_t)4 * ((ER * BW * 4 + 127) & ~127) + (size_t)2 * ER * MO_TW * sizeof(float);
+    return (size_t)4 * ((MO_FB * ER * BW * 4 + 127) & ~127) + (size_t)2 * ER * MO_TW * sizeof(float);
 }
 
 // ------------------------------------------------------------------ table-driven walk
@@ -488,8 +491,8 @@ int launch_moments_nw(const MomentsParams &mp, const float *ref32, const float *
     constexpr int ER = MO_TH + 2 * NW, LPAD = (NW + 3) & ~3, BW = MO_TW + 2 * LPAD;
     CUtensorMap mr, ms;
     int rc;
-    if ((rc = make_stack_map(&mr, ref32, mp.Na, mp.H, mp.W, mp.pitch, BW, ER))) return rc;
-    if ((rc = make_stack_map(&ms, sam32, mp.Na, mp.H, mp.W, mp.pitch, BW, ER))) return rc;
+    if ((rc = make_stack_map(&mr, ref32, mp.Na, mp.H, mp.W, mp.pitch, BW, ER, MO_FB))) return rc;
+    if ((rc = make_stack_map(&ms, sam32, mp.Na, mp.H, mp.W, mp.pitch, BW, ER, MO_FB))) return rc;
     const size_t smem = moments_smem<NW>();
     UMPA_CUDA(cudaFuncSetAttribute(moments_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     moments_kernel<NW><<<grid, MO_NT, smem, st>>>(mr, ms, mp);
