@@ -119,9 +119,13 @@ __device__ inline int walk_minimise(Eval &eval, int subpx, const double *quad, F
 {
     enum { P_INIT, P_TOP, P_LO, P_HI, P_DECIDE, P_FILL, P_DONE };
     const double tol = 1e-8;                       // absolute, Optim.cpp:243
+    constexpr unsigned COL0 = 0x108421u, COL4 = 0x1084210u, ALL = 0x1ffffffu;
     int settled0 = 0, settled1 = 0, axis = 0, st = UMPA_ST_OK;
-    int phase = P_INIT, fill = 0, ip = 0, jp = 0;
+    int phase = P_INIT, ip = 0, jp = 0;
     bool up_m = false, up_p = false, skip_limit = false, finished = false;
+    // which entries of d hold an evaluated cost (the reference tests d < -0.5; a register bit is cheaper
+    // than a shared-memory load and lets the 4x4 fill find its next missing entry with one ffs)
+    unsigned known = 0;
     FitArgs keep = args;
 #pragma unroll
     for (int n = 0; n < 25; n++) d[n] = -1.;
@@ -133,20 +137,25 @@ __device__ inline int walk_minimise(Eval &eval, int subpx, const double *quad, F
         bool want = false;
         int e0 = 0, e1 = 0, slot = 12;
         while (!want && phase != P_DONE) {
-            if (phase == P_INIT) {
+            switch (phase) {
+            case P_INIT:
                 want = true; e0 = c0; e1 = c1; slot = 12;
-            } else if (phase == P_TOP) {
+                break;
+            case P_TOP:
                 if (!skip_limit && ncalls >= UMPA_MAX_CALLS) { st = 0; phase = P_DONE; }   // Optim.cpp:267,477
                 else { skip_limit = false; phase = P_LO; }
-            } else if (phase == P_LO) {
+                break;
+            case P_LO:
                 slot = axis ? 7 : 11;
-                if (d[slot] < -.5) { want = true; e0 = c0 - axis; e1 = c1 - (1 - axis); }
+                if (!((known >> slot) & 1u)) { want = true; e0 = c0 - axis; e1 = c1 - (1 - axis); }
                 else { up_m = d[slot] > d[12] + tol; phase = P_HI; }
-            } else if (phase == P_HI) {
+                break;
+            case P_HI:
                 slot = axis ? 17 : 13;
-                if (d[slot] < -.5) { want = true; e0 = c0 + axis; e1 = c1 + (1 - axis); }
+                if (!((known >> slot) & 1u)) { want = true; e0 = c0 + axis; e1 = c1 + (1 - axis); }
                 else { up_p = d[slot] > d[12] - tol; phase = P_DECIDE; }
-            } else if (phase == P_DECIDE) {
+                break;
+            case P_DECIDE: {
                 const int lo = axis ? 7 : 11, hi = axis ? 17 : 13;
                 if (up_m && up_p) {
                     const int dir = d[lo] < d[hi] ? -1 : 1;
@@ -155,7 +164,6 @@ __device__ inline int walk_minimise(Eval &eval, int subpx, const double *quad, F
                     else {
                         ip = d[17] < d[7] ? 1 : 0;
                         jp = d[13] < d[11] ? 1 : 0;
-                        fill = 0;
                         phase = P_FILL;
                     }
                 } else {
@@ -168,33 +176,40 @@ __device__ inline int walk_minimise(Eval &eval, int subpx, const double *quad, F
                             c0 += 1;
                             for (int n = 0; n < 20; n++) d[n] = d[n + 5];
                             for (int n = 20; n < 25; n++) d[n] = -1.;
+                            known >>= 5;
                         } else {
                             c1 += 1;
                             for (int n = 0; n < 24; n++) d[n] = d[n + 1];
                             for (int r = 0; r < 5; r++) d[5 * r + 4] = -1.;
+                            known = (known >> 1) & ~COL4;
                         }
                     } else {
                         if (axis) {
                             c0 -= 1;
                             for (int n = 24; n >= 5; n--) d[n] = d[n - 5];
                             for (int n = 0; n < 5; n++) d[n] = -1.;
+                            known = (known << 5) & ALL;
                         } else {
                             c1 -= 1;
                             for (int n = 24; n >= 1; n--) d[n] = d[n - 1];
                             for (int r = 0; r < 5; r++) d[5 * r] = -1.;
+                            known = (known << 1) & ~COL0 & ALL;
                         }
                     }
                     if (axis) settled0 = 0; else settled1 = 0;
                     phase = P_TOP;
                 }
-            } else {                               // P_FILL: next missing entry of the 4x4 block
-                while (fill < 16) {
-                    const int r = fill >> 2, q = fill & 3;
-                    slot = 5 * (ip + r) + jp + q;
-                    if (d[slot] < -.9) { want = true; e0 = c0 + ip + r - 2; e1 = c1 + jp + q - 2; break; }
-                    fill++;
-                }
-                if (!want) { finished = true; phase = P_DONE; }
+                break;
+            }
+            default: {                             // P_FILL: next missing entry of the 4x4 block (row-major)
+                const unsigned block = 0x7bdefu << (5 * ip + jp);       // 4 rows of 4 bits, 5 apart
+                const unsigned pending = block & ~known;
+                if (pending) {
+                    slot = __ffs(pending) - 1;
+                    want = true; e0 = c0 + slot / 5 - 2; e1 = c1 + slot % 5 - 2;
+                } else { finished = true; phase = P_DONE; }
+                break;
+            }
             }
         }
         if (!want) break;
@@ -207,20 +222,20 @@ __device__ inline int walk_minimise(Eval &eval, int subpx, const double *quad, F
 
         // ---- file the result ----
         d[slot] = v;
+        known |= 1u << slot;
         if (phase == P_INIT) { keep = args; phase = P_TOP; }
         else if (phase == P_LO) { up_m = v > d[12] + tol; if (!up_m) keep = args; phase = P_HI; }
         else if (phase == P_HI) { up_p = v > d[12] - tol; if (!up_p) keep = args; phase = P_DECIDE; }
-        else {                                     // P_FILL
-            if (v < d[12]) {                       // lower value off-axis: hard restart there
-                c0 = e0; c1 = e1;
+        else if (v < d[12]) {                      // P_FILL, lower value off-axis: hard restart there
+            c0 = e0; c1 = e1;
 #pragma unroll
-                for (int t = 0; t < 25; t++) d[t] = -1.;
-                d[12] = v;
-                args = keep;
-                settled0 = settled1 = 0;
-                skip_limit = true;
-                phase = P_TOP;
-            } else fill++;
+            for (int t = 0; t < 25; t++) d[t] = -1.;
+            d[12] = v;
+            known = 1u << 12;
+            args = keep;
+            settled0 = settled1 = 0;
+            skip_limit = true;
+            phase = P_TOP;
         }
     }
 
