@@ -43,10 +43,10 @@ CONFIGS = {
 }
 SAFE_CROP = {"NoDF": 0, "DF": 0, "DFKernel": 8}
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
-# `ncu --set full` capture of the same command (profiles/r01d_epilogue_v2_ncu_summary.txt): the cross-table
-# kernel reads the two FP32 stacks once (0.85 GB) and writes the 81-plane table (1.30 GB).
-NCU_TRAFFIC = {("cfg2", 1): 851.6e6 + 1.3024e9}
-NCU_TRAFFIC_SOURCE = "profiles/r01d_epilogue_v2_ncu_summary.txt (ncu --set full, shift_table_kernel<9,3,2>)"
+# `ncu --set full` capture of the same command (profiles/r01f_final_kernels_ncu_summary.txt): the cross-table
+# kernel reads the two FP32 stacks once (0.88 GB with the tile halos) and writes the 81-plane table (1.31 GB).
+NCU_TRAFFIC = {("cfg2", 1): 880.3e6 + 1.3138e9}
+NCU_TRAFFIC_SOURCE = "profiles/r01f_final_kernels_ncu_summary.txt (ncu --set full, shift_table_kernel<9,3,2>)"
 
 
 def algorithmic_flops_per_px(cfg):
