@@ -184,3 +184,63 @@ def test_cfg2_masked_mixed_path():
         assert np.array_equal(got[k][880:940, 1080:1150][sub], exp[k][sub]), k
     print("masked config 2: mixed path %.1f ms (host maps included); lazy path on a %d-pixel ROI %.1f ms"
           % (1e3 * t_mixed, exp["err"].size, 1e3 * t_lazy_roi))
+
+
+def test_pipelined_variants_bit_identical():
+    """The banded, host-converted call with a strided ROI / a start guess / the DFKernel model returns the
+    bits of the corresponding device-resident call (host constants in both: same centred FP32 stacks)."""
+    import torch
+    from umpa_b200 import UMPAModelDF, UMPAModelDFKernel, synth
+    d = _stacks(8, 1536, 1280, 5, True, pinned=True)
+    sam, ref = list(d["sam"].numpy()), list(d["ref"].numpy())
+    with _env(UMPA_BANDS=1, UMPA_HOST_THREADS=0):
+        base = UMPAModelDF(sam, ref, window_size=2, max_shift=5)
+        full = base.match(quiet=True, debug=False)
+    m = UMPAModelDF(sam, ref, window_size=2, max_shift=5)
+    got = m.match(step=3, quiet=True, debug=False)
+    assert m.last_stream_info["bands"] > 1 and m.last_stream_info["host_threads"] > 0, m.last_stream_info
+    for k in ("f", "T", "dx", "dy", "df", "err", "debug_Ncalls"):
+        assert np.array_equal(got[k], full[k][::3, ::3]), k
+    m = UMPAModelDF(sam, ref, window_size=2, max_shift=5)
+    g2 = m.match(dxdy=(1., -1.), ROI=((10, 1500, 1), (4, 1200, 1)), quiet=True, debug=False)
+    with _env(UMPA_BANDS=1, UMPA_HOST_THREADS=0):
+        b2 = UMPAModelDF(sam, ref, window_size=2, max_shift=5).match(dxdy=(1., -1.), ROI=((10, 1500, 1), (4, 1200, 1)),
+                                                                      quiet=True, debug=False)
+    for k in ("f", "T", "dx", "dy", "df", "err", "debug_Ncalls"):
+        assert np.array_equal(g2[k], b2[k]), k
+    # DFKernel, 3 bands + host conversion vs one band
+    sam3, ref3 = [s[:, :640] .copy() for s in sam[:4]], [r[:, :640].copy() for r in ref[:4]]
+    hs = [torch.from_numpy(x).pin_memory().numpy() for x in sam3]
+    hr = [torch.from_numpy(x).pin_memory().numpy() for x in ref3]
+    mk = UMPAModelDFKernel(hs, hr, window_size=2, max_shift=4)
+    abc = synth.blur_abc(*mk.sh)
+    gk = mk.match(abc=abc, quiet=True, debug=False)
+    assert mk.last_match_info["path"] == "table" and mk.last_stream_info["bands"] > 1
+    with _env(UMPA_BANDS=1, UMPA_HOST_THREADS=0):
+        bk = UMPAModelDFKernel(hs, hr, window_size=2, max_shift=4).match(abc=abc, quiet=True, debug=False)
+    for k in ("f", "T", "dx", "dy", "err", "debug_Ncalls"):
+        assert np.array_equal(gk[k], bk[k]), k
+
+
+def test_small_and_odd_shapes():
+    """Edge shapes through the table path: one frame, frames barely larger than the padding, widths that are
+    not multiples of 4, the smallest shift range -- against the lazy path."""
+    from umpa_b200 import UMPAModelDF, UMPAModelNoDF, synth
+    for (Na, H, W, Nw, ms, cls) in ((3, 40, 43, 1, 2, UMPAModelNoDF), (1, 30, 31, 2, 2, UMPAModelNoDF), (2, 17, 19, 2, 2, UMPAModelDF),
+                                    (3, 64, 70, 1, 3, UMPAModelNoDF), (5, 33, 129, 3, 4, UMPAModelDF)):
+        d = synth.speckle_stack(Na, max(H, 64), max(W, 64), seed=Na + H, max_shift=max(ms, 3),
+                                dark_field=cls is UMPAModelDF, amplitude=.4)
+        sam = [np.ascontiguousarray(x[:H, :W]) for x in d["sam"]]
+        ref = [np.ascontiguousarray(x[:H, :W]) for x in d["ref"]]
+        m = cls(sam, ref, window_size=Nw, max_shift=ms)
+        m.cuda_path = "lazy"
+        exp = m.match(quiet=True)
+        m.cuda_path = "table"
+        got = m.match(quiet=True)
+        assert m.last_match_info["path"] == "table" and got["f"].shape == exp["f"].shape
+        compare_fp32(got, exp, label="shape %s" % ((Na, H, W, Nw, ms),), max_exception_frac=.1)
+    # a 1x1 window on 3 frames is left to the FP64 path (too few samples per cost for FP32 sums)
+    d = synth.speckle_stack(3, 64, 70, seed=1, max_shift=3, dark_field=False, amplitude=.4)
+    m = UMPAModelNoDF(list(d["sam"]), list(d["ref"]), window_size=0, max_shift=3)
+    m.match(quiet=True)
+    assert m.last_match_info["path"] == "lazy"

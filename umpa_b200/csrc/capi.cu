@@ -392,6 +392,25 @@ struct HostRates {
     double dma_alone_gbs = 0.;                   // DMA engine with no conversion running (probed once)
 } g_rates;
 
+// do [lo, hi) lie inside one CUDA allocation (pinned host block)?  cuMemGetAddressRange through the runtime's
+// driver entry point; "no" when it cannot be told.
+bool same_allocation(const void *lo, const void *hi)
+{
+    typedef int (*RangeFn)(unsigned long long *, size_t *, unsigned long long);
+    static RangeFn fn = []() -> RangeFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) return nullptr;
+        return (RangeFn)p;
+    }();
+    if (!fn) return false;
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (fn(&base, &size, (unsigned long long)(uintptr_t)lo) != 0) { cudaGetLastError(); return false; }
+    return (unsigned long long)(uintptr_t)hi <= base + size;
+}
+
 int host_threads()
 {
     if (const char *e = getenv("UMPA_HOST_THREADS")) return std::max(0, atoi(e));
@@ -458,10 +477,11 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
                 const size_t bytes = (size_t)pr * W * sizeof(double);
                 ptrdiff_t gap = Na > 1 ? m->h_sam[1] - m->h_sam[0] : (ptrdiff_t)H * W;
                 for (int k = 2; k < Na; k++) if (m->h_sam[k] - m->h_sam[k - 1] != gap) gap = 0;
+                if (gap > 0 && !same_allocation(m->h_sam[0], m->h_sam[Na - 1] + (size_t)H * W)) gap = 0;
                 cudaEvent_t e0 = nullptr, e1 = nullptr;
                 cudaEventCreate(&e0); cudaEventCreate(&e1);
                 cudaEventRecord(e0, m->s_copy);
-                if (gap >= (ptrdiff_t)H * W)
+                if (gap >= (ptrdiff_t)H * W && gap * (ptrdiff_t)sizeof(double) < ((ptrdiff_t)1 << 31))
                     cudaMemcpy2DAsync(m->d_sam64, (size_t)H * W * sizeof(double), m->h_sam[0], (size_t)gap * sizeof(double), bytes, Na,
                                       cudaMemcpyHostToDevice, m->s_copy);
                 else
@@ -506,12 +526,16 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
     }
 
     // frames that are equally spaced slices of one host stack go up with one 2-D copy per stack and band
+    // (cudaMemcpy2D pitches are limited to cudaDevAttrMaxPitch = 2^31 - 1 bytes, and the whole source range has
+    //  to lie inside ONE pinned allocation: equally spaced frames from separate allocations are rejected)
+    const ptrdiff_t max_pitch = ((ptrdiff_t)1 << 31) - 1;
     auto spacing = [&](const std::vector<const double *> &h) -> ptrdiff_t {
+        if ((ptrdiff_t)H * W * (ptrdiff_t)sizeof(double) > max_pitch) return 0;
         if (Na < 2) return (ptrdiff_t)H * W;
         const ptrdiff_t d = h[1] - h[0];
-        if (d < (ptrdiff_t)H * W) return 0;
+        if (d < (ptrdiff_t)H * W || d * (ptrdiff_t)sizeof(double) > max_pitch) return 0;
         for (int k = 2; k < Na; k++) if (h[k] - h[k - 1] != d) return 0;
-        return d;
+        return same_allocation(h[0], h[Na - 1] + (size_t)H * W) ? d : 0;
     };
     const ptrdiff_t gap_s = spacing(m->h_sam), gap_r = spacing(m->h_ref);
 
@@ -602,8 +626,16 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
     // converted rows [y0, y1) (>= Yc) of every frame of one stack: staging -> centred FP32 device stack
     auto upload32 = [&](float *dst, int stack, int y0, int y1) -> cudaError_t {
         const size_t rb = (size_t)pitch * sizeof(float);
-        return cudaMemcpy2DAsync(dst + (size_t)y0 * pitch, (size_t)H * rb, g_stage.p + ((size_t)stack * Na * HC + (y0 - Yc)) * pitch,
-                                 (size_t)HC * rb, (size_t)(y1 - y0) * rb, Na, cudaMemcpyHostToDevice, m->s_copy);
+        const float *src = g_stage.p + ((size_t)stack * Na * HC + (y0 - Yc)) * pitch;
+        if ((ptrdiff_t)((size_t)H * rb) <= max_pitch)
+            return cudaMemcpy2DAsync(dst + (size_t)y0 * pitch, (size_t)H * rb, src, (size_t)HC * rb, (size_t)(y1 - y0) * rb, Na,
+                                     cudaMemcpyHostToDevice, m->s_copy);
+        for (int k = 0; k < Na; k++) {
+            cudaError_t e = cudaMemcpyAsync(dst + ((size_t)k * H + y0) * pitch, src + (size_t)k * HC * pitch, (size_t)(y1 - y0) * rb,
+                                            cudaMemcpyHostToDevice, m->s_copy);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
     };
 
     mark(m->s_copy);

@@ -661,6 +661,9 @@ bool table_eligible(const umpa_model *m, const RoiView &roi, std::string *why, b
     if (!m->uniform && m->masked) return no("masks together with ragged frames / positions");
     if (m->masked && !mixed) return no("masks");
     if (!m->separable) return no("window is not separable");
+    // a handful of samples per cost (e.g. a 1x1 window on 3 frames): the fit is nearly exact, cost << signal
+    // energy, and FP32 sums lose it to cancellation (367 of 2509 pixels off by > 1e-4 in that example)
+    if (m->K * m->K * m->Na < 25) return no("fewer than 25 samples per cost: FP32 sums too coarse");
     if (m->refshift && m->kind == UMPA_DFKERNEL) return no("DFKernel with reference_shift=1");
     if (m->kind == UMPA_DFKERNEL) {
         if (!ktable_supported(m->Nw, m->max_shift, roi.step0)) return no("DFKernel: (Nw, max_shift, step) outside the instantiated blur-table kernels");
