@@ -181,6 +181,9 @@ def main():
     run_case("nodf_masked_sparse", "NoDF", sp["sam"], sp["ref"], mask=msp)
     run_case("df_masked_sparse_ref", "DF", sp["sam"], sp["ref"], mask=msp, assign="ref")
 
+    # DFKernel with a sparse mask / with sample stepping (the blur widens the reach by 8 pixels)
+    run_case("dfk_masked_sparse", "DFKernel", sp["sam"], sp["ref"], mask=msp, Nw=1, max_shift=4)
+
     # sample stepping: ragged frames at integer offsets (model.pyx:265-283)
     pos = [(0, 0), (3, 0), (0, 5), (2, 2), (5, 4)]
     shapes = [(40, 44), (38, 44), (40, 40), (36, 42), (35, 40)]
@@ -198,6 +201,7 @@ def main():
     ref6 = [stp["ref"][k][py:py + h, px:px + w].copy() for k, ((py, px), (h, w)) in enumerate(zip(pos6, shp6))]
     run_case("df_positions_big", "DF", sam6, ref6, pos=pos6)
     run_case("nodf_positions_big", "NoDF", sam6, ref6, pos=pos6, assign="ref")
+    run_case("dfk_positions_big", "DFKernel", sam6, ref6, pos=pos6, Nw=1, max_shift=4)
 
     # options
     run_case("df_assign_ref", "DF", clean_df["sam"], clean_df["ref"], assign="ref")

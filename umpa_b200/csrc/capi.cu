@@ -319,7 +319,7 @@ int match_view(umpa_model *m, const RoiView &v, const umpa_outputs &out, cudaStr
     else if (out.df && m->kind != UMPA_DF) UMPA_CUDA(cudaMemsetAsync(out.df, 0, n * sizeof(double), st));
     std::string why;
     bool use_table = false;
-    if (m->path_opt != UMPA_PATH_LAZY && (m->masked || !m->uniform) && m->kind != UMPA_DFKERNEL && table_eligible(m, v, nullptr, true)) {
+    if (m->path_opt != UMPA_PATH_LAZY && (m->masked || !m->uniform) && table_eligible(m, v, nullptr, true)) {
         // masks / ragged frames: table kernels on the pixels where they are exact, FP64 lazy evaluation elsewhere
         if ((rc = ensure_resident(m, st))) return rc;
         m->last_path = UMPA_PATH_MIXED;
