@@ -72,3 +72,25 @@ def test_umpa_normal_and_nobias_wrappers():
         np.testing.assert_array_equal(n[k], plain[k])
     r = align.UMPA_normal(sam, ref, window=1, shift=3, ROI=(slice(2, 40, 2), slice(1, 60, 3)))
     assert r["dx"].shape == (19, 20)
+
+
+@pytest.mark.gpu
+def test_speckle_matching_wrappers():
+    """UMPA/speckle_matching.py:12-75: match / match_unbiased are the model calls they wrap."""
+    from umpa_b200 import UMPAModelDF, UMPAModelNoDF, match, match_unbiased, synth
+    d = synth.speckle_stack(5, 64, 72, seed=6, max_shift=4, dark_field=True)
+    sam, ref = list(d["sam"]), list(d["ref"])
+    a = match(sam, ref, 2)
+    b = UMPAModelDF(sam, ref, window_size=2).match(step=1, quiet=True)
+    for k in ("dx", "dy", "T", "df", "f", "err"):
+        np.testing.assert_array_equal(a[k], b[k])
+    assert "df" not in match(sam, ref, 2, df=False) and UMPAModelNoDF is not None
+    bias = UMPAModelDF(ref, ref, window_size=2).match(step=2, quiet=True)
+    u = match_unbiased(sam, ref, 2, step=2)
+    p = UMPAModelDF(sam, ref, window_size=2).match(step=2, quiet=True)
+    np.testing.assert_array_equal(u["dx"], p["dx"] - bias["dx"])
+    np.testing.assert_array_equal(u["dy"], p["dy"] - bias["dy"])
+    np.testing.assert_array_equal(match_unbiased(sam, ref, 2, step=2, bias=False)["dx"], p["dx"])
+    np.testing.assert_array_equal(match_unbiased(sam, ref, 2, step=2, bias=(1., 2.))["dy"], p["dy"] - 2.)
+    nc = [np.asfortranarray(s) for s in sam]
+    np.testing.assert_array_equal(match(nc, ref, 2)["dx"], a["dx"])

@@ -1,33 +1,43 @@
-"""Convenience wrappers with the reference's signatures (UMPA/speckle_matching.py:12-75)."""
+"""The two convenience entry points of the reference's ``UMPA/speckle_matching.py`` (lines 12-75),
+same names, arguments and result dictionaries, on top of the CUDA models."""
+import numpy as np
+
 from . import model
+
+_MODELS = {True: model.UMPAModelDF, False: model.UMPAModelNoDF}
+
+
+def _contiguous(frames, what):
+    """The reference warns and copies when a frame is not C-contiguous (speckle_matching.py:33-39)."""
+    if all(np.asarray(f).flags.c_contiguous for f in frames):
+        return frames
+    print('Warning: provided list of %s frames are not c contiguous - working with a copy.' % what)
+    return [np.ascontiguousarray(f) for f in frames]
+
+
+def _run(sample, reference, Nw, mask, step, dark_field):
+    pm = _MODELS[bool(dark_field)](sam_list=_contiguous(sample, 'sample'), ref_list=_contiguous(reference, 'reference'),
+                                   mask_list=mask, window_size=Nw)
+    return pm.match(step=step)
 
 
 def match(Isample, Iref, Nw, mask=None, step=1, max_shift=4, df=True):
-    """UMPA/speckle_matching.py:12-48.  Like the reference, ``max_shift`` is accepted but NOT
-    forwarded to the model (it is documented there as "currently ignored")."""
-    if any(not x.flags.c_contiguous for x in Isample):
-        print('Warning: provided list of sample frames are not c contiguous - working with a copy.')
-        Isample = [x.copy() for x in Isample]
-    if any(not x.flags.c_contiguous for x in Iref):
-        print('Warning: provided list of reference frames are not c contiguous - working with a copy.')
-        Iref = [x.copy() for x in Iref]
-    cls = model.UMPAModelDF if df else model.UMPAModelNoDF
-    PM = cls(sam_list=Isample, ref_list=Iref, mask_list=mask, window_size=Nw)
-    return PM.match(step=step)
+    """speckle_matching.py:12-48.  ``max_shift`` is accepted and, as in the reference (which documents it
+    as "currently ignored"), not forwarded: the model keeps its default of 4."""
+    return _run(Isample, Iref, Nw, mask, step, df)
 
 
 def match_unbiased(Isample, Iref, Nw, mask=None, step=1, max_shift=4, df=True, bias=True):
-    """UMPA/speckle_matching.py:51-75: subtract the bias found by matching Iref against itself."""
+    """speckle_matching.py:51-75: ``bias=True`` matches the reference stack against itself and subtracts
+    the displacement it finds, ``bias=False`` subtracts nothing, a ``(dx, dy)`` pair is subtracted as given."""
     if bias is True:
-        cls = model.UMPAModelDF if df else model.UMPAModelNoDF
-        PMref = cls(sam_list=Iref, ref_list=Iref, mask_list=mask, window_size=Nw)
-        bias_result = PMref.match(step=step)
-        dx, dy = bias_result['dx'], bias_result['dy']
+        self_match = _run(Iref, Iref, Nw, mask, step, df)
+        offset = (self_match['dx'], self_match['dy'])
     elif bias is False:
-        dx, dy = 0., 0.
+        offset = (0., 0.)
     else:
-        dx, dy = bias
-    result = match(Isample=Isample, Iref=Iref, Nw=Nw, mask=mask, step=step, max_shift=max_shift, df=df)
-    result['dx'] -= dx
-    result['dy'] -= dy
-    return result
+        offset = bias
+    out = _run(Isample, Iref, Nw, mask, step, df)
+    out['dx'] -= offset[0]
+    out['dy'] -= offset[1]
+    return out
