@@ -63,7 +63,13 @@ def executed_fma_per_px_cross(cfg):
     plus the separable filter (row pass on the extended rows, column pass).  Tile geometry of
     table_path.cu: extended tile 16 x 32, output tile (16-2Nw) x (32-2Nw)."""
     S, K, Na, Nw = 2 * cfg["ms"] - 1, 2 * cfg["Nw"] + 1, cfg["Na"], cfg["Nw"]
-    eh, ew = int(os.environ.get("UMPA_TAB_EH", "16")), 32
+    # extended tile height as plan_tiles (table_path.cu) picks it
+    def _cost(eh):
+        sh = 3 if S <= 9 else (2 if S <= 17 else 1)
+        g = min(384 // (eh * 8), -(-S // sh))
+        return eh / float(eh - 2 * Nw) * (1. + .15 * (-(-S // (g * sh)) - 1))
+    eh = min((e for e in (16, 24, 32, 48) if e - 2 * Nw >= 2), key=lambda e: (_cost(e), e))
+    eh, ew = int(os.environ.get("UMPA_TAB_EH", eh)), 32
     th, tw = eh - 2 * Nw, ew - 2 * Nw
     per_tile = S * S * (Na * eh * ew + K * eh * tw + K * th * tw)
     return per_tile / float(th * tw)

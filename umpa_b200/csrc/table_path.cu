@@ -545,7 +545,21 @@ size_t plan_tiles(TableParams &p, int S, bool filter, int *nt)
     const int NA4 = (delta + S + 3 + 3) / 4, SH = row_block_of(S);
     p.TW = (EXT_W - 2 * halo) & ~3;
     if (p.TW < 8) return 0;
-    p.EH = 16;                                         // 16 rows x 8 strips = 128 threads per group
+    // Extended tile height (EH rows x 8 strips = EH*8 threads per group).  A tall tile wastes less on the window
+    // halo (TH/EH) but leaves room for fewer groups, i.e. more passes over the frames.  Cost model fitted to
+    // measurements (config 5, Nw=6: EH 16/24/32/48 -> 2.14/1.20/1.19/1.02 ms; config 4, Nw=3, S=15: 16/24 ->
+    // 28.9/24.8 ms; config 2 stays at 16): rows computed per useful row, +15 % per extra pass.
+    p.EH = 16;
+    if (filter) {
+        double best = 1e30;
+        for (int eh : {16, 24, 32, 48}) {
+            if (eh - 2 * halo < 2) continue;
+            const int g = std::min(MAX_NT / (eh * 8), (S + SH - 1) / SH);
+            const int np = (S + g * SH - 1) / (g * SH);
+            const double cost = (double)eh / (eh - 2 * halo) * (1. + .15 * (np - 1));
+            if (cost < best - 1e-9) { best = cost; p.EH = eh; }
+        }
+    }
     if (const char *e = getenv("UMPA_TAB_EH")) p.EH = atoi(e);          // tuning knobs (experiments only)
     p.TH = p.EH - 2 * halo;
     if (p.TH < 2) return 0;
