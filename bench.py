@@ -376,7 +376,8 @@ def ours(args, cfg):
             f_exe = 2. * cfg["Na"] * ((K_ + S_ - 1) ** 2 * 17 ** 2 + (K_ + S_ - 1) * K_ * K_ * S_ + (K_ + S_ - 1) ** 2)
             kname = "ktable_kernel<Nw=%d,S=%d> (per-pixel blur tables)" % (cfg["Nw"], S_)
             note = ("achieved = SURVEY 8d direct-form flop/px x px / kernel time; the kernel executes that form "
-                    "(blur of the (K+S-1)^2 patch per frame), executed/algorithmic = %.2f")
+                    "(blur of the (K+S-1)^2 patch per frame; executed/algorithmic <= %.2f: kernel taps below 1e-10 of "
+                    "the pixel's largest tap are zero and the blur loops stop at the last non-zero row / column)")
         else:
             f_exe = 2. * executed_fma_per_px_cross(cfg)
             kname = "shift_table_kernel<S=%d,Nw=%d> (cross table)" % (2 * cfg["ms"] - 1, cfg["Nw"])

@@ -24,6 +24,8 @@
 // floats per frame, double-buffered with cp.async.  Lane (slot, y) owns patch row y of pixel
 // `slot` of its warp: PS accumulators, the 17 kernel taps of a row are applied to a register
 // row of PS+16 reference values (float4 LDS, conflict-free pitch), 17*PS FMAs per 13 LDS.128.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -131,6 +133,12 @@ __global__ void __launch_bounds__(KT_NT, 1) ktable_kernel(KTableParams p)
     for (int n = tid; n < K * K; n += KT_NT) W2[n] = __ldg(p.g + n / K) * __ldg(p.g + n % K);
 
     // ---- this warp's blur kernels: k = exp(-a i^2 - b i j - c j^2) / sum, FP64, stored as FP32 ----
+    // Support of the FP32 kernels: taps below 1e-10 of the pixel's largest tap are set to zero (the Gaussian of a
+    // typical (a, b, c) ~ 0.5 is that small beyond |i| = 6; what is dropped is far below the FP32 rounding of the
+    // 289-term sum, and sigma is the sum of the taps that remain, so the centring identity stays exact).  RI / RJ:
+    // largest |i| / |j| with a non-zero tap among this warp's pixels -- the blur loops stop there.  (A pixel's
+    // result does not depend on which other pixel shares its warp: the extra taps it may be run over are zeros.)
+    int RI = 0, RJ = 0;
     float dsig_mine = 0.f;                             // sigma - 1 of this lane's pixel
     for (int s = 0; s < PPW; s++) {
         const int pli = warp * PPW + s, xis = xi0 + pli;
@@ -149,17 +157,33 @@ __global__ void __launch_bounds__(KT_NT, 1) ktable_kernel(KTableParams p)
             part += v[t];
         }
         const double norm = warp_sum(part);
-        double sp = 0.;
+        double sp = 0., vmax = 0.;
+#pragma unroll
+        for (int t = 0; t < NE; t++) vmax = fmax(vmax, v[t]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
         float *kd = Ks + pli * KPIX;
+        int ri = 0, rj = 0;
 #pragma unroll
         for (int t = 0; t < NE; t++) {
             const int e = lane + 32 * t;
             if (e < KSIDE * KSIDE) {
-                const float kf = (float)(v[t] / norm);
+                const bool keep = !(v[t] < 1e-10 * vmax);      // (NaN-safe: a broken kernel keeps its full support)
+                const float kf = keep ? (float)(v[t] / norm) : 0.f;
                 kd[(e / KSIDE) * KROW + e % KSIDE] = kf;
                 sp += (double)kf;
+                if (keep) {
+                    ri = max(ri, abs(e / KSIDE - UMPA_KWS));
+                    rj = max(rj, abs(e % KSIDE - UMPA_KWS));
+                }
             }
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ri = max(ri, __shfl_xor_sync(0xffffffffu, ri, o));
+            rj = max(rj, __shfl_xor_sync(0xffffffffu, rj, o));
+        }
+        RI = max(RI, ri); RJ = max(RJ, rj);
         for (int e = lane; e < KSIDE * (KROW - KSIDE); e += 32)
             kd[(e / (KROW - KSIDE)) * KROW + KSIDE + e % (KROW - KSIDE)] = 0.f;
         const double sig = warp_sum(sp);
@@ -202,24 +226,31 @@ __global__ void __launch_bounds__(KT_NT, 1) ktable_kernel(KTableParams p)
 #pragma unroll
         for (int x = 0; x < PS; x++) acc[x] = 0.f;
         const float *Rb = Rbuf + (k & 1) * p.RR * RP + (prow + yc) * RP;
+        // rows ii in [8-RI, 8+RI]; columns jj in [8-JR, 8+JR] with JR the compile-time bound >= RJ
+        auto blur = [&](auto jrc) {
+            constexpr int JR = decltype(jrc)::value;
 #pragma unroll 1
-        for (int ii = 0; ii < KSIDE; ii++) {
-            float r[4 * NR4], kk[KROW];
+            for (int ii = UMPA_KWS - RI; ii <= UMPA_KWS + RI; ii++) {
+                float r[4 * NR4], kk[KROW];
 #pragma unroll
-            for (int v4 = 0; v4 < NR4; v4++) {
-                const float4 t = *reinterpret_cast<const float4 *>(Rb + ii * RP + 4 * v4);
-                r[4 * v4] = t.x; r[4 * v4 + 1] = t.y; r[4 * v4 + 2] = t.z; r[4 * v4 + 3] = t.w;
+                for (int v4 = 0; v4 < NR4; v4++) {
+                    const float4 t = *reinterpret_cast<const float4 *>(Rb + ii * RP + 4 * v4);
+                    r[4 * v4] = t.x; r[4 * v4 + 1] = t.y; r[4 * v4 + 2] = t.z; r[4 * v4 + 3] = t.w;
+                }
+#pragma unroll
+                for (int v4 = 0; v4 < KROW / 4; v4++) {
+                    const float4 t = *reinterpret_cast<const float4 *>(Kp + ii * KROW + 4 * v4);
+                    kk[4 * v4] = t.x; kk[4 * v4 + 1] = t.y; kk[4 * v4 + 2] = t.z; kk[4 * v4 + 3] = t.w;
+                }
+#pragma unroll
+                for (int jj = UMPA_KWS - JR; jj <= UMPA_KWS + JR; jj++)
+#pragma unroll
+                    for (int x = 0; x < PS; x++) acc[x] = fmaf(kk[jj], r[x + jj], acc[x]);
             }
-#pragma unroll
-            for (int v4 = 0; v4 < KROW / 4; v4++) {
-                const float4 t = *reinterpret_cast<const float4 *>(Kp + ii * KROW + 4 * v4);
-                kk[4 * v4] = t.x; kk[4 * v4 + 1] = t.y; kk[4 * v4 + 2] = t.z; kk[4 * v4 + 3] = t.w;
-            }
-#pragma unroll
-            for (int jj = 0; jj < KSIDE; jj++)
-#pragma unroll
-                for (int x = 0; x < PS; x++) acc[x] = fmaf(kk[jj], r[x + jj], acc[x]);
-        }
+        };
+        if (RJ <= 4) blur(std::integral_constant<int, 4>());
+        else if (RJ <= 6) blur(std::integral_constant<int, 6>());
+        else blur(std::integral_constant<int, 8>());
 
         const float tsc = 2.f * sigf * __ldg(p.mean_r + k);
 #pragma unroll
