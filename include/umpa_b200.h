@@ -182,6 +182,12 @@ UMPA_API int umpa_last_stage_ms(umpa_model *m, float *ms, int n);
 /* bytes of device memory currently owned by the handle */
 UMPA_API int64_t umpa_device_bytes(const umpa_model *m);
 
+/* Host helpers of the pipelined upload (hoststage.cu), exposed for CPU-side tests: the centring constant of
+ * a frame (mean over rows 0, step, 2 step, ...) and the FP64 -> centred FP32 conversion of `rows` rows of W
+ * doubles into rows of `pitch` floats (zero padded) -- the arithmetic of center_frames: (float)(x - c). */
+UMPA_API double umpa_host_sampled_mean(const double *frame, int H, int W, int step);
+UMPA_API void umpa_host_center_rows(float *dst, const double *src, int rows, int W, int pitch, double c);
+
 /* Measured FP32-FMA peak of the current device (dependent-free FFMA chains on all SMs, CUDA
  * events): the denominator of the FP32-FMA roofline that bench.py reports. */
 UMPA_API int umpa_fma_peak(double *tflops, int *sm_count);

@@ -87,3 +87,26 @@ def test_product_does_not_import_oracle():
     for fn in os.listdir(os.path.join(pkg, "csrc")):
         if fn.endswith((".cu", ".cuh")):
             assert "oracle" not in open(os.path.join(pkg, "csrc", fn)).read(), fn
+
+
+def test_host_staging_helpers():
+    """hoststage.cu without a GPU: the conversion is (float)(x - c) exactly (AVX2 and scalar tails, padded
+    pitch, unaligned destinations), the sampled mean is the mean of rows 0, step, 2 step, ..."""
+    import ctypes as C
+    from umpa_b200 import _capi
+    L = _capi.lib()
+    rng = np.random.default_rng(0)
+    for rows, W, pitch, off in ((7, 64, 64, 0), (5, 37, 40, 0), (3, 129, 132, 3), (1, 5, 8, 1)):
+        src = rng.normal(3., 2., (rows, W))
+        buf = np.full(rows * pitch + 8, np.float32(-7.), dtype=np.float32)
+        dst = buf[off:off + rows * pitch]
+        c = 2.9375 + 1e-9
+        L.umpa_host_center_rows(dst.ctypes.data_as(C.POINTER(C.c_float)), src.ctypes.data_as(C.POINTER(C.c_double)),
+                                rows, W, pitch, c)
+        out = dst.reshape(rows, pitch)
+        np.testing.assert_array_equal(out[:, :W], (src - c).astype(np.float32))
+        assert np.all(out[:, W:] == 0) and np.all(buf[:off] == -7) and np.all(buf[off + rows * pitch:] == -7)
+    fr = rng.normal(1., .5, (100, 77))
+    for step in (1, 3, 32, 1000):
+        got = L.umpa_host_sampled_mean(fr.ctypes.data_as(C.POINTER(C.c_double)), 100, 77, step)
+        assert abs(got - fr[::step].mean()) < 1e-13

@@ -62,3 +62,14 @@ void host_center_rows(float *dst, const double *src, int rows, int W, int pitch,
         for (int x = W; x < pitch; x++) d[x] = 0.f;
     }
 }
+
+// ---- test hooks (no GPU needed): the two host helpers above through the C ABI ----------------
+extern "C" UMPA_API double umpa_host_sampled_mean(const double *frame, int H, int W, int step)
+{
+    return host_sampled_mean(frame, H, W, step);
+}
+
+extern "C" UMPA_API void umpa_host_center_rows(float *dst, const double *src, int rows, int W, int pitch, double c)
+{
+    host_center_rows(dst, src, rows, W, pitch, c);
+}
