@@ -77,6 +77,38 @@ void pool_free(void *p, size_t bytes)
     g_pool_bytes += bytes;
 }
 
+// Pinned host chunks (16 KB) for the per-model constants, kept for the life of the process.
+namespace {
+constexpr size_t PIN_CHUNK = 16 * 1024;
+std::mutex g_pin_mu;
+std::vector<void *> g_pin_free;
+// one set of non-blocking streams per device, shared by the models of the process
+struct DevStreams { int dev; cudaStream_t s[3]; };
+std::mutex g_stream_mu;
+std::vector<DevStreams> g_streams;
+}  // namespace
+
+void *pinned_small_take(size_t bytes, bool *own)
+{
+    void *p = nullptr;
+    if (bytes <= PIN_CHUNK) {
+        *own = false;
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        if (!g_pin_free.empty()) { p = g_pin_free.back(); g_pin_free.pop_back(); return p; }
+        return cudaHostAlloc(&p, PIN_CHUNK, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+    }
+    *own = true;
+    return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+}
+
+void pinned_small_give(void *p, bool own)
+{
+    if (!p) return;
+    if (own) { cudaFreeHost(p); return; }
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    g_pin_free.push_back(p);
+}
+
 int scratch_reserve(umpa_model *m, Scratch &s, size_t bytes)
 {
     if (s.bytes >= bytes && s.p) return UMPA_OK;
@@ -135,6 +167,38 @@ void quad_matrix(double *Q /*6x16*/)
         }
 }
 
+// Arena layout (byte offsets; every array 256 B aligned).  The first part is fixed, the rest scales with Na.
+constexpr size_t ARENA_QUAD = 0;                                             // 96 doubles
+constexpr size_t ARENA_WIN = 1024;                                           // UMPA_MAX_K^2 doubles
+constexpr size_t ARENA_G = ARENA_WIN + ((UMPA_MAX_K * UMPA_MAX_K * 8 + 255) & ~(size_t)255);
+constexpr size_t ARENA_CONSTS = ARENA_G + 256;                               // 3 doubles
+constexpr size_t ARENA_FIXED = ARENA_CONSTS + 256;
+size_t arena_a256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+int arena_carve(umpa_model *m)
+{
+    const size_t Na = (size_t)m->Na;
+    const size_t per[] = {2 * Na * 4, 2 * Na * 4,            // dim, pos
+                          Na * 8, Na * 8, Na * 8,            // frame pointer tables
+                          Na * 4, Na * 4, 2 * Na * 8,        // mean_s, mean_r, means64
+                          2 * Na * 64 * 8};                  // partial sums (SUM_BLOCKS = 64)
+    size_t need = ARENA_FIXED;
+    for (size_t b : per) need += arena_a256(b);
+    need = (need + 65535) & ~(size_t)65535;                  // few distinct sizes -> the cache hits
+    UMPA_CUDA(pool_malloc((void **)&m->arena, need));
+    m->arena_bytes = need;
+    m->d_quad = (double *)(m->arena + ARENA_QUAD);
+    m->d_consts = (double *)(m->arena + ARENA_CONSTS);
+    char *p = m->arena + ARENA_FIXED;
+    auto take = [&](size_t b) { char *r = p; p += arena_a256(b); return r; };
+    m->d_dim = (int *)take(per[0]); m->d_pos = (int *)take(per[1]);
+    m->d_sam_ptrs = (const double **)take(per[2]); m->d_ref_ptrs = (const double **)take(per[3]);
+    m->d_mask_ptrs = (const double **)take(per[4]);
+    m->d_mean_s = (float *)take(per[5]); m->d_mean_r = (float *)take(per[6]);
+    m->d_means64 = (double *)take(per[7]); m->d_partials = (double *)take(per[8]);
+    return UMPA_OK;
+}
+
 // window bookkeeping: copy, separability test (w == r c^T / total), device copies
 int install_window(umpa_model *m, int Nw, const double *win)
 {
@@ -166,11 +230,16 @@ int install_window(umpa_model *m, int Nw, const double *win)
         for (int a = 0; a < K; a++) { m->g[a] = r[a] / sqrt(fabs(tot)) * (tot < 0 ? -1. : 1.); gf[a] = (float)m->g[a]; }
     // g (x) g = r r^T / tot = win.  Its float copy sums to win_sum only to FP32 accuracy; the
     // walk divides by the FP64 sum of the *float* factor products where it matters (see table_path.cu).
-    if (m->d_win) cudaFree(m->d_win);
-    if (m->d_g) cudaFree(m->d_g);
-    m->d_win = nullptr; m->d_g = nullptr;
-    UMPA_CUDA(cudaMalloc(&m->d_win, K * K * sizeof(double)));
-    UMPA_CUDA(cudaMalloc(&m->d_g, std::max(K, 1) * sizeof(float)));
+    if (m->win_own) { cudaFree(m->d_win); cudaFree(m->d_g); m->win_own = false; }
+    if (K <= UMPA_MAX_K) {                       // the arena holds a window of up to UMPA_MAX_K^2
+        m->d_win = (double *)(m->arena + ARENA_WIN);
+        m->d_g = (float *)(m->arena + ARENA_G);
+    } else {
+        m->d_win = nullptr; m->d_g = nullptr;
+        UMPA_CUDA(cudaMalloc(&m->d_win, K * K * sizeof(double)));
+        UMPA_CUDA(cudaMalloc(&m->d_g, K * sizeof(float)));
+        m->win_own = true;
+    }
     UMPA_CUDA(cudaMemcpy(m->d_win, win, K * K * sizeof(double), cudaMemcpyHostToDevice));
     UMPA_CUDA(cudaMemcpy(m->d_g, gf.data(), K * sizeof(float), cudaMemcpyHostToDevice));
     if (sep) {
@@ -221,19 +290,11 @@ void free_frames(umpa_model *m)
     const size_t b32 = (size_t)m->Na * m->H * m->pitch * sizeof(float);
     pool_free(m->d_sam64, b64); pool_free(m->d_ref64, b64); pool_free(m->d_mask64, b64);
     pool_free(m->d_sam32, b32); pool_free(m->d_ref32, b32);
-    for (void *p : {(void *)m->d_sam_ptrs, (void *)m->d_ref_ptrs, (void *)m->d_mask_ptrs,
-                    (void *)m->d_mean_s, (void *)m->d_mean_r, (void *)m->d_means64, (void *)m->d_partials,
-                    (void *)m->d_consts})
-        if (p) cudaFree(p);
-    m->d_consts = nullptr;
     m->h_sam.clear(); m->h_ref.clear(); m->h_mask.clear();
     m->maskbad_valid = false;
     m->host_pending = false; m->fp64_missing = false;
     m->d_sam64 = m->d_ref64 = m->d_mask64 = nullptr;
-    m->d_sam_ptrs = m->d_ref_ptrs = m->d_mask_ptrs = nullptr;
     m->d_sam32 = m->d_ref32 = nullptr;
-    m->d_mean_s = m->d_mean_r = nullptr;
-    m->d_means64 = m->d_partials = nullptr;
     m->frames_set = false;
 }
 
@@ -266,7 +327,10 @@ void host_means(const umpa_model *m, std::vector<double> &mu)
             mu[f] = host_sampled_mean(f < Na ? m->h_sam[k] : m->h_ref[k], fh, fw, table_row_step(fh));
         }
     };
-    const int nt = std::max(1, std::min(8, std::min(2 * Na, (int)std::thread::hardware_concurrency() - 1)));
+    size_t samples = 0;                          // what the threads share: small jobs are not worth a thread start
+    for (int k = 0; k < Na; k++) samples += (size_t)2 * ((m->dim[2 * k] + table_row_step(m->dim[2 * k]) - 1) / table_row_step(m->dim[2 * k])) * m->dim[2 * k + 1];
+    const int want = (int)std::min<size_t>(8, samples / 1000000 + 1);
+    const int nt = std::max(1, std::min(want, std::min(2 * Na, (int)std::thread::hardware_concurrency() - 1)));
     std::vector<std::thread> pool;
     for (int t = 1; t < nt; t++) pool.emplace_back(work);
     work();
@@ -304,9 +368,13 @@ int ensure_fp32(umpa_model *m, cudaStream_t st) { return m->host_pending ? ensur
 int ensure_streams(umpa_model *m)
 {
     if (m->s_comp) return UMPA_OK;
-    UMPA_CUDA(cudaStreamCreateWithFlags(&m->s_copy, cudaStreamNonBlocking));
-    UMPA_CUDA(cudaStreamCreateWithFlags(&m->s_comp, cudaStreamNonBlocking));
-    UMPA_CUDA(cudaStreamCreateWithFlags(&m->s_out, cudaStreamNonBlocking));
+    std::lock_guard<std::mutex> lk(g_stream_mu);
+    for (auto &d : g_streams)
+        if (d.dev == m->device) { m->s_copy = d.s[0]; m->s_comp = d.s[1]; m->s_out = d.s[2]; return UMPA_OK; }
+    DevStreams d{m->device, {nullptr, nullptr, nullptr}};
+    for (auto &st : d.s) UMPA_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    g_streams.push_back(d);
+    m->s_copy = d.s[0]; m->s_comp = d.s[1]; m->s_out = d.s[2];
     return UMPA_OK;
 }
 
@@ -765,14 +833,11 @@ int umpa_create(umpa_model **out, int kind, int Na, const int32_t *dim, const in
             m->W = std::max(m->W, m->pos[2 * k + 1] + m->dim[2 * k + 1]);
         }
     }
-    int rc = install_window(m, Nw, win);
+    int rc = arena_carve(m);
     if (rc) { umpa_destroy(m); return rc; }
+    if ((rc = install_window(m, Nw, win))) { umpa_destroy(m); return rc; }
     double Q[96];
     quad_matrix(Q);
-    if (cudaMalloc(&m->d_dim, 2 * Na * sizeof(int)) != cudaSuccess || cudaMalloc(&m->d_pos, 2 * Na * sizeof(int)) != cudaSuccess ||
-        cudaMalloc(&m->d_quad, sizeof(Q)) != cudaSuccess) {
-        umpa_set_error("cudaMalloc failed in umpa_create"); umpa_destroy(m); return UMPA_ERR_CUDA;
-    }
     cudaMemcpy(m->d_dim, m->dim.data(), 2 * Na * sizeof(int), cudaMemcpyHostToDevice);
     cudaMemcpy(m->d_pos, m->pos.data(), 2 * Na * sizeof(int), cudaMemcpyHostToDevice);
     cudaMemcpy(m->d_quad, Q, sizeof(Q), cudaMemcpyHostToDevice);
@@ -787,11 +852,9 @@ void umpa_destroy(umpa_model *m)
     free_frames(m);
     for (Scratch *s : {&m->filtA, &m->filtB, &m->auxS, &m->auxR, &m->tabX, &m->tabM, &m->outbuf, &m->maskbad, &m->dirty})
         if (s->p) pool_free(s->p, s->bytes);
-    for (cudaStream_t st : {m->s_copy, m->s_comp, m->s_out})
-        if (st) cudaStreamDestroy(st);
-    if (m->h_small) cudaFreeHost(m->h_small);
-    for (void *p : {(void *)m->d_dim, (void *)m->d_pos, (void *)m->d_win, (void *)m->d_quad, (void *)m->d_g})
-        if (p) cudaFree(p);
+    pinned_small_give(m->h_small, m->h_small_own);       // (the streams are shared per device and stay)
+    if (m->win_own) { cudaFree(m->d_win); cudaFree(m->d_g); }
+    if (m->arena) pool_free(m->arena, m->arena_bytes);
     for (int i = 0; i < 5; i++)
         if (m->ev[i]) cudaEventDestroy(m->ev[i]);
     delete m;
@@ -819,7 +882,6 @@ int umpa_set_frames(umpa_model *m, const double *const *sam, const double *const
     for (int a = 0; a < 3; a++) {
         if (!srcs[a]) continue;
         UMPA_CUDA(pool_malloc((void **)dsts[a], total * sizeof(double)));
-        UMPA_CUDA(cudaMalloc((void **)ptrs[a], Na * sizeof(double *)));
         std::vector<const double *> hp(Na);
         for (int k = 0; k < Na; k++) hp[k] = *dsts[a] + m->frame_off[k];
         UMPA_CUDA(cudaMemcpy((void *)*ptrs[a], hp.data(), Na * sizeof(double *), cudaMemcpyHostToDevice));

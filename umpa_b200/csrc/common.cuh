@@ -109,6 +109,14 @@ struct umpa_model {
     bool maskbad_valid = false;
     bool moments_valid = false;
 
+    // One device block for all the small per-model arrays (shapes, window, pointer tables, constants):
+    // carved once in umpa_create, recycled through the block cache -- callers create a model per
+    // projection, and a dozen cudaMalloc/cudaFree pairs per model cost more than a 256^2 match.
+    char *arena = nullptr;
+    size_t arena_bytes = 0;
+    bool win_own = false;                        // d_win / d_g outside the arena (window side > UMPA_MAX_K)
+    bool h_small_own = false;                    // h_small outside the pinned chunk pool
+
     // bookkeeping
     int last_path = 0, last_launches = 0;
     bool profiling = false;
@@ -118,7 +126,9 @@ struct umpa_model {
 };
 
 int scratch_reserve(umpa_model *m, Scratch &s, size_t bytes);
-cudaError_t pool_malloc(void **p, size_t bytes);   // cached cudaMalloc / cudaFree for big blocks
+cudaError_t pool_malloc(void **p, size_t bytes);   // cached cudaMalloc / cudaFree
+void *pinned_small_take(size_t bytes, bool *own);  // pinned host memory for constants on their way to the device
+void pinned_small_give(void *p, bool own);
 void pool_free(void *p, size_t bytes);
 
 // implemented in lazy_path.cu

@@ -609,11 +609,7 @@ int table_alloc32(umpa_model *m)
     const size_t n32 = (size_t)Na * m->H * m->pitch;
     UMPA_CUDA(pool_malloc((void **)&m->d_sam32, n32 * sizeof(float)));
     UMPA_CUDA(pool_malloc((void **)&m->d_ref32, n32 * sizeof(float)));
-    UMPA_CUDA(cudaMalloc(&m->d_mean_s, Na * sizeof(float)));
-    UMPA_CUDA(cudaMalloc(&m->d_mean_r, Na * sizeof(float)));
-    UMPA_CUDA(cudaMalloc(&m->d_means64, 2 * Na * sizeof(double)));
-    UMPA_CUDA(cudaMalloc(&m->d_consts, 3 * sizeof(double)));
-    UMPA_CUDA(cudaMalloc(&m->d_partials, (size_t)2 * Na * SUM_BLOCKS * sizeof(double)));
+    // (the constants and the partial sums live in the model's arena, capi.cu: arena_carve)
     m->dev_bytes += 2 * n32 * sizeof(float);
     return UMPA_OK;
 }
@@ -633,7 +629,10 @@ int table_set_means(umpa_model *m, const double *mu, cudaStream_t st)
     if (!table_applicable(m)) return UMPA_OK;
     const int Na = m->Na;
     const size_t nd = 2 * (size_t)Na + 3;
-    if (!m->h_small) UMPA_CUDA(cudaHostAlloc(&m->h_small, nd * sizeof(double) + 2 * Na * sizeof(float), cudaHostAllocDefault));
+    if (!m->h_small) {
+        m->h_small = pinned_small_take(nd * sizeof(double) + 2 * Na * sizeof(float), &m->h_small_own);
+        if (!m->h_small) { umpa_set_error("cudaHostAlloc failed for the model constants"); return UMPA_ERR_CUDA; }
+    }
     double *hd = (double *)m->h_small;
     float *hf = (float *)(hd + nd);
     double cd = 0., cc = 0., dd = 0.;
