@@ -397,7 +397,9 @@ struct TableEval {
             const double beta = (t3 * t4 - t5 * t6) * rden;
             args.t = beta + Kc;
             args.v = Kc;                  // dark field = Kc / t, divided once at the end
-            return (t1 + beta * beta * t2 + Kc * Kc * t3 - 2. * beta * t4 - 2. * Kc * t5 + 2. * beta * Kc * t6) * w.inv_Na;
+            // the reference's residual t1 + b^2 t2 + K^2 t3 - 2 b t4 - 2 K t5 + 2 b K t6 (Model.cpp:855-858) at the
+            // solution of the normal equations (b t2 + K t6 = t4, b t6 + K t3 = t5) is t1 - b t4 - K t5
+            return (t1 - beta * t4 - Kc * t5) * w.inv_Na;
         }
         args.t = t5 / t3;
         return (t1 - t5 * args.t) * w.inv_Na;
