@@ -16,17 +16,20 @@ constexpr int SMEM_CAP = 227 * 1024;
 // table[s][p] = sum_k A_k(p+s) * B_k(p)   (FILTER: then window-filtered over p)
 //
 // One CTA owns an output tile TH x TW and produces ALL S*S shifts for it.  Work split:
-//   * the extended tile (TH + 2*halo rows, 32 columns = TW + 2*halo) is cut into strips of
+//   * the extended tile (EH = TH + 2*halo rows, 32 columns = TW + 2*halo) is cut into strips of
 //     4 consecutive pixels; a thread owns one strip -> 8 strips per row, so every quarter
 //     warp reads one contiguous 128 B shared-memory line (conflict-free LDS.128);
 //   * G warp groups work on the same frame at the same time, group g accumulating shift rows
 //     [ (pass*G+g)*SH, +SH ): SH*S*4 FP32 accumulators per thread live in registers across all
 //     frames, so each frame tile is streamed through shared memory exactly once per pass;
 //   * frames arrive by TMA (cp.async.bulk.tensor, 3-D map over [Na][H][pitch], zero fill out
-//     of bounds) into a ring of NST stages guarded by full/empty mbarriers; thread 0 is the
-//     producer, nobody executes a per-frame __syncthreads();
-//   * epilogue (per shift row): accumulators -> shared, separable window filter (row pass in
-//     registers, column pass with 4-row register blocking), float4 stores to the table.
+//     of bounds) into a ring of NST stages of FB frames each (one box per stack and stage),
+//     guarded by full/empty mbarriers; thread 0 is the producer, nobody executes a per-frame
+//     __syncthreads();
+//   * epilogue (per shift row, window half-width compiled in): row pass of the separable window in
+//     registers (shuffles inside the 8-lane row group), row-filtered strips to the group's slice of
+//     shared memory, named barrier per group, column pass per thread (K float4 loads), float4
+//     stores to the table.
 
 struct TableParams {
     float *table;                // [S*S][rows_p][cols_p]

@@ -1,4 +1,5 @@
-// table_path.cu -- the fast CUDA path for UMPAModelNoDF / UMPAModelDF .match().
+// table_path.cu -- the fast CUDA path for .match(): UMPAModelNoDF / UMPAModelDF here, UMPAModelDFKernel
+// through kernel_path.cu; masked models and ragged frames through mixed_match (bottom of this file).
 //
 // What the reference computes per pixel p and integer shift s (UMPA/lib/Model.cpp:359-509,
 // 631-862; reference window moves: ia = i + shift, Model.cpp:415-421 / 695-701):
@@ -15,9 +16,10 @@
 //   * t4(p,s) = sum_k a_k(p+s) b_k(p) / sum w  with the per-frame filtered images
 //     a_k = w (*) R_k, b_k = w (*) S_k  -- again Na FMAs per (p,s);
 //   * t1 depends on p only, t2/t3/t6 on p+s only: they are images, computed once.
-// Frames are stored mean-centred in FP32 (x' = x - mean_k, centring done in FP64); the
+// Frames are stored centred in FP32 (x' = x - c_k, c_k = mean of the frame's sampled rows, FP64); the
 // uncentred sums are rebuilt in FP64 from the centred ones plus four cheap cross images,
 // so FP32 cancellation scales with the speckle variance instead of the mean squared.
+// assign_coordinates = 'ref' swaps the roles of the stacks and negates the shift (TableEval<RS>).
 // The per-pixel solve, the reference's integer walk (Optim.cpp:233-479) and the spline
 // refinement run in FP64 on those tables (walk.cuh).
 //
@@ -26,6 +28,8 @@
 //   moments_kernel     a_k, b_k stacks + aux images                (HBM bound)
 //   shift_table_kernel C_s + filter -> cross table;  a_k,b_k -> mean table (FP32 FMA / smem bound)
 //   table_walk_kernel  FP64 solve + walk + spline per pixel
+//   mask_rows_kernel / dirty_kernel / dirty_rect_kernel   which pixels of a masked / ragged model the
+//                      table kernels may own (the rest goes to lazy_path.cu)
 #include <cuda.h>
 
 #include <algorithm>
