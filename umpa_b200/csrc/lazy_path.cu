@@ -48,6 +48,31 @@ __device__ inline double blur_at(const double *__restrict__ img, int i, int j, i
     return out;
 }
 
+// The same blur for CB consecutive window elements (i, j .. j+CB-1) at once: every kernel tap is loaded once
+// and used CB times (the per-pixel kernels live in global memory: one load per MAC made the DFKernel
+// evaluation L2-bandwidth bound), the frame row segment sits in registers.  Each element's sum runs over
+// the taps in the order of blur_at, so the results are bit-identical.
+template <int CB>
+__device__ inline void blur_row_at(const double *__restrict__ img, int i, int j, int W,
+                                   const double *__restrict__ kern, size_t ks, double (&out)[CB])
+{
+#pragma unroll
+    for (int c = 0; c < CB; c++) out[c] = 0.;
+    for (int r = -UMPA_KWS; r <= UMPA_KWS; r++) {
+        const double *row = img + (size_t)(i + r) * W + j - UMPA_KWS;
+        const double *kr = kern + (size_t)(UMPA_KSIDE * (r + UMPA_KWS)) * ks;
+        double seg[UMPA_KSIDE + CB - 1];
+#pragma unroll
+        for (int t = 0; t < UMPA_KSIDE + CB - 1; t++) seg[t] = row[t];
+#pragma unroll
+        for (int q = 0; q < UMPA_KSIDE; q++) {
+            const double kv = kr[(size_t)q * ks];
+#pragma unroll
+            for (int c = 0; c < CB; c++) out[c] += kv * seg[q + c];
+        }
+    }
+}
+
 // mask-weighted blur (Utils.cpp:103-117)
 __device__ inline double weighted_blur_at(const double *__restrict__ img, const double *__restrict__ wgt,
                                           int i, int j, int W, const double *__restrict__ kern, size_t ks)
@@ -71,6 +96,31 @@ struct LazyEval {
     int i, j;
     const double *kern;       // DFKernel: this pixel's normalised 17x17 kernel (interleaved)
     size_t ks;                // stride between its elements
+
+    // DFKernel, unmasked: the window sums of one frame with the blur taken CB window columns at a time
+    // (blur_row_at); the last chunk of a row is moved back inside the window, elements are added to the
+    // sums in the reference's order (row-major), so nothing changes bitwise.
+    template <int CB>
+    __device__ void dfk_window(const double *__restrict__ R, const double *__restrict__ S, int r0, int rc0, int s0,
+                               int sc0, int W, int K, double &t1, double &t3, double &t5) const
+    {
+        for (int a = 0; a < K; a++)
+            for (int b0 = 0; b0 < K; b0 += CB) {
+                double rb[CB];
+                const int bs = min(b0, K - CB);
+                blur_row_at<CB>(R, r0 + a, rc0 + bs, W, kern, ks, rb);
+#pragma unroll
+                for (int c = 0; c < CB; c++) {
+                    const int b = bs + c;
+                    if (b >= b0) {
+                        const double w = m.win[a * K + b], s = S[(size_t)(s0 + a) * W + sc0 + b], r = rb[c];
+                        t1 += w * s * s;
+                        t3 += w * r * r;
+                        t5 += w * r * s;
+                    }
+                }
+            }
+    }
 
     __device__ int operator()(int si, int sj, double &cost, FitArgs &args) const
     {
@@ -129,6 +179,9 @@ struct LazyEval {
                 t2 += m.masked ? mean * mean * s2 : mean * mean;
                 t4 += mean * s4;
                 t6 += mean * s6;
+            } else if (m.kind == UMPA_DFKERNEL && !m.masked && K >= 4) {
+                if (K >= 7) dfk_window<7>(R, S, r0, rc0, s0, sc0, W, K, t1, t3, t5);
+                else dfk_window<4>(R, S, r0, rc0, s0, sc0, W, K, t1, t3, t5);
             } else {
                 for (int a = 0; a < K; a++)
                     for (int b = 0; b < K; b++) {
