@@ -244,3 +244,22 @@ def test_small_and_odd_shapes():
     m = UMPAModelNoDF(list(d["sam"]), list(d["ref"]), window_size=0, max_shift=3)
     m.match(quiet=True)
     assert m.last_match_info["path"] == "lazy"
+
+
+def test_pageable_frames_go_through_host_conversion():
+    """Ordinary (pageable) numpy frames: every row is converted by the host threads into pinned staging
+    (the driver's own staging of pageable FP64 would be the slow path); same bits as pinned frames."""
+    from umpa_b200 import UMPAModelDF
+    d = _stacks(6, 1536, 1280, 5, True, pinned=True)
+    pinned_s, pinned_r = list(d["sam"].numpy()), list(d["ref"].numpy())
+    a = UMPAModelDF(pinned_s, pinned_r, window_size=2, max_shift=5).match(quiet=True, debug=False)
+    pag_s, pag_r = [np.array(x, copy=True) for x in pinned_s], [np.array(x, copy=True) for x in pinned_r]
+    m = UMPAModelDF(pag_s, pag_r, window_size=2, max_shift=5)
+    b = m.match(quiet=True, debug=False)
+    info = m.last_stream_info
+    assert info["bands"] > 1 and info["host_threads"] > 0 and info["host_rows_per_frame"] == 1536, info
+    for k in ("f", "T", "dx", "dy", "df", "err", "debug_Ncalls"):
+        assert np.array_equal(a[k], b[k]), k
+    # the FP64 stacks are fetched when a hook needs them
+    v = m.min(m.padding + 10, m.padding + 20)
+    assert abs(v[2] - b["dx"][10, 20]) < 1e-3
