@@ -110,3 +110,25 @@ def test_host_staging_helpers():
     for step in (1, 3, 32, 1000):
         got = L.umpa_host_sampled_mean(fr.ctypes.data_as(C.POINTER(C.c_double)), 100, 77, step)
         assert abs(got - fr[::step].mean()) < 1e-13
+
+
+def test_bench_algorithmic_flops_match_survey():
+    """F_alg per output pixel of the five BASELINE configurations, and the tile model
+    bench.py uses for the executed-flop figure agrees with plan_tiles (table_path.cu) on the tile height."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    want = {"cfg1": 24500, "cfg2": 101250, "cfg3": 3648150, "cfg4": 882000, "cfg5": 66248}
+    for name, f in want.items():
+        assert bench.algorithmic_flops_per_px(bench.CONFIGS[name]) == f, name
+    # executed FMAs per output pixel of the cross-table kernel: config 2 uses 16-row tiles (12 x 28 outputs)
+    S, K, Na = 9, 5, 25
+    assert abs(bench.executed_fma_per_px_cross(bench.CONFIGS["cfg2"]) -
+               S * S * (Na * 16 * 32 + K * 16 * 28 + K * 12 * 28) / (12. * 28)) < 1e-9
+    # config 5 (Nw = 6) takes the 48-row tile, config 4 (Nw = 3, S = 15) the 24-row tile
+    e5 = bench.executed_fma_per_px_cross(bench.CONFIGS["cfg5"])
+    assert abs(e5 - 49 * (4 * 48 * 32 + 13 * 48 * 20 + 13 * 36 * 20) / (36. * 20)) < 1e-9
+    e4 = bench.executed_fma_per_px_cross(bench.CONFIGS["cfg4"])
+    assert abs(e4 - 225 * (40 * 24 * 32 + 7 * 24 * 26 + 7 * 18 * 26) / (18. * 26)) < 1e-9
