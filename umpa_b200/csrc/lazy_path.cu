@@ -145,26 +145,23 @@ struct LazyEval {
             const int s0 = qi - pi - Nw, sc0 = qj - pj - Nw;      // top-left of the sample window
 
             if (m.kind == UMPA_DF) {
+                // One pass over the window.  The reference takes the weighted mean of the reference window in a
+                // loop of its own (Model.cpp:722-735) and then sums w*r again as s6 (unmasked branch): the two
+                // accumulate the same products in the same order, so `mean` before its division IS that sum.
                 double mean = 0., den = 0.;
-                for (int a = 0; a < K; a++)
-                    for (int b = 0; b < K; b++) {
-                        const double w = m.win[a * K + b];
-                        mean += w * R[(size_t)(r0 + a) * W + rc0 + b];
-                        den += w;
-                    }
-                mean /= den;
                 double s2 = 0., s4 = 0., s6 = 0.;
                 for (int a = 0; a < K; a++)
                     for (int b = 0; b < K; b++) {
                         const size_t nr = (size_t)(r0 + a) * W + rc0 + b;
                         const size_t ns = (size_t)(s0 + a) * W + sc0 + b;
                         const double w = m.win[a * K + b], s = S[ns], r = R[nr];
+                        mean += w * r;
+                        den += w;
                         if (!m.masked) {
                             t1 += w * s * s;
                             t3 += w * r * r;
                             s4 += w * s;
                             t5 += w * r * s;
-                            s6 += w * r;
                         } else {
                             const double g = mix_weights(M[nr], M[ns]);
                             t1 += g * w * s * s;
@@ -176,6 +173,8 @@ struct LazyEval {
                             wt += g * w;
                         }
                     }
+                if (!m.masked) s6 = mean;
+                mean /= den;
                 t2 += m.masked ? mean * mean * s2 : mean * mean;
                 t4 += mean * s4;
                 t6 += mean * s6;
