@@ -91,6 +91,9 @@ __device__ inline double weighted_blur_at(const double *__restrict__ img, const 
 }
 
 // One cost evaluation at raw pixel (i,j).
+// KIND: the model kind when known at compile time (the match kernel is instantiated per kind, so that the
+// NoDF / DF variants do not carry the registers of the DFKernel blur), -1 = read m.kind at run time (hooks).
+template <int KIND = -1>
 struct LazyEval {
     const LazyView &m;
     int i, j;
@@ -126,6 +129,7 @@ struct LazyEval {
     {
         const int st = shift_status(m.max_shift, si, sj);
         if (st != UMPA_ST_OK) return st;
+        const int kind = KIND >= 0 ? KIND : m.kind;
         const int Nw = m.Nw, K = 2 * Nw + 1;
         int ri, rj, qi, qj;       // centres of the reference and of the sample window
         if (m.refshift) { ri = i; rj = j; qi = i - si; qj = j - sj; }
@@ -144,7 +148,7 @@ struct LazyEval {
             const int r0 = ri - pi - Nw, rc0 = rj - pj - Nw;      // top-left of the reference window
             const int s0 = qi - pi - Nw, sc0 = qj - pj - Nw;      // top-left of the sample window
 
-            if (m.kind == UMPA_DF) {
+            if (kind == UMPA_DF) {
                 // One pass over the window.  The reference takes the weighted mean of the reference window in a
                 // loop of its own (Model.cpp:722-735) and then sums w*r again as s6 (unmasked branch): the two
                 // accumulate the same products in the same order, so `mean` before its division IS that sum.
@@ -178,7 +182,7 @@ struct LazyEval {
                 t2 += m.masked ? mean * mean * s2 : mean * mean;
                 t4 += mean * s4;
                 t6 += mean * s6;
-            } else if (m.kind == UMPA_DFKERNEL && !m.masked && K >= 4) {
+            } else if (kind == UMPA_DFKERNEL && !m.masked && K >= 4) {
                 if (K >= 7) dfk_window<7>(R, S, r0, rc0, s0, sc0, W, K, t1, t3, t5);
                 else dfk_window<4>(R, S, r0, rc0, s0, sc0, W, K, t1, t3, t5);
             } else {
@@ -188,7 +192,7 @@ struct LazyEval {
                         const size_t ns = (size_t)(s0 + a) * W + sc0 + b;
                         const double w = m.win[a * K + b], s = S[ns];
                         double r;
-                        if (m.kind == UMPA_DFKERNEL)
+                        if (kind == UMPA_DFKERNEL)
                             r = m.masked ? weighted_blur_at(R, M, r0 + a, rc0 + b, W, kern, ks)
                                          : blur_at(R, r0 + a, rc0 + b, W, kern, ks);
                         else
@@ -207,7 +211,7 @@ struct LazyEval {
                     }
             }
         }
-        if (m.kind == UMPA_DF) {
+        if (kind == UMPA_DF) {
             const double den = t2 * t3 - t6 * t6;
             const double Kc = (t2 * t5 - t4 * t6) / den;
             const double beta = (t3 * t4 - t5 * t6) / den;
@@ -237,6 +241,7 @@ __device__ inline void build_blur_kernel(double a, double b, double c, double *k
 
 // kern_ws: workspace for the per-pixel blur kernels (DFKernel), 289 doubles per launched thread.
 // row0: first output row of this launch (DFKernel is launched in row bands to bound kern_ws).
+template <int KIND>
 __global__ void __launch_bounds__(128)
 lazy_match_kernel(LazyView m, RoiView roi, umpa_outputs out, double *kern_ws, int row0)
 {
@@ -249,11 +254,11 @@ lazy_match_kernel(LazyView m, RoiView roi, umpa_outputs out, double *kern_ws, in
 
     double *kern = nullptr;
     const size_t ks = (size_t)gridDim.x * gridDim.y * blockDim.x;
-    if (m.kind == UMPA_DFKERNEL) {
+    if (KIND == UMPA_DFKERNEL) {
         kern = kern_ws + ((size_t)blockIdx.y * gridDim.x * blockDim.x + xj);
         build_blur_kernel(roi.abc[3 * n], roi.abc[3 * n + 1], roi.abc[3 * n + 2], kern, ks);
     }
-    LazyEval eval{m, roi.off0 + roi.step0 * xi, roi.off1 + roi.step1 * xj, kern, ks};
+    LazyEval<KIND> eval{m, roi.off0 + roi.step0 * xi, roi.off1 + roi.step1 * xj, kern, ks};
     FitArgs args{0., 0.};
     double d[25], a[16], uv[2] = {roi.uv0[0], roi.uv0[1]}, f = 0.;
     int ncalls;
@@ -267,7 +272,7 @@ __global__ void lazy_cost_kernel(LazyView m, int i, int j, int si, int sj, doubl
                                  double *res, double *kern)
 {
     if (m.kind == UMPA_DFKERNEL) build_blur_kernel(a, b, c, kern, 1);
-    LazyEval eval{m, i, j, kern, 1};
+    LazyEval<> eval{m, i, j, kern, 1};
     FitArgs args{0., 0.};
     double cost = 0.;
     const int st = eval(si, sj, cost, args);
@@ -278,7 +283,7 @@ __global__ void lazy_min_kernel(LazyView m, int i, int j, double *io, double *ke
 {
     // io: [0..6] values, [7..8] uv, [9..33] d, [34..49] a, [50] ncalls, [51] status
     if (m.kind == UMPA_DFKERNEL) build_blur_kernel(io[4], io[5], io[6], kern, 1);
-    LazyEval eval{m, i, j, kern, 1};
+    LazyEval<> eval{m, i, j, kern, 1};
     FitArgs args{0., 0.};
     double d[25], a[16], uv[2] = {io[7], io[8]}, f = 0.;
     int ncalls;
@@ -335,7 +340,9 @@ int lazy_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaS
     }
     for (int row0 = 0; row0 < roi.N0; row0 += band) {
         dim3 grid(gx, std::min(band, roi.N0 - row0));
-        lazy_match_kernel<<<grid, threads, 0, st>>>(make_view(m), roi, out, ws, row0);
+        if (m->kind == UMPA_NODF) lazy_match_kernel<UMPA_NODF><<<grid, threads, 0, st>>>(make_view(m), roi, out, ws, row0);
+        else if (m->kind == UMPA_DF) lazy_match_kernel<UMPA_DF><<<grid, threads, 0, st>>>(make_view(m), roi, out, ws, row0);
+        else lazy_match_kernel<UMPA_DFKERNEL><<<grid, threads, 0, st>>>(make_view(m), roi, out, ws, row0);
         UMPA_CUDA(cudaGetLastError());
         m->last_launches += 1;
     }
