@@ -159,6 +159,9 @@ def main():
     wide_abc[..., 2] *= .08
     wide_abc[..., 1] *= .2
     run_case("dfk_wide_blur", "DFKernel", kbig["sam"], kbig["ref"], Nw=1, max_shift=5, abc=wide_abc)
+    run_case("dfk_assign_ref", "DFKernel", kbig["sam"], kbig["ref"], Nw=2, max_shift=4, assign="ref")
+    run_case("dfk_assign_ref_step", "DFKernel", kbig["sam"], kbig["ref"], Nw=2, max_shift=5, assign="ref",
+             ROI=((0, 40, 3), (2, 44, 2)), abc=synth.blur_abc(14, 21))
 
     # masks: smooth positive weights with a dead block and a few dead pixels
     rng = np.random.default_rng(5)

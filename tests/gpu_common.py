@@ -36,4 +36,5 @@ def run_case(case, path="auto"):
 
 TABLE_CASES = ("nodf_clean", "df_clean", "nodf_noisy", "df_noisy", "df_lowcontrast", "df_nw3_ms6",
                "nodf_nw1", "df_subpx0", "df_subpx1", "df_step3", "df_roi", "df_dxdy",
-               "df_assign_ref", "dfk_clean", "dfk_nw3_ms5", "dfk_roi_step", "dfk_wide_blur")
+               "df_assign_ref", "dfk_clean", "dfk_nw3_ms5", "dfk_roi_step", "dfk_wide_blur",
+               "dfk_assign_ref", "dfk_assign_ref_step")

@@ -114,6 +114,25 @@ def test_cfg3_dfkernel_blur_tables_vs_lazy():
     assert st["n_ok"] > .99 * exp["err"].size
 
 
+def test_dfkernel_assign_ref_blur_tables_vs_lazy():
+    """DFKernel with assign_coordinates='ref' (the sample window moves): role-swapped blur tables against
+    the FP64 lazy path on a strided subsample of a 12 x 640 x 768 model, two window sizes."""
+    from umpa_b200 import UMPAModelDFKernel, synth
+    d = _stacks(12, 640, 768, 4, True)
+    for Nw, ms in ((2, 4), (3, 5)):
+        m = UMPAModelDFKernel(list(d["sam"]), list(d["ref"]), window_size=Nw, max_shift=ms)
+        m.assign_coordinates = "ref"
+        N0, N1 = m.sh
+        abc = synth.blur_abc(N0, N1)
+        full = m.match(abc=abc, quiet=True)
+        assert m.last_match_info["path"] == "table" and (full["err"] == 1).mean() > .99
+        m.cuda_path = "lazy"
+        exp = m.match(ROI=((1, N0, 16), (5, N1, 16)), abc=np.ascontiguousarray(abc[1::16, 5::16]), quiet=True)
+        got = {k: v[1::16, 5::16] for k, v in full.items()}
+        st = compare_fp32(got, exp, label="dfk assign=ref table-vs-lazy Nw=%d" % Nw)
+        assert st["n_ok"] > .98 * exp["err"].size
+
+
 def test_cfg4_large_field_roi_consistency():
     """Config 4 (DF 40 x 4096^2, Nw=3, max_shift=8; 5.4 GB of FP32 stacks, 2 x 15 GB of tables): full
     match on the device, a cropped match and the FP64 lazy path on a strided subsample agree."""

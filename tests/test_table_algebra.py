@@ -35,3 +35,58 @@ def test_regrouped_cost_equals_direct(name):
             assert abs(D64[si + h, sj + h, i, j] - v) <= 1e-10 * max(1., abs(v))
         # FP32 accumulation: error stays at the 1e-5 level of the cost scale
         assert abs(cost32[si + h, sj + h, i, j] - f) <= 3e-5 * scale
+
+
+@pytest.mark.parametrize("refshift", [0, 1])
+def test_dfkernel_blur_table_identities(refshift):
+    """The blur-table form of DFKernel's cost (kernel_path.cu): blurred CENTRED reference patch once per
+    pixel, t3 / t5 rebuilt from the centred sums and the frame constants -- for assign_coordinates='sam'
+    (the blurred window moves over the patch) and 'ref' (the blurred window stays, the sample window moves
+    by -s; Model.cpp:1045-1051).  FP64 numpy against the oracle's direct evaluation."""
+    c = load_case("dfk_assign_ref" if refshift else "dfk_roi_step")
+    sam, ref = np.array(c["sam"]), np.array(c["ref"])
+    Nw, ms, pad = c["Nw"], c["max_shift"], c["padding"]
+    K, h = 2 * Nw + 1, ms - 1
+    o = port.OracleModel("DFKernel", c["sam"], c["ref"], window_size=Nw, max_shift=ms)
+    o.set_options(reference_shift=refshift)
+    w = port.make_window(Nw)
+    sw = w.sum()
+    ck, dk = ref.mean(axis=(1, 2)), sam.mean(axis=(1, 2))         # any constants do
+    Rc, Sc = ref - ck[:, None, None], sam - dk[:, None, None]
+    cd, cc, dd = (ck * dk).sum(), (ck * ck).sum(), (dk * dk).sum()
+    rng = np.random.default_rng(3)
+    for _ in range(12):
+        i, j = (int(rng.integers(pad, sam.shape[1] - pad)), int(rng.integers(pad, sam.shape[2] - pad)))
+        abc = tuple(rng.uniform(.2, .8, 2)) + (float(rng.uniform(.2, .8)),)
+        abc = (abc[0], float(rng.uniform(-.1, .1)), abc[2])
+        kern = port.blur_kernel(*abc).reshape(17, 17)
+        sig = kern.sum()
+        win = lambda img, y, x: img[:, y - Nw:y + Nw + 1, x - Nw:x + Nw + 1]   # (Na, K, K) window at (y, x)
+        # blurred centred reference on the patch the shifts can reach
+        P = K + 2 * h
+        Bp = np.zeros((len(ref), P, P))
+        for y in range(P):
+            for x in range(P):
+                qy, qx = i - Nw - h + y, j - Nw - h + x
+                Bp[:, y, x] = (Rc[:, qy - 8:qy + 9, qx - 8:qx + 9] * kern).sum(axis=(1, 2))
+        for si in (-h, -1, 0, 2):
+            for sj in (-2, 0, 1, h):
+                (f, t, _), st = o.cost(i, j, si, sj, abc)
+                assert st == 1
+                if refshift:        # reference window at the pixel, sample window at p - s
+                    Bw = Bp[:, h:h + K, h:h + K]
+                    Sw, Sr = win(Sc, i - si, j - sj), win(sam, i - si, j - sj)
+                else:               # blurred window at p + s, sample window at the pixel
+                    Bw = Bp[:, h + si:h + si + K, h + sj:h + sj + K]
+                    Sw, Sr = win(Sc, i, j), win(sam, i, j)
+                t5c = (w * Bw * Sr).sum()
+                t3c = (w * (Bw * Bw + 2. * sig * ck[:, None, None] * Bw)).sum()
+                V = (ck[:, None, None] * w * Sw).sum()
+                T1, P1 = (w * Sw * Sw).sum(), (dk[:, None, None] * w * Sw).sum()
+                t1 = T1 + 2. * P1 + sw * dd
+                t5 = t5c + sig * (V + sw * cd)
+                t3 = t3c + sig * sig * sw * cc
+                T = t5 / t3
+                cost = (t1 - t5 * T) / len(ref)
+                assert abs(T - t) <= 1e-11 * abs(t)
+                assert abs(cost - f) <= 1e-11 * max(abs(f), t1 / len(ref) * 1e-3)

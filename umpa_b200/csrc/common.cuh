@@ -153,6 +153,6 @@ double host_sampled_mean(const double *frame, int H, int W, int step);
 void host_center_rows(float *dst, const double *src, int rows, int W, int pitch, double c);
 
 // implemented in kernel_path.cu: per-pixel FP32 tables of UMPAModelDFKernel (blur fused into the window pass)
-bool ktable_supported(int Nw, int max_shift, int step0);
+bool ktable_supported(int Nw, int max_shift, int step0, bool refshift);
 int ktable_row_floats(int max_shift);                          // floats per pixel row: t5c[S^2], t3c[S^2], sigma-1
 int ktable_build(umpa_model *m, const RoiView &roi, float *tab, cudaStream_t st);

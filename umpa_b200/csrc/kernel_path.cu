@@ -77,26 +77,32 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-template <int NW, int S>
+template <int NW, int S, bool RS>
 size_t ktable_smem_floats(int RR, int SR)
 {
     using G = KTGeom<NW, S>;
     auto a4 = [](size_t n) { return (n + 3) & ~(size_t)3; };
-    return 2 * (size_t)RR * G::RP + a4(2 * (size_t)SR * G::K) + (size_t)G::NP * KPIX + (size_t)G::NP * G::K * G::WP +
+    return 2 * (size_t)RR * G::RP + a4(2 * (size_t)SR * (RS ? G::PS : G::K)) + (size_t)G::NP * KPIX + (size_t)G::NP * G::K * G::WP +
            a4(G::K * G::K) + a4((size_t)G::NP * G::PS * G::QP) + (size_t)G::NP * G::PS * G::PSTR;
 }
 
-template <int NW, int S>
+// RS = reference_shift (assign_coordinates = 'ref', Model.cpp:1060-1075): the blurred reference window stays at
+// the pixel and the SAMPLE window moves by -s.  Same machinery with the roles swapped: the patch rows held by
+// the lanes are rows of the (uncentred) sample, the K x K weights are w * B' (the blurred reference at the
+// window, the centre of the blurred patch), t3 does not depend on the shift, and t5 comes out indexed by the
+// negated shift -- which is the index TableEval<RS> looks up.
+template <int NW, int S, bool RS>
 __global__ void __launch_bounds__(KT_NT, 1) ktable_kernel(KTableParams p)
 {
     using G = KTGeom<NW, S>;
+    constexpr int HS = G::HS, SCW = RS ? G::PS : G::K;        // columns of the sample region
     constexpr int K = G::K, PS = G::PS, RW = G::RW, PPW = G::PPW, SW = G::SW, NP = G::NP;
     constexpr int NR4 = G::NR4, RP = G::RP, QP = G::QP, WP = G::WP, PSTR = G::PSTR, REACH = G::REACH;
     extern __shared__ __align__(16) float sm[];
     auto a4 = [](int n) { return (n + 3) & ~3; };
     float *Rbuf = sm;
     float *Sbuf = Rbuf + 2 * p.RR * RP;
-    float *Ks = Sbuf + a4(2 * p.SR * K);
+    float *Ks = Sbuf + a4(2 * p.SR * SCW);
     float *Ws = Ks + NP * KPIX;
     float *W2 = Ws + NP * K * WP;
     float *Qs = W2 + a4(K * K);
@@ -113,16 +119,16 @@ __global__ void __launch_bounds__(KT_NT, 1) ktable_kernel(KTableParams p)
 
     auto load = [&](int k, int b) {
         const float *R = p.ref + (size_t)k * fstride, *Sg = p.sam + (size_t)k * fstride;
-        float *dR = Rbuf + b * p.RR * RP, *dS = Sbuf + b * p.SR * K;
+        float *dR = Rbuf + b * p.RR * RP, *dS = Sbuf + b * p.SR * SCW;
         for (int n = tid; n < p.RR * RW; n += KT_NT) {
             const int rr = n / RW, cc = n - rr * RW;
             const int gy = i0 - REACH + rr, gx = j0 - REACH + cc;
             const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
             cp_async4(dR + rr * RP + cc, R + (ok ? (size_t)gy * p.pitch + gx : 0), ok);
         }
-        for (int n = tid; n < p.SR * K; n += KT_NT) {
-            const int sr = n / K, cc = n - sr * K;
-            const int gy = i0 - NW + sr, gx = j0 - NW + cc;
+        for (int n = tid; n < p.SR * SCW; n += KT_NT) {
+            const int sr = n / SCW, cc = n - sr * SCW;
+            const int gy = i0 - NW - (RS ? HS : 0) + sr, gx = j0 - NW - (RS ? HS : 0) + cc;
             const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
             cp_async4(dS + n, Sg + (ok ? (size_t)gy * p.pitch + gx : 0), ok);
         }
@@ -211,16 +217,16 @@ __global__ void __launch_bounds__(KT_NT, 1) ktable_kernel(KTableParams p)
         asm volatile("cp.async.commit_group;\n" ::);
 
         // weighted sample window of this pixel: ws(a,b) = w(a,b) * S_k(p + (a,b) - Nw)   (uncentred S)
-        {
-            const float dk = __ldg(p.mean_s + k);
-            const float *Sb = Sbuf + (k & 1) * p.SR * K + prow * K;
+        const float dk = __ldg(p.mean_s + k);
+        if (!RS) {
+            const float *Sb = Sbuf + (k & 1) * p.SR * SCW + prow * SCW;
             if (slot < PPW)
                 for (int e = y; e < K * K; e += SW) {
                     const int a = e / K, b = e - a * K;
                     Wp[a * WP + b] = W2[e] * (Sb[e] + dk);
                 }
+            __syncwarp();
         }
-        __syncwarp();
 
         float acc[PS];
 #pragma unroll
@@ -253,8 +259,26 @@ __global__ void __launch_bounds__(KT_NT, 1) ktable_kernel(KTableParams p)
         else blur(std::integral_constant<int, 8>());
 
         const float tsc = 2.f * sigf * __ldg(p.mean_r + k);
+        float prod[PS];                                // what the K x K weights multiply: B' rows, or (RS) sample rows
+        if (!RS) {
 #pragma unroll
-        for (int x = 0; x < PS; x++) q3[x] = fmaf(acc[x], acc[x] + tsc, q3[x]);
+            for (int x = 0; x < PS; x++) { q3[x] = fmaf(acc[x], acc[x] + tsc, q3[x]); prod[x] = acc[x]; }
+        } else {
+            // the blurred reference at the window = rows / columns HS .. HS+K-1 of the blurred patch
+            if (lane_on && y >= HS && y < HS + K) {
+                const int a = y - HS;
+#pragma unroll
+                for (int b = 0; b < K; b++) {
+                    const float wv = W2[a * K + b], bv = acc[HS + b];
+                    Wp[a * WP + b] = wv * bv;
+                    q3[0] = fmaf(wv * bv, bv + tsc, q3[0]);
+                }
+            }
+            __syncwarp();
+            const float *Sb = Sbuf + (k & 1) * p.SR * SCW + (prow + yc) * SCW;
+#pragma unroll
+            for (int x = 0; x < PS; x++) prod[x] = Sb[x] + dk;
+        }
 #pragma unroll
         for (int a = 0; a < K; a++) {
             float ws[WP];
@@ -266,7 +290,7 @@ __global__ void __launch_bounds__(KT_NT, 1) ktable_kernel(KTableParams p)
 #pragma unroll
             for (int sj = 0; sj < S; sj++)
 #pragma unroll
-                for (int b = 0; b < K; b++) P[a][sj] = fmaf(ws[b], acc[sj + b], P[a][sj]);
+                for (int b = 0; b < K; b++) P[a][sj] = fmaf(ws[b], prod[sj + b], P[a][sj]);
         }
         __syncwarp();                                  // Wp is rewritten next frame
     }
@@ -294,9 +318,14 @@ __global__ void __launch_bounds__(KT_NT, 1) ktable_kernel(KTableParams p)
             float t3c = 0.f, t5c = 0.f;
 #pragma unroll
             for (int a = 0; a < K; a++) {
+                if (!RS) {
 #pragma unroll
-                for (int b = 0; b < K; b++) t3c = fmaf(W2[a * K + b], qb[(si + a) * QP + sj + b], t3c);
+                    for (int b = 0; b < K; b++) t3c = fmaf(W2[a * K + b], qb[(si + a) * QP + sj + b], t3c);
+                }
                 t5c += pb[(size_t)(si + a) * PSTR + a * S + sj];
+            }
+            if (RS) {                                  // shift-independent: the lanes' window rows, summed
+                for (int yy = HS; yy < HS + K; yy++) t3c += qb[yy * QP];
             }
             row[n] = t5c;
             row[S * S + n] = t3c;
@@ -309,20 +338,20 @@ __global__ void __launch_bounds__(KT_NT, 1) ktable_kernel(KTableParams p)
 typedef void (*KTableKernel)(KTableParams);
 
 template <int NW, int S>
-bool ktable_bind(int step0, KTableKernel *k, size_t *smem, int *np, int *RR, int *SR)
+bool ktable_bind(int step0, bool rs, KTableKernel *k, size_t *smem, int *np, int *RR, int *SR)
 {
     using G = KTGeom<NW, S>;
     *RR = (G::NP - 1) * step0 + G::PS + 2 * UMPA_KWS;
-    *SR = (G::NP - 1) * step0 + G::K;
-    *smem = ktable_smem_floats<NW, S>(*RR, *SR) * sizeof(float);
+    *SR = (G::NP - 1) * step0 + (rs ? G::PS : G::K);
+    *smem = (rs ? ktable_smem_floats<NW, S, true>(*RR, *SR) : ktable_smem_floats<NW, S, false>(*RR, *SR)) * sizeof(float);
     *np = G::NP;
-    *k = ktable_kernel<NW, S>;
+    *k = rs ? ktable_kernel<NW, S, true> : ktable_kernel<NW, S, false>;
     return *smem <= (size_t)227 * 1024;
 }
 
-bool ktable_pick(int Nw, int S, int step0, KTableKernel *k, size_t *smem, int *np, int *RR, int *SR)
+bool ktable_pick(int Nw, int S, int step0, bool rs, KTableKernel *k, size_t *smem, int *np, int *RR, int *SR)
 {
-#define KT_CASE(nw, s) if (Nw == nw && S == s) return ktable_bind<nw, s>(step0, k, smem, np, RR, SR);
+#define KT_CASE(nw, s) if (Nw == nw && S == s) return ktable_bind<nw, s>(step0, rs, k, smem, np, RR, SR);
     KT_CASE(1, 3) KT_CASE(1, 5) KT_CASE(1, 7) KT_CASE(1, 9) KT_CASE(1, 11)
     KT_CASE(2, 3) KT_CASE(2, 5) KT_CASE(2, 7) KT_CASE(2, 9) KT_CASE(2, 11)
     KT_CASE(3, 3) KT_CASE(3, 5) KT_CASE(3, 7) KT_CASE(3, 9)
@@ -332,10 +361,10 @@ bool ktable_pick(int Nw, int S, int step0, KTableKernel *k, size_t *smem, int *n
 
 }  // namespace
 
-bool ktable_supported(int Nw, int max_shift, int step0)
+bool ktable_supported(int Nw, int max_shift, int step0, bool refshift)
 {
     KTableKernel k; size_t smem; int np, RR, SR;
-    return ktable_pick(Nw, 2 * max_shift - 1, step0, &k, &smem, &np, &RR, &SR);
+    return ktable_pick(Nw, 2 * max_shift - 1, step0, refshift, &k, &smem, &np, &RR, &SR);
 }
 
 int ktable_row_floats(int max_shift) { const int S = 2 * max_shift - 1; return (2 * S * S + 1 + 3) & ~3; }
@@ -346,7 +375,7 @@ int ktable_build(umpa_model *m, const RoiView &roi, float *tab, cudaStream_t st)
     size_t smem = 0;
     int np = 0, RR = 0, SR = 0;
     const int S = 2 * m->max_shift - 1;
-    if (!ktable_pick(m->Nw, S, roi.step0, &kern, &smem, &np, &RR, &SR)) {
+    if (!ktable_pick(m->Nw, S, roi.step0, m->refshift != 0, &kern, &smem, &np, &RR, &SR)) {
         umpa_set_error("blur-table path: Nw=%d max_shift=%d step=%d not instantiated", m->Nw, m->max_shift, roi.step0);
         return UMPA_ERR_UNSUPPORTED;
     }

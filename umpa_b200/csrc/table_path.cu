@@ -329,7 +329,7 @@ struct TableEval {
     const float4 *pAux;             // moving aux image at this pixel (shift 0)
     const float *pX, *pM;           // this pixel in plane 0 of the cross / mean table
 
-    struct Raw { float4 aux; float x, m; };     // what one evaluation reads: three independent gathers
+    struct Raw { float4 aux; float x, m, sg; }; // what one evaluation reads: three independent gathers (+ sigma-1, DFKernel)
 
     __device__ int operator()(int si, int sj, double &cst, FitArgs &args) const
     {
@@ -355,10 +355,13 @@ struct TableEval {
         const int ti = RS ? -si : si, tj = RS ? -sj : sj;
         const unsigned sidx = (unsigned)((ti + ms - 1) * S + (tj + ms - 1));
         Raw r;
-        if (!RS && w.kind == UMPA_DFKERNEL) {
+        r.sg = 0.f;
+        if (w.kind == UMPA_DFKERNEL) {
             r.x = __ldg(krow + sidx);
             r.m = __ldg(krow + S * S + sidx);
-            r.aux = make_float4(__ldg(krow + 2 * S * S), 0.f, 0.f, 0.f);
+            r.sg = __ldg(krow + 2 * S * S);
+            r.aux = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (RS) r.aux = __ldg(pAux + (ti * w.pitch + tj));          // the sample's (T1, P1, V, -) at p - s
             return r;
         }
         // per-pixel base pointers + one 32x32->64 multiply per table (plane sizes fit 32 bits)
@@ -370,14 +373,17 @@ struct TableEval {
 
     __device__ double cost(const Raw &r, FitArgs &args) const
     {
-        if (!RS && w.kind == UMPA_DFKERNEL) {
+        if (w.kind == UMPA_DFKERNEL) {
             // t3 = sum w B^2, t5 = sum w B S with B = k_p (*) R (Model.cpp:1076-1099), rebuilt from the
-            // centred FP32 sums: B = B' + sigma c_k
-            const double sig = 1. + (double)r.aux.x;
-            const double t5 = (double)r.x + sig * (c1 + w.swk * cd);
+            // centred FP32 sums: B = B' + sigma c_k.  RS: t1 and the sample's V come from the sample's aux
+            // image at p - s (r.aux), not from the pixel.
+            const double sig = 1. + (double)r.sg;
+            const double V = RS ? (double)r.aux.z : c1;
+            const double t1 = RS ? (double)r.aux.x + 2. * (double)r.aux.y + w.sw * dd : c0;
+            const double t5 = (double)r.x + sig * (V + w.swk * cd);
             const double t3 = (double)r.m + sig * sig * w.swk * cc;
             args.t = t5 / t3;
-            return (c0 - t5 * args.t) * w.inv_Na;
+            return (t1 - t5 * args.t) * w.inv_Na;
         }
         const float4 mv = r.aux;
         double t1, t2, t3, lin;
@@ -683,9 +689,8 @@ bool table_eligible(const umpa_model *m, const RoiView &roi, std::string *why, b
     // a handful of samples per cost (e.g. a 1x1 window on 3 frames): the fit is nearly exact, cost << signal
     // energy, and FP32 sums lose it to cancellation (367 of 2509 pixels off by > 1e-4 in that example)
     if (m->K * m->K * m->Na < 25) return no("fewer than 25 samples per cost: FP32 sums too coarse");
-    if (m->refshift && m->kind == UMPA_DFKERNEL) return no("DFKernel with reference_shift=1");
     if (m->kind == UMPA_DFKERNEL) {
-        if (!ktable_supported(m->Nw, m->max_shift, roi.step0)) return no("DFKernel: (Nw, max_shift, step) outside the instantiated blur-table kernels");
+        if (!ktable_supported(m->Nw, m->max_shift, roi.step0, m->refshift != 0)) return no("DFKernel: (Nw, max_shift, step) outside the instantiated blur-table kernels");
         if (!m->d_sam32) return no("FP32 stacks not prepared");
         return true;
     }
