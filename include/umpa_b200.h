@@ -112,6 +112,14 @@ UMPA_API void umpa_destroy(umpa_model *m);
 UMPA_API int umpa_set_frames(umpa_model *m, const double *const *sam, const double *const *ref,
                     const double *const *mask, int on_device, void *stream);
 
+/* The same for float32 HOST frames (detector data): the reference only reads float64 buffers
+ * (UMPA/model.pyx:236-237 casts whatever it is given to double*), so its callers widen such data first;
+ * here they cross PCIe as they are -- half the bytes -- and are widened on the GPU (exact), which gives the
+ * results of umpa_set_frames() on the widened frames bit for bit.  Always deferred (like on_device = 2):
+ * the pointers must stay valid until the first umpa_match_host / umpa_match / umpa_cost / umpa_min. */
+UMPA_API int umpa_set_frames_f32(umpa_model *m, const float *const *sam, const float *const *ref,
+                        const float *const *mask);
+
 /* replaces ModelBase::set_window (UMPA/lib/Model.cpp:239-246; Nw setter model.pyx:702-704) */
 UMPA_API int umpa_set_window(umpa_model *m, int Nw, const double *win);
 
@@ -186,6 +194,7 @@ UMPA_API int64_t umpa_device_bytes(const umpa_model *m);
  * a frame (mean over rows 0, step, 2 step, ...) and the FP64 -> centred FP32 conversion of `rows` rows of W
  * doubles into rows of `pitch` floats (zero padded) -- the arithmetic of center_frames: (float)(x - c). */
 UMPA_API double umpa_host_sampled_mean(const double *frame, int H, int W, int step);
+UMPA_API double umpa_host_sampled_mean_f32(const float *frame, int H, int W, int step);
 UMPA_API void umpa_host_center_rows(float *dst, const double *src, int rows, int W, int pitch, double c);
 
 /* Measured FP32-FMA peak of the current device (dependent-free FFMA chains on all SMs, CUDA

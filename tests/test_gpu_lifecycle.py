@@ -91,3 +91,63 @@ def test_rematch_same_handle_and_other_options():
     assert m.last_match_info["path"] == "table" and (r["err"] == 1).mean() > .9
     m.assign_coordinates = "sam"
     _same(m.match(quiet=True), a)
+
+
+def _f32_pair(seed, H, W, Na=8, pinned=False):
+    """float32 stacks and their exact float64 widening"""
+    import torch
+    d = _stack(seed, H=H, W=W, Na=Na)
+    s32, r32 = np.asarray(d["sam"], dtype=np.float32), np.asarray(d["ref"], dtype=np.float32)
+    if pinned:                                  # one pinned allocation per stack: the 2-D copy route
+        hs, hr = (torch.empty(s32.shape, dtype=torch.float32, pin_memory=True) for _ in range(2))
+        hs.copy_(torch.from_numpy(s32)); hr.copy_(torch.from_numpy(r32))
+        s32, r32 = hs.numpy(), hr.numpy()
+    return s32, r32, s32.astype(np.float64), r32.astype(np.float64)
+
+
+@pytest.mark.parametrize("H,W,pinned", [(700, 640, True), (700, 640, False), (531, 515, True)])
+def test_float32_host_frames_equal_their_widening(H, W, pinned):
+    """umpa_set_frames_f32: float32 frames cross PCIe as they are and are widened / centred on the GPU;
+    every result equals the float64 route on the widened arrays bit for bit -- pipelined or not, table
+    and lazy path, the cost() hook after a pipelined match (no FP64 copy on the device until then)."""
+    import umpa_b200
+    s32, r32, s64, r64 = _f32_pair(21, H, W, pinned=pinned)
+    for cls in (umpa_b200.UMPAModelDF, umpa_b200.UMPAModelNoDF):
+        m64 = cls(list(s64), list(r64), max_shift=4)
+        want = m64.match(quiet=True)
+        m32 = cls(list(s32), list(r32), max_shift=4)
+        assert m32._f32
+        got = m32.match(quiet=True)
+        assert m32.last_match_info["path"] == "table" and m32.last_stream_info["bands"] > 1
+        _same(got, want)
+        assert np.array_equal(got["debug_d"], want["debug_d"], equal_nan=True)
+        i, j = m32.padding + 11, m32.padding + 17
+        assert m32.cost(i, j, 1, -2) == m64.cost(i, j, 1, -2)          # widens the FP64 stacks now
+        m32.cuda_path = m64.cuda_path = "lazy"
+        roi = ((5, 60, 3), (7, 90, 4))
+        _same(m32.match(ROI=roi, quiet=True), m64.match(ROI=roi, quiet=True))
+    # without the pipeline (everything uploaded before the first kernel)
+    import os
+    os.environ["UMPA_NO_STREAMING"] = "1"
+    try:
+        m32 = umpa_b200.UMPAModelDF(list(s32), list(r32), max_shift=4)
+        _same(m32.match(quiet=True), umpa_b200.UMPAModelDF(list(s64), list(r64), max_shift=4).match(quiet=True))
+    finally:
+        del os.environ["UMPA_NO_STREAMING"]
+
+
+def test_float32_host_frames_masked_and_dfkernel():
+    import umpa_b200
+    s32, r32, s64, r64 = _f32_pair(23, 300, 333, Na=6)
+    mask = np.ones_like(s32)
+    mask[:, 100:110, 50:70] = 0.
+    mask[2, 200, 200] = .5
+    m32 = umpa_b200.UMPAModelDF(list(s32), list(r32), mask_list=list(mask), max_shift=4)
+    m64 = umpa_b200.UMPAModelDF(list(s64), list(r64), mask_list=list(mask.astype(np.float64)), max_shift=4)
+    got, want = m32.match(quiet=True), m64.match(quiet=True)
+    assert m32.last_match_info["path"] == "mixed"
+    _same(got, want)
+    k32 = umpa_b200.UMPAModelDFKernel(list(s32), list(r32), max_shift=4)
+    k64 = umpa_b200.UMPAModelDFKernel(list(s64), list(r64), max_shift=4)
+    abc = umpa_b200.synth.blur_abc(*k32.sh)
+    _same(k32.match(abc=abc, quiet=True), k64.match(abc=abc, quiet=True))

@@ -110,6 +110,11 @@ def test_host_staging_helpers():
     for step in (1, 3, 32, 1000):
         got = L.umpa_host_sampled_mean(fr.ctypes.data_as(C.POINTER(C.c_double)), 100, 77, step)
         assert abs(got - fr[::step].mean()) < 1e-13
+        # float32 frames (umpa_set_frames_f32): the mean of the widened frame, bit for bit
+        f32 = fr.astype(np.float32)
+        wide = np.ascontiguousarray(f32, dtype=np.float64)
+        assert (L.umpa_host_sampled_mean_f32(f32.ctypes.data_as(C.POINTER(C.c_float)), 100, 77, step) ==
+                L.umpa_host_sampled_mean(wide.ctypes.data_as(C.POINTER(C.c_double)), 100, 77, step))
 
 
 def test_bench_algorithmic_flops_match_survey():

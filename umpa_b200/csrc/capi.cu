@@ -291,6 +291,8 @@ void free_frames(umpa_model *m)
     pool_free(m->d_sam64, b64); pool_free(m->d_ref64, b64); pool_free(m->d_mask64, b64);
     pool_free(m->d_sam32, b32); pool_free(m->d_ref32, b32);
     m->h_sam.clear(); m->h_ref.clear(); m->h_mask.clear();
+    m->h_sam_f.clear(); m->h_ref_f.clear(); m->h_mask_f.clear();
+    m->host_f32 = false;
     m->maskbad_valid = false;
     m->host_pending = false; m->fp64_missing = false;
     m->d_sam64 = m->d_ref64 = m->d_mask64 = nullptr;
@@ -324,7 +326,8 @@ void host_means(const umpa_model *m, std::vector<double> &mu)
             const int f = next.fetch_add(1);
             if (f >= 2 * Na) break;
             const int k = f < Na ? f : f - Na, fh = m->dim[2 * k], fw = m->dim[2 * k + 1];
-            mu[f] = host_sampled_mean(f < Na ? m->h_sam[k] : m->h_ref[k], fh, fw, table_row_step(fh));
+            if (m->host_f32) mu[f] = host_sampled_mean_f32(f < Na ? m->h_sam_f[k] : m->h_ref_f[k], fh, fw, table_row_step(fh));
+            else mu[f] = host_sampled_mean(f < Na ? m->h_sam[k] : m->h_ref[k], fh, fw, table_row_step(fh));
         }
     };
     size_t samples = 0;                          // what the threads share: small jobs are not worth a thread start
@@ -337,27 +340,58 @@ void host_means(const umpa_model *m, std::vector<double> &mu)
     for (auto &t : pool) t.join();
 }
 
+__global__ void widen_kernel(double *dst, const float *src, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = (double)src[i];
+}
+
+int widen_stack(double *dst, const float *src, size_t n, cudaStream_t st)
+{
+    widen_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(dst, src, n);
+    UMPA_CUDA(cudaGetLastError());
+    return UMPA_OK;
+}
+
 // Deferred host frames (umpa_set_frames on_device = 2): bring the FP64 stacks (and, if they are not
 // there yet, the centred FP32 stacks) to the device now, on `st`.
 int ensure_resident(umpa_model *m, cudaStream_t st)
 {
     if (!m->host_pending && !m->fp64_missing) return UMPA_OK;
-    const std::vector<const double *> *srcs[3] = {&m->h_sam, &m->h_ref, &m->h_mask};
     double *dsts[3] = {m->d_sam64, m->d_ref64, m->d_mask64};
-    for (int a = 0; a < 3; a++)
-        for (int k = 0; k < (int)srcs[a]->size(); k++) {
-            const size_t n = (size_t)m->dim[2 * k] * m->dim[2 * k + 1];
-            UMPA_CUDA(cudaMemcpyAsync(dsts[a] + m->frame_off[k], (*srcs[a])[k], n * sizeof(double), cudaMemcpyHostToDevice, st));
+    float *tmp = nullptr;                        // float32 host frames: one stack at a time through a device buffer
+    const size_t tmp_bytes = m->stack_elems * sizeof(float);
+    if (m->host_f32) {
+        UMPA_CUDA(pool_malloc((void **)&tmp, tmp_bytes));
+        const std::vector<const float *> *srcs[3] = {&m->h_sam_f, &m->h_ref_f, &m->h_mask_f};
+        for (int a = 0; a < 3; a++) {
+            if (srcs[a]->empty()) continue;
+            for (int k = 0; k < (int)srcs[a]->size(); k++) {
+                const size_t n = (size_t)m->dim[2 * k] * m->dim[2 * k + 1];
+                cudaError_t e = cudaMemcpyAsync(tmp + m->frame_off[k], (*srcs[a])[k], n * sizeof(float), cudaMemcpyHostToDevice, st);
+                if (e != cudaSuccess) { pool_free(tmp, tmp_bytes); UMPA_CUDA(e); }
+            }
+            int rc = widen_stack(dsts[a], tmp, m->stack_elems, st);
+            if (rc) { cudaStreamSynchronize(st); pool_free(tmp, tmp_bytes); return rc; }
         }
+    } else {
+        const std::vector<const double *> *srcs[3] = {&m->h_sam, &m->h_ref, &m->h_mask};
+        for (int a = 0; a < 3; a++)
+            for (int k = 0; k < (int)srcs[a]->size(); k++) {
+                const size_t n = (size_t)m->dim[2 * k] * m->dim[2 * k + 1];
+                UMPA_CUDA(cudaMemcpyAsync(dsts[a] + m->frame_off[k], (*srcs[a])[k], n * sizeof(double), cudaMemcpyHostToDevice, st));
+            }
+    }
     if (m->host_pending && (m->uniform || !m->masked)) {
         std::vector<double> mu;
         host_means(m, mu);
         int rc = table_alloc32(m);
         if (!rc) rc = table_set_means(m, mu.data(), st);
         if (!rc) rc = table_center_rows(m, 0, m->H, st);
-        if (rc) return rc;
+        if (rc) { if (tmp) { cudaStreamSynchronize(st); pool_free(tmp, tmp_bytes); } return rc; }
     }
-    UMPA_CUDA(cudaStreamSynchronize(st));
+    cudaError_t se = cudaStreamSynchronize(st);
+    if (tmp) pool_free(tmp, tmp_bytes);
+    UMPA_CUDA(se);
     m->host_pending = false; m->fp64_missing = false;
     return UMPA_OK;
 }
@@ -794,6 +828,126 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
     return UMPA_OK;
 }
 
+// The same pipeline for float32 host frames (umpa_set_frames_f32): the rows cross PCIe as they are -- half
+// the bytes of the float64 route, so no host conversion -- straight into the FP32 stacks, and are centred there.
+int streamed_match_f32(umpa_model *m, const RoiView &v, const umpa_outputs &dev, const umpa_outputs &host)
+{
+    const int Na = m->Na, H = m->H, W = m->W, pitch = m->pitch;
+    std::vector<int> edge;                      // band b = output rows [edge[b], edge[b+1])  (as in streamed_match)
+    {
+        int nu = std::max(1, std::min(10, v.N0 / 128));
+        if (const char *e = getenv("UMPA_BANDS")) nu = std::max(1, std::min(v.N0, atoi(e)));
+        const int rows_per = (v.N0 + nu - 1) / nu;
+        for (int r = 0; r < v.N0; r += rows_per) edge.push_back(r);
+        edge.push_back(v.N0);
+        for (int split = 0; split < 2 && nu > 1; split++) {
+            const int lo = edge[edge.size() - 2], hi = edge.back();
+            if (hi - lo < 64) break;
+            edge.insert(edge.end() - 1, lo + (hi - lo + 1) / 2);
+        }
+    }
+    const int nb = (int)edge.size() - 1;
+    std::vector<double> mu;
+    host_means(m, mu);
+    int rc = table_set_means(m, mu.data(), m->s_comp);
+    if (rc) return rc;
+
+    // equally spaced frames of one pinned allocation and no row padding: one 2-D copy per stack and band
+    const ptrdiff_t max_pitch = ((ptrdiff_t)1 << 31) - 1;
+    auto spacing = [&](const std::vector<const float *> &h) -> ptrdiff_t {
+        if (pitch != W || (ptrdiff_t)H * W * (ptrdiff_t)sizeof(float) > max_pitch) return 0;
+        if (Na < 2) return (ptrdiff_t)H * W;
+        const ptrdiff_t d = h[1] - h[0];
+        if (d < (ptrdiff_t)H * W || d * (ptrdiff_t)sizeof(float) > max_pitch) return 0;
+        for (int k = 2; k < Na; k++) if (h[k] - h[k - 1] != d) return 0;
+        return same_allocation(h[0], h[Na - 1] + (size_t)H * W) ? d : 0;
+    };
+    const ptrdiff_t gap_s = spacing(m->h_sam_f), gap_r = spacing(m->h_ref_f);
+    auto upload = [&](float *dst, const std::vector<const float *> &h, ptrdiff_t gap, int y0, int y1) -> cudaError_t {
+        const size_t rb = (size_t)W * sizeof(float);
+        if (gap > 0)
+            return cudaMemcpy2DAsync(dst + (size_t)y0 * pitch, (size_t)H * rb, h[0] + (size_t)y0 * W, (size_t)gap * sizeof(float),
+                                     (size_t)(y1 - y0) * rb, Na, cudaMemcpyHostToDevice, m->s_copy);
+        for (int k = 0; k < Na; k++) {
+            cudaError_t e = cudaMemcpy2DAsync(dst + ((size_t)k * H + y0) * pitch, (size_t)pitch * sizeof(float), h[k] + (size_t)y0 * W, rb,
+                                              rb, (size_t)(y1 - y0), cudaMemcpyHostToDevice, m->s_copy);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
+
+    std::vector<cudaEvent_t> ev(2 * nb, nullptr);
+    auto fail = [&](int code) {
+        cudaStreamSynchronize(m->s_copy); cudaStreamSynchronize(m->s_comp); cudaStreamSynchronize(m->s_out);
+        for (auto e : ev) if (e) cudaEventDestroy(e);
+        return code;
+    };
+#define ST_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+        umpa_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return fail(UMPA_ERR_CUDA); } } while (0)
+    for (auto &e : ev) ST_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    const bool trace = getenv("UMPA_STREAM_TRACE") != nullptr;     // timeline of the three streams on stderr
+    std::vector<cudaEvent_t> tev;                // trace only: start, then per band: copy, comp, out
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tev.push_back(e);
+    };
+    if (trace) { cudaStreamSynchronize(m->s_copy); cudaStreamSynchronize(m->s_comp); }
+    mark(m->s_copy);
+    int up_hi = 0, launches = 0;                // rows [0, up_hi) are on the device and centred
+    for (int b = 0; b < nb; b++) {
+        const int r0 = edge[b], r1 = edge[b + 1];
+        const int need = b == nb - 1 ? H : std::min(H, v.off0 + v.step0 * (r1 - 1) + m->padding + 1);
+        const int hi = std::max(up_hi, need);
+        if (hi > up_hi) {
+            ST_CUDA(upload(m->d_sam32, m->h_sam_f, gap_s, up_hi, hi));
+            ST_CUDA(upload(m->d_ref32, m->h_ref_f, gap_r, up_hi, hi));
+        }
+        ST_CUDA(cudaEventRecord(ev[2 * b], m->s_copy));
+        mark(m->s_copy);
+        ST_CUDA(cudaStreamWaitEvent(m->s_comp, ev[2 * b], 0));
+        if ((rc = table_center_rows_inplace(m, up_hi, hi, m->s_comp))) return fail(rc);
+        up_hi = hi;
+        RoiView vb = v;
+        vb.off0 = v.off0 + v.step0 * r0; vb.N0 = r1 - r0;
+        const size_t px0 = (size_t)r0 * v.N1;
+        if (v.abc) vb.abc = v.abc + 3 * px0;
+        if (v.cover) vb.cover = v.cover + px0;
+        const umpa_outputs db = offset_outputs(dev, px0);
+        m->last_launches = 0;
+        if ((rc = match_view(m, vb, db, m->s_comp, true))) return fail(rc);
+        launches += m->last_launches;
+        ST_CUDA(cudaEventRecord(ev[2 * b + 1], m->s_comp));
+        mark(m->s_comp);
+        ST_CUDA(cudaStreamWaitEvent(m->s_out, ev[2 * b + 1], 0));
+        if ((rc = download_outputs(offset_outputs(host, px0), db, (size_t)(r1 - r0) * v.N1, m->s_out))) return fail(rc);
+        mark(m->s_out);
+    }
+    m->last_launches = launches;
+    ST_CUDA(cudaStreamSynchronize(m->s_out));
+    ST_CUDA(cudaStreamSynchronize(m->s_comp));
+    ST_CUDA(cudaStreamSynchronize(m->s_copy));
+#undef ST_CUDA
+    if (trace) {
+        fprintf(stderr, "[umpa stream] float32 frames, %d bands\n", nb);
+        for (int b = 0; b < nb; b++) {
+            float tc = 0.f, tk = 0.f, to = 0.f;
+            cudaEventElapsedTime(&tc, tev[0], tev[1 + 3 * b]);
+            cudaEventElapsedTime(&tk, tev[0], tev[2 + 3 * b]);
+            cudaEventElapsedTime(&to, tev[0], tev[3 + 3 * b]);
+            fprintf(stderr, "[umpa stream] band %2d: uploaded %.2f  computed %.2f  downloaded %.2f ms\n", b, tc, tk, to);
+        }
+        for (auto e : tev) cudaEventDestroy(e);
+    }
+    for (auto e : ev) if (e) cudaEventDestroy(e);
+    m->host_pending = false;
+    m->fp64_missing = true;                     // no FP64 copy on the device: ensure_resident widens one on demand
+    m->stream_bands = nb; m->stream_threads = 0; m->stream_host_rows = 0;
+    return UMPA_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -860,36 +1014,45 @@ void umpa_destroy(umpa_model *m)
     delete m;
 }
 
-int umpa_set_frames(umpa_model *m, const double *const *sam, const double *const *ref, const double *const *mask,
-                    int on_device, void *stream)
+// device stacks + pointer tables for a new set of frames (shared by the float64 and float32 entry points)
+static int alloc_frames(umpa_model *m, bool has_mask)
 {
-    if (!m || !sam || !ref) { umpa_set_error("umpa_set_frames: NULL argument"); return UMPA_ERR_ARG; }
-    if (on_device < 0 || on_device > 2) { umpa_set_error("umpa_set_frames: on_device must be 0, 1 or 2"); return UMPA_ERR_ARG; }
-    cudaStream_t st = (cudaStream_t)stream;
     free_frames(m);
     const int Na = m->Na;
     m->frame_off.assign(Na, 0);
     size_t total = 0;
     for (int k = 0; k < Na; k++) { m->frame_off[k] = total; total += (size_t)m->dim[2 * k] * m->dim[2 * k + 1]; }
     m->stack_elems = total;
-    m->masked = mask != nullptr;
-    const double *const *srcs[3] = {sam, ref, mask};
-    for (int a = 0; a < 3; a++)
-        for (int k = 0; srcs[a] && k < Na; k++)
-            if (!srcs[a][k]) { umpa_set_error("umpa_set_frames: frame %d is NULL", k); return UMPA_ERR_ARG; }
+    m->masked = has_mask;
     double **dsts[3] = {&m->d_sam64, &m->d_ref64, &m->d_mask64};
     const double ***ptrs[3] = {&m->d_sam_ptrs, &m->d_ref_ptrs, &m->d_mask_ptrs};
     for (int a = 0; a < 3; a++) {
-        if (!srcs[a]) continue;
+        if (a == 2 && !has_mask) continue;
         UMPA_CUDA(pool_malloc((void **)dsts[a], total * sizeof(double)));
         std::vector<const double *> hp(Na);
         for (int k = 0; k < Na; k++) hp[k] = *dsts[a] + m->frame_off[k];
         UMPA_CUDA(cudaMemcpy((void *)*ptrs[a], hp.data(), Na * sizeof(double *), cudaMemcpyHostToDevice));
     }
-    m->dev_bytes += (int64_t)(total * sizeof(double) * (mask ? 3 : 2));
+    m->dev_bytes += (int64_t)(total * sizeof(double) * (has_mask ? 3 : 2));
     int rc = table_alloc32(m);
     if (rc) return rc;
     m->frames_set = true;
+    return UMPA_OK;
+}
+
+int umpa_set_frames(umpa_model *m, const double *const *sam, const double *const *ref, const double *const *mask,
+                    int on_device, void *stream)
+{
+    if (!m || !sam || !ref) { umpa_set_error("umpa_set_frames: NULL argument"); return UMPA_ERR_ARG; }
+    if (on_device < 0 || on_device > 2) { umpa_set_error("umpa_set_frames: on_device must be 0, 1 or 2"); return UMPA_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Na = m->Na;
+    const double *const *srcs[3] = {sam, ref, mask};
+    for (int a = 0; a < 3; a++)
+        for (int k = 0; srcs[a] && k < Na; k++)
+            if (!srcs[a][k]) { umpa_set_error("umpa_set_frames: frame %d is NULL", k); return UMPA_ERR_ARG; }
+    int rc = alloc_frames(m, mask != nullptr);
+    if (rc) return rc;
     if (on_device == 2) {                       // keep the host pointers; the first match uploads
         m->h_sam.assign(sam, sam + Na);
         m->h_ref.assign(ref, ref + Na);
@@ -898,13 +1061,32 @@ int umpa_set_frames(umpa_model *m, const double *const *sam, const double *const
         return UMPA_OK;
     }
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    double *dsts[3] = {m->d_sam64, m->d_ref64, m->d_mask64};
     for (int a = 0; a < 3; a++)
         for (int k = 0; srcs[a] && k < Na; k++) {
             const size_t n = (size_t)m->dim[2 * k] * m->dim[2 * k + 1];
-            UMPA_CUDA(cudaMemcpyAsync(*dsts[a] + m->frame_off[k], srcs[a][k], n * sizeof(double), kind, st));
+            UMPA_CUDA(cudaMemcpyAsync(dsts[a] + m->frame_off[k], srcs[a][k], n * sizeof(double), kind, st));
         }
     if ((rc = table_prepare_frames(m, st))) return rc;
     UMPA_CUDA(cudaStreamSynchronize(st));
+    return UMPA_OK;
+}
+
+int umpa_set_frames_f32(umpa_model *m, const float *const *sam, const float *const *ref, const float *const *mask)
+{
+    if (!m || !sam || !ref) { umpa_set_error("umpa_set_frames_f32: NULL argument"); return UMPA_ERR_ARG; }
+    const int Na = m->Na;
+    const float *const *srcs[3] = {sam, ref, mask};
+    for (int a = 0; a < 3; a++)
+        for (int k = 0; srcs[a] && k < Na; k++)
+            if (!srcs[a][k]) { umpa_set_error("umpa_set_frames_f32: frame %d is NULL", k); return UMPA_ERR_ARG; }
+    int rc = alloc_frames(m, mask != nullptr);
+    if (rc) return rc;
+    m->h_sam_f.assign(sam, sam + Na);
+    m->h_ref_f.assign(ref, ref + Na);
+    if (mask) m->h_mask_f.assign(mask, mask + Na);
+    m->host_f32 = true;
+    m->host_pending = true;                     // the first match / cost / min uploads (umpa_set_frames, on_device = 2)
     return UMPA_OK;
 }
 
@@ -991,7 +1173,7 @@ int umpa_match_host(umpa_model *m, const int32_t roi[6], const double uv0[2], co
 
     // frames still on the host and the table path applies: pipeline upload / kernels / download
     if (m->host_pending && m->path_opt != UMPA_PATH_LAZY && !getenv("UMPA_NO_STREAMING") && table_eligible(m, v, nullptr))
-        return streamed_match(m, v, d, *out);
+        return m->host_f32 ? streamed_match_f32(m, v, d, *out) : streamed_match(m, v, d, *out);
 
     if ((rc = match_view(m, v, d, m->s_comp))) return rc;
     if ((rc = download_outputs(*out, d, n, m->s_comp))) return rc;

@@ -96,6 +96,8 @@ struct umpa_model {
     // host frames whose upload is deferred to the first match (umpa_set_frames with on_device = 2):
     // umpa_match_host then pipelines upload, kernels and download in row bands
     std::vector<const double *> h_sam, h_ref, h_mask;
+    std::vector<const float *> h_sam_f, h_ref_f, h_mask_f;    // umpa_set_frames_f32: float32 host frames instead
+    bool host_f32 = false;
     bool host_pending = false;                   // nothing of the host frames is on the device yet
     bool fp64_missing = false;                   // FP32 stacks complete, FP64 stacks not (rows the host converted)
     cudaStream_t s_copy = nullptr, s_comp = nullptr, s_out = nullptr;
@@ -141,6 +143,7 @@ int coverage_map(umpa_model *m, const RoiView &roi, double *out_dev, cudaStream_
 int table_prepare_frames(umpa_model *m, cudaStream_t st);      // FP64 stacks -> centred FP32 stacks (all three steps)
 int table_alloc32(umpa_model *m);                              // 1. FP32 stacks + constants (no-op when not applicable)
 int table_means(umpa_model *m, cudaStream_t st);               // 2. centring constants from the sampled rows (see table_row_step)
+int table_center_rows_inplace(umpa_model *m, int y0, int y1, cudaStream_t st);   // 3'. raw FP32 rows already in the FP32 stacks
 int table_center_rows(umpa_model *m, int y0, int y1, cudaStream_t st);   // 3. rows [y0,y1) of every frame -> centred FP32
 int table_set_means(umpa_model *m, const double *mu, cudaStream_t st);   // 2'. constants computed by the host (mu: 2*Na)
 int table_row_step(int H);                                     // rows y = 0, step, 2 step, ... define the centring constants
@@ -150,6 +153,7 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
 
 // implemented in hoststage.cu (host code)
 double host_sampled_mean(const double *frame, int H, int W, int step);
+double host_sampled_mean_f32(const float *frame, int H, int W, int step);     // == host_sampled_mean of the widened frame
 void host_center_rows(float *dst, const double *src, int rows, int W, int pitch, double c);
 
 // implemented in kernel_path.cu: per-pixel FP32 tables of UMPAModelDFKernel (blur fused into the window pass)

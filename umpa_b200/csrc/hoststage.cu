@@ -7,22 +7,29 @@
 
 #include "common.cuh"
 
-// mean of rows 0, step, 2 step, ... of one H x W frame (fixed summation order: row by row, 4 lanes)
-double host_sampled_mean(const double *frame, int H, int W, int step)
+// mean of rows 0, step, 2 step, ... of one H x W frame (fixed summation order: row by row, 4 lanes;
+// float32 frames are widened element by element, so they give the mean of the widened frame bit for bit)
+template <typename T>
+static double sampled_mean(const T *frame, int H, int W, int step)
 {
     double s = 0.;
     size_t count = 0;
     for (int y = 0; y < H; y += step) {
-        const double *row = frame + (size_t)y * W;
+        const T *row = frame + (size_t)y * W;
         double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
         int x = 0;
-        for (; x + 4 <= W; x += 4) { a0 += row[x]; a1 += row[x + 1]; a2 += row[x + 2]; a3 += row[x + 3]; }
-        for (; x < W; x++) a0 += row[x];
+        for (; x + 4 <= W; x += 4) {
+            a0 += (double)row[x]; a1 += (double)row[x + 1]; a2 += (double)row[x + 2]; a3 += (double)row[x + 3];
+        }
+        for (; x < W; x++) a0 += (double)row[x];
         s += (a0 + a1) + (a2 + a3);
         count += (size_t)W;
     }
     return s / (double)count;
 }
+
+double host_sampled_mean(const double *frame, int H, int W, int step) { return sampled_mean(frame, H, W, step); }
+double host_sampled_mean_f32(const float *frame, int H, int W, int step) { return sampled_mean(frame, H, W, step); }
 
 namespace {
 
@@ -67,6 +74,11 @@ void host_center_rows(float *dst, const double *src, int rows, int W, int pitch,
 extern "C" UMPA_API double umpa_host_sampled_mean(const double *frame, int H, int W, int step)
 {
     return host_sampled_mean(frame, H, W, step);
+}
+
+extern "C" UMPA_API double umpa_host_sampled_mean_f32(const float *frame, int H, int W, int step)
+{
+    return host_sampled_mean_f32(frame, H, W, step);
 }
 
 extern "C" UMPA_API void umpa_host_center_rows(float *dst, const double *src, int rows, int W, int pitch, double c)

@@ -118,6 +118,18 @@ __global__ void center_frames(const double *const *sam, const double *const *ref
     dst[x] = (float)(v - means64[f]);
 }
 
+// float32 host frames (umpa_set_frames_f32) are copied raw into the FP32 stacks and centred where they lie:
+// the same value as center_frames gives for the widened frame -- (float)((double)x - c) -- and (float)(0 - c)
+// in the pitch padding.  Equal frames at position 0 only (the pipelined path).  grid (ceil(pitch/256), rows, 2*Na)
+__global__ void center_inplace(const double *means64, int Na, int H, int W, int pitch, int y0, float *sam32, float *ref32)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = y0 + blockIdx.y, f = blockIdx.z;
+    if (x >= pitch) return;
+    float *row = (f < Na ? sam32 + ((size_t)f * H + y) * pitch : ref32 + ((size_t)(f - Na) * H + y) * pitch);
+    const double v = x < W ? (double)row[x] : 0.;
+    row[x] = (float)(v - means64[f]);
+}
+
 // ------------------------------------------------------------------ moments
 
 struct MomentsParams {
@@ -667,6 +679,15 @@ int table_center_rows(umpa_model *m, int y0, int y1, cudaStream_t st)
     if (!table_applicable(m) || y1 <= y0) return UMPA_OK;
     center_frames<<<dim3((m->pitch + 255) / 256, y1 - y0, 2 * m->Na), 256, 0, st>>>(
         m->d_sam_ptrs, m->d_ref_ptrs, m->d_dim, m->d_pos, m->d_means64, m->Na, m->H, m->pitch, y0, m->d_sam32, m->d_ref32);
+    UMPA_CUDA(cudaGetLastError());
+    return UMPA_OK;
+}
+
+int table_center_rows_inplace(umpa_model *m, int y0, int y1, cudaStream_t st)
+{
+    if (!m->uniform || y1 <= y0) return UMPA_OK;
+    center_inplace<<<dim3((m->pitch + 255) / 256, y1 - y0, 2 * m->Na), 256, 0, st>>>(
+        m->d_means64, m->Na, m->H, m->W, m->pitch, y0, m->d_sam32, m->d_ref32);
     UMPA_CUDA(cudaGetLastError());
     return UMPA_OK;
 }

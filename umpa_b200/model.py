@@ -11,7 +11,8 @@ Differences from the reference that a caller can see (documented, deliberate):
     kernels); device (torch) frames when the model is constructed.  Later in-place edits of
     the caller's arrays are not seen (the reference keeps raw pointers);
   * non-float64 inputs are converted (the reference reads them as garbage,
-    model.pyx:236-237);
+    model.pyx:236-237); when every frame is a float32 numpy array the frames go to the GPU as
+    float32 (half the upload) and are widened there -- same results as for the widened arrays;
   * ``num_threads`` is accepted and ignored;
   * ``match(..., debug=False)`` skips the ``debug_*`` arrays (the reference decides
     this at compile time with ``DEF DEBUG``, model.pyx:26, 493-497);
@@ -58,6 +59,8 @@ class UMPAModelBase:
         Nw = int(window_size)
         Na = len(sam_list)
         self._on_device = all(isinstance(x, torch.Tensor) for x in sam_list)
+        every = list(sam_list) + list(ref_list) + (list(mask_list) if mask_list is not None else [])
+        self._f32 = all(isinstance(x, np.ndarray) and x.dtype == np.float32 for x in every)
 
         self._check_contiguous(sam_list)
         sams = [self._frame(s) for s in sam_list]
@@ -125,9 +128,13 @@ class UMPAModelBase:
         # kernels in row bands (umpa_match_host).  Like the reference (model.pyx:242-262) the model
         # keeps references to the caller's arrays until then.
         self._frames_keepalive = (sams, refs, masks)
-        _capi.check(L.umpa_set_frames(self._h, ptrs(sams), ptrs(refs),
-                                      ptrs(masks) if masks is not None else None,
-                                      1 if self._on_device else 2, self._stream()))
+        if self._f32:
+            _capi.check(L.umpa_set_frames_f32(self._h, ptrs(sams), ptrs(refs),
+                                              ptrs(masks) if masks is not None else None))
+        else:
+            _capi.check(L.umpa_set_frames(self._h, ptrs(sams), ptrs(refs),
+                                          ptrs(masks) if masks is not None else None,
+                                          1 if self._on_device else 2, self._stream()))
         self._geo.set_ROI(ROI)
 
     # ------------------------------------------------------------------ plumbing
@@ -144,7 +151,7 @@ class UMPAModelBase:
             if not x.is_cuda:
                 raise RuntimeError('Frames given as torch tensors must all live on the GPU.')
             return x.to(torch.float64).contiguous()
-        return np.ascontiguousarray(np.asarray(x), dtype=np.float64)
+        return np.ascontiguousarray(np.asarray(x), dtype=np.float32 if self._f32 else np.float64)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
