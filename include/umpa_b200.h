@@ -196,6 +196,7 @@ UMPA_API int64_t umpa_device_bytes(const umpa_model *m);
 UMPA_API double umpa_host_sampled_mean(const double *frame, int H, int W, int step);
 UMPA_API double umpa_host_sampled_mean_f32(const float *frame, int H, int W, int step);
 UMPA_API void umpa_host_center_rows(float *dst, const double *src, int rows, int W, int pitch, double c);
+UMPA_API void umpa_host_center_rows_f32(float *dst, const float *src, int rows, int W, int pitch, double c);
 
 /* Measured FP32-FMA peak of the current device (dependent-free FFMA chains on all SMs, CUDA
  * events): the denominator of the FP32-FMA roofline that bench.py reports. */

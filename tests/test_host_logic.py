@@ -106,6 +106,13 @@ def test_host_staging_helpers():
         out = dst.reshape(rows, pitch)
         np.testing.assert_array_equal(out[:, :W], (src - c).astype(np.float32))
         assert np.all(out[:, W:] == 0) and np.all(buf[:off] == -7) and np.all(buf[off + rows * pitch:] == -7)
+        # float32 source rows (pageable float32 frames): widened, centred, rounded once
+        src32 = src.astype(np.float32)
+        buf[:] = -7.
+        L.umpa_host_center_rows_f32(dst.ctypes.data_as(C.POINTER(C.c_float)), src32.ctypes.data_as(C.POINTER(C.c_float)),
+                                    rows, W, pitch, c)
+        np.testing.assert_array_equal(out[:, :W], (src32.astype(np.float64) - c).astype(np.float32))
+        assert np.all(out[:, W:] == 0) and np.all(buf[:off] == -7) and np.all(buf[off + rows * pitch:] == -7)
     fr = rng.normal(1., .5, (100, 77))
     for step in (1, 3, 32, 1000):
         got = L.umpa_host_sampled_mean(fr.ctypes.data_as(C.POINTER(C.c_double)), 100, 77, step)

@@ -14,7 +14,7 @@ PATH_NAMES = {0: "none", 1: "table", 2: "lazy", 3: "mixed"}
 EXPORTS = ("umpa_create", "umpa_destroy", "umpa_set_frames", "umpa_set_frames_f32", "umpa_set_window", "umpa_set_option",
            "umpa_get_option", "umpa_match", "umpa_match_host", "umpa_cost", "umpa_min", "umpa_coverage", "umpa_correct_bad_pixels",
            "umpa_last_match_info", "umpa_last_stream_info", "umpa_set_profiling", "umpa_last_stage_ms", "umpa_device_bytes",
-           "umpa_fma_peak", "umpa_host_sampled_mean", "umpa_host_sampled_mean_f32", "umpa_host_center_rows", "umpa_last_error", "umpa_version")
+           "umpa_fma_peak", "umpa_host_sampled_mean", "umpa_host_sampled_mean_f32", "umpa_host_center_rows", "umpa_host_center_rows_f32", "umpa_last_error", "umpa_version")
 
 
 class Outputs(C.Structure):
@@ -85,6 +85,8 @@ def lib():
     L.umpa_host_sampled_mean_f32.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int]
     L.umpa_host_center_rows.restype = None
     L.umpa_host_center_rows.argtypes = [C.POINTER(C.c_float), dp, C.c_int, C.c_int, C.c_int, C.c_double]
+    L.umpa_host_center_rows_f32.restype = None
+    L.umpa_host_center_rows_f32.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_double]
     L.umpa_last_error.restype = C.c_char_p
     L.umpa_version.restype = C.c_char_p
     _lib = L

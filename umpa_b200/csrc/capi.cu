@@ -532,6 +532,8 @@ int host_threads()
 // center_frames: FP64 subtract, one rounding) while the DMA engine is busy with the upper part in
 // FP64; the converted rows then cross at half the bytes, straight into the FP32 stacks.
 // Pixels are independent: the result is the one the unpipelined path gives for the same constants.
+int streamed_match_f32(umpa_model *m, const RoiView &v, const umpa_outputs &dev, const umpa_outputs &host);
+
 int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, const umpa_outputs &host)
 {
     const int Na = m->Na, H = m->H, W = m->W, pitch = m->pitch;
@@ -558,7 +560,16 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
     // host conversion: rows [Yc, H) of every frame are converted by nthr host threads
     int nthr = nb > 1 ? host_threads() : 0;
     int Yc = H;
-    if (nthr > 0) {
+    if (m->host_f32) {
+        // float32 frames: pinned ones go up as they are at the full DMA rate (streamed_match_f32); pageable ones
+        // would crawl through the driver's staging (measured: 80 ms for config 2), so the host threads centre ALL
+        // their rows into the pinned staging instead -- the float64 machinery below with a float source.
+        cudaPointerAttributes pa{};
+        const bool pinned = cudaPointerGetAttributes(&pa, m->h_sam_f[0]) == cudaSuccess && pa.type != cudaMemoryTypeUnregistered;
+        cudaGetLastError();
+        if (pinned || nthr == 0) return streamed_match_f32(m, v, dev, host);
+        Yc = 0;
+    } else if (nthr > 0) {
         // Which share x of the rows should the host convert?  Per input byte a converted row costs the
         // host memory system 2 bytes of traffic (read, write FP32, DMA read of the FP32) against 1 for a
         // row that goes up as FP64, and PCIe half a byte against one.  With M = B_conc + 1.5 R_conc the
@@ -626,6 +637,7 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
             } else g_stage.bytes = want;
         }
     }
+    if (m->host_f32 && nthr == 0) return streamed_match_f32(m, v, dev, host);    // no staging: plain copies after all
 
     // frames that are equally spaced slices of one host stack go up with one 2-D copy per stack and band
     // (cudaMemcpy2D pitches are limited to cudaDevAttrMaxPitch = 2^31 - 1 bytes, and the whole source range has
@@ -639,7 +651,7 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
         for (int k = 2; k < Na; k++) if (h[k] - h[k - 1] != d) return 0;
         return same_allocation(h[0], h[Na - 1] + (size_t)H * W) ? d : 0;
     };
-    const ptrdiff_t gap_s = spacing(m->h_sam), gap_r = spacing(m->h_ref);
+    const ptrdiff_t gap_s = m->host_f32 ? 0 : spacing(m->h_sam), gap_r = m->host_f32 ? 0 : spacing(m->h_ref);
 
     // ---- host workers: constants first, then conversion jobs in the order the bands need them ----
     struct Job { int band, stack, frame, y0, y1; };
@@ -666,7 +678,8 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
         for (;;) {
             const int f = next_mean.fetch_add(1);
             if (f >= 2 * Na) break;
-            mu[f] = host_sampled_mean(f < Na ? m->h_sam[f] : m->h_ref[f - Na], H, W, rs);
+            if (m->host_f32) mu[f] = host_sampled_mean_f32(f < Na ? m->h_sam_f[f] : m->h_ref_f[f - Na], H, W, rs);
+            else mu[f] = host_sampled_mean(f < Na ? m->h_sam[f] : m->h_ref[f - Na], H, W, rs);
         }
         means_done.fetch_add(1, std::memory_order_acq_rel);
         while (means_done.load(std::memory_order_acquire) < nthr) std::this_thread::yield();
@@ -675,9 +688,12 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
             const int j = next_job.fetch_add(1);
             if (j >= (int)jobs.size() || abort_flag.load()) break;
             const Job &q = jobs[j];
-            const double *src = (q.stack == 0 ? m->h_sam[q.frame] : m->h_ref[q.frame]) + (size_t)q.y0 * W;
             float *dst = g_stage.p + ((size_t)(q.stack * Na + q.frame) * HC + (q.y0 - Yc)) * pitch;
-            host_center_rows(dst, src, q.y1 - q.y0, W, pitch, mu[q.stack == 0 ? q.frame : Na + q.frame]);
+            const double c = mu[q.stack == 0 ? q.frame : Na + q.frame];
+            if (m->host_f32)
+                host_center_rows_f32(dst, (q.stack == 0 ? m->h_sam_f[q.frame] : m->h_ref_f[q.frame]) + (size_t)q.y0 * W, q.y1 - q.y0, W, pitch, c);
+            else
+                host_center_rows(dst, (q.stack == 0 ? m->h_sam[q.frame] : m->h_ref[q.frame]) + (size_t)q.y0 * W, q.y1 - q.y0, W, pitch, c);
             left[q.band].fetch_sub(1, std::memory_order_acq_rel);
             conv_t1[wid] = clk::now();
         }
@@ -809,7 +825,7 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
     for (auto e : ev) if (e) cudaEventDestroy(e);
     m->host_pending = false;
     m->fp64_missing = Yc < H;
-    if (nthr > 0 && !jobs.empty()) {             // update the measured rates
+    if (nthr > 0 && !jobs.empty() && !m->host_f32) {     // update the measured rates
         clk::time_point a = conv_t0[0], z = conv_t1[0];
         for (int t = 1; t < nthr; t++) { a = std::min(a, conv_t0[t]); z = std::max(z, conv_t1[t]); }
         const double secs = std::chrono::duration<double>(z - a).count();
@@ -1173,7 +1189,7 @@ int umpa_match_host(umpa_model *m, const int32_t roi[6], const double uv0[2], co
 
     // frames still on the host and the table path applies: pipeline upload / kernels / download
     if (m->host_pending && m->path_opt != UMPA_PATH_LAZY && !getenv("UMPA_NO_STREAMING") && table_eligible(m, v, nullptr))
-        return m->host_f32 ? streamed_match_f32(m, v, d, *out) : streamed_match(m, v, d, *out);
+        return streamed_match(m, v, d, *out);      // (float32 frames: it picks the plain or the host-staged pipeline)
 
     if ((rc = match_view(m, v, d, m->s_comp))) return rc;
     if ((rc = download_outputs(*out, d, n, m->s_comp))) return rc;

@@ -155,6 +155,7 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
 double host_sampled_mean(const double *frame, int H, int W, int step);
 double host_sampled_mean_f32(const float *frame, int H, int W, int step);     // == host_sampled_mean of the widened frame
 void host_center_rows(float *dst, const double *src, int rows, int W, int pitch, double c);
+void host_center_rows_f32(float *dst, const float *src, int rows, int W, int pitch, double c);
 
 // implemented in kernel_path.cu: per-pixel FP32 tables of UMPAModelDFKernel (blur fused into the window pass)
 bool ktable_supported(int Nw, int max_shift, int step0, bool refshift);

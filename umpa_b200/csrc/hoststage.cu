@@ -52,11 +52,28 @@ __attribute__((target("avx2"))) void convert_avx2(float *dst, const double *src,
     _mm_sfence();
 }
 
-}  // namespace
+void convert_scalar(float *dst, const float *src, size_t n, double c)
+{
+    for (size_t i = 0; i < n; i++) dst[i] = (float)((double)src[i] - c);
+}
 
-// dst[y][x] = (float)(src[y][x] - c) for `rows` rows of W doubles -> rows of `pitch` floats (zero padded).
-// Same arithmetic as center_frames (table_path.cu): FP64 subtraction, one rounding to FP32.
-void host_center_rows(float *dst, const double *src, int rows, int W, int pitch, double c)
+__attribute__((target("avx2"))) void convert_avx2(float *dst, const float *src, size_t n, double c)
+{
+    const __m256d vc = _mm256_set1_pd(c);
+    size_t i = 0;
+    for (; i < n && ((uintptr_t)(dst + i) & 31); i++) dst[i] = (float)((double)src[i] - c);
+    for (; i + 8 <= n; i += 8) {
+        const __m256 v = _mm256_loadu_ps(src + i);
+        const __m128 lo = _mm256_cvtpd_ps(_mm256_sub_pd(_mm256_cvtps_pd(_mm256_castps256_ps128(v)), vc));
+        const __m128 hi = _mm256_cvtpd_ps(_mm256_sub_pd(_mm256_cvtps_pd(_mm256_extractf128_ps(v, 1)), vc));
+        _mm256_stream_ps(dst + i, _mm256_set_m128(hi, lo));
+    }
+    for (; i < n; i++) dst[i] = (float)((double)src[i] - c);
+    _mm_sfence();
+}
+
+template <typename T>
+void center_rows(float *dst, const T *src, int rows, int W, int pitch, double c)
 {
     static const bool avx2 = __builtin_cpu_supports("avx2");
     if (pitch == W) {
@@ -70,6 +87,14 @@ void host_center_rows(float *dst, const double *src, int rows, int W, int pitch,
     }
 }
 
+}  // namespace
+
+// dst[y][x] = (float)(src[y][x] - c) for `rows` rows of W doubles -> rows of `pitch` floats (zero padded).
+// Same arithmetic as center_frames (table_path.cu): FP64 subtraction, one rounding to FP32.
+void host_center_rows(float *dst, const double *src, int rows, int W, int pitch, double c) { center_rows(dst, src, rows, W, pitch, c); }
+// float32 source rows: widened, centred, rounded once -- what the device does to rows that went up raw (center_inplace)
+void host_center_rows_f32(float *dst, const float *src, int rows, int W, int pitch, double c) { center_rows(dst, src, rows, W, pitch, c); }
+
 // ---- test hooks (no GPU needed): the two host helpers above through the C ABI ----------------
 extern "C" UMPA_API double umpa_host_sampled_mean(const double *frame, int H, int W, int step)
 {
@@ -79,6 +104,11 @@ extern "C" UMPA_API double umpa_host_sampled_mean(const double *frame, int H, in
 extern "C" UMPA_API double umpa_host_sampled_mean_f32(const float *frame, int H, int W, int step)
 {
     return host_sampled_mean_f32(frame, H, W, step);
+}
+
+extern "C" UMPA_API void umpa_host_center_rows_f32(float *dst, const float *src, int rows, int W, int pitch, double c)
+{
+    host_center_rows_f32(dst, src, rows, W, pitch, c);
 }
 
 extern "C" UMPA_API void umpa_host_center_rows(float *dst, const double *src, int rows, int W, int pitch, double c)
