@@ -532,26 +532,30 @@ int host_threads()
 // center_frames: FP64 subtract, one rounding) while the DMA engine is busy with the upper part in
 // FP64; the converted rows then cross at half the bytes, straight into the FP32 stacks.
 // Pixels are independent: the result is the one the unpipelined path gives for the same constants.
+// Row bands of a pipelined match: equal slices of the N0 output rows, the last one halved twice so that little
+// work is left when the final rows arrive (kernels and download hide behind the upload).  UMPA_BANDS overrides.
+std::vector<int> band_edges(int N0)
+{
+    std::vector<int> edge;
+    int nu = std::max(1, std::min(10, N0 / 128));
+    if (const char *e = getenv("UMPA_BANDS")) nu = std::max(1, std::min(N0, atoi(e)));
+    const int rows_per = (N0 + nu - 1) / nu;
+    for (int r = 0; r < N0; r += rows_per) edge.push_back(r);
+    edge.push_back(N0);
+    for (int split = 0; split < 2 && nu > 1; split++) {
+        const int lo = edge[edge.size() - 2], hi = edge.back();
+        if (hi - lo < 64) break;
+        edge.insert(edge.end() - 1, lo + (hi - lo + 1) / 2);
+    }
+    return edge;
+}
+
 int streamed_match_f32(umpa_model *m, const RoiView &v, const umpa_outputs &dev, const umpa_outputs &host);
 
 int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, const umpa_outputs &host)
 {
     const int Na = m->Na, H = m->H, W = m->W, pitch = m->pitch;
-    // bands: equal slices of the output rows, the last one halved twice so that little work is left
-    // when the final rows arrive (kernels and download hide behind the upload)
-    std::vector<int> edge;                      // band b = output rows [edge[b], edge[b+1])
-    {
-        int nu = std::max(1, std::min(10, v.N0 / 128));
-        if (const char *e = getenv("UMPA_BANDS")) nu = std::max(1, std::min(v.N0, atoi(e)));
-        const int rows_per = (v.N0 + nu - 1) / nu;
-        for (int r = 0; r < v.N0; r += rows_per) edge.push_back(r);
-        edge.push_back(v.N0);
-        for (int split = 0; split < 2 && nu > 1; split++) {
-            const int lo = edge[edge.size() - 2], hi = edge.back();
-            if (hi - lo < 64) break;
-            edge.insert(edge.end() - 1, lo + (hi - lo + 1) / 2);
-        }
-    }
+    const std::vector<int> edge = band_edges(v.N0);     // band b = output rows [edge[b], edge[b+1])
     const int nb = (int)edge.size() - 1;
     std::vector<int> need(nb);                  // band b needs input rows [0, need[b])
     for (int b = 0; b < nb; b++)
@@ -849,19 +853,7 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
 int streamed_match_f32(umpa_model *m, const RoiView &v, const umpa_outputs &dev, const umpa_outputs &host)
 {
     const int Na = m->Na, H = m->H, W = m->W, pitch = m->pitch;
-    std::vector<int> edge;                      // band b = output rows [edge[b], edge[b+1])  (as in streamed_match)
-    {
-        int nu = std::max(1, std::min(10, v.N0 / 128));
-        if (const char *e = getenv("UMPA_BANDS")) nu = std::max(1, std::min(v.N0, atoi(e)));
-        const int rows_per = (v.N0 + nu - 1) / nu;
-        for (int r = 0; r < v.N0; r += rows_per) edge.push_back(r);
-        edge.push_back(v.N0);
-        for (int split = 0; split < 2 && nu > 1; split++) {
-            const int lo = edge[edge.size() - 2], hi = edge.back();
-            if (hi - lo < 64) break;
-            edge.insert(edge.end() - 1, lo + (hi - lo + 1) / 2);
-        }
-    }
+    const std::vector<int> edge = band_edges(v.N0);     // band b = output rows [edge[b], edge[b+1])
     const int nb = (int)edge.size() - 1;
     std::vector<double> mu;
     host_means(m, mu);
