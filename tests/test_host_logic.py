@@ -113,6 +113,13 @@ def test_host_staging_helpers():
                                     rows, W, pitch, c)
         np.testing.assert_array_equal(out[:, :W], (src32.astype(np.float64) - c).astype(np.float32))
         assert np.all(out[:, W:] == 0) and np.all(buf[:off] == -7) and np.all(buf[off + rows * pitch:] == -7)
+    # a NaN / Inf pixel on a sampled row counts as 0: the constant stays finite (any constant is valid)
+    bad = rng.normal(1., .5, (64, 50))
+    good = bad.copy()
+    bad[32, 7], bad[0, 49] = np.nan, np.inf
+    good[32, 7] = good[0, 49] = 0.
+    assert (L.umpa_host_sampled_mean(bad.ctypes.data_as(C.POINTER(C.c_double)), 64, 50, 2) ==
+            L.umpa_host_sampled_mean(good.ctypes.data_as(C.POINTER(C.c_double)), 64, 50, 2))
     fr = rng.normal(1., .5, (100, 77))
     for step in (1, 3, 32, 1000):
         got = L.umpa_host_sampled_mean(fr.ctypes.data_as(C.POINTER(C.c_double)), 100, 77, step)

@@ -9,6 +9,10 @@
 
 // mean of rows 0, step, 2 step, ... of one H x W frame (fixed summation order: row by row, 4 lanes;
 // float32 frames are widened element by element, so they give the mean of the widened frame bit for bit)
+// A NaN / Inf pixel (a dead pixel divided by its flat field) must stay a local defect -- the windows that touch
+// it -- as it is in the reference; it counts as 0 here so that it does not poison the frame's constant.
+static inline double finite_or_zero(double v) { return v - v == 0. ? v : 0.; }
+
 template <typename T>
 static double sampled_mean(const T *frame, int H, int W, int step)
 {
@@ -19,9 +23,10 @@ static double sampled_mean(const T *frame, int H, int W, int step)
         double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
         int x = 0;
         for (; x + 4 <= W; x += 4) {
-            a0 += (double)row[x]; a1 += (double)row[x + 1]; a2 += (double)row[x + 2]; a3 += (double)row[x + 3];
+            a0 += finite_or_zero((double)row[x]); a1 += finite_or_zero((double)row[x + 1]);
+            a2 += finite_or_zero((double)row[x + 2]); a3 += finite_or_zero((double)row[x + 3]);
         }
-        for (; x < W; x++) a0 += (double)row[x];
+        for (; x < W; x++) a0 += finite_or_zero((double)row[x]);
         s += (a0 + a1) + (a2 + a3);
         count += (size_t)W;
     }

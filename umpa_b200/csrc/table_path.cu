@@ -65,7 +65,10 @@ __global__ void frame_partial_sums(const double *const *sam, const double *const
     double s = 0.;
     for (int r = blockIdx.x; r < nrows; r += SUM_BLOCKS) {
         const double *row = src + (size_t)r * row_step * W;
-        for (int x = threadIdx.x; x < W; x += blockDim.x) s += row[x];
+        for (int x = threadIdx.x; x < W; x += blockDim.x) {
+            const double v = row[x];
+            s += isfinite(v) ? v : 0.;             // a NaN / Inf pixel stays a local defect (hoststage.cu: finite_or_zero)
+        }
     }
     __shared__ double red[256];
     red[threadIdx.x] = s;

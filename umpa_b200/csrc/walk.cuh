@@ -121,7 +121,7 @@ __device__ inline int walk_minimise(Eval &eval, int subpx, const double *quad, F
     const double tol = 1e-8;                       // absolute, Optim.cpp:243
     constexpr unsigned COL0 = 0x108421u, COL4 = 0x1084210u, ALL = 0x1ffffffu;
     int settled0 = 0, settled1 = 0, axis = 0, st = UMPA_ST_OK;
-    int phase = P_INIT, ip = 0, jp = 0;
+    int phase = P_INIT, ip = 0, jp = 0, idle = 0;
     bool up_m = false, up_p = false, skip_limit = false, finished = false;
     // which entries of d hold an evaluated cost (the reference tests d < -0.5; a register bit is cheaper
     // than a shared-memory load and lets the 4x4 fill find its next missing entry with one ffs)
@@ -143,6 +143,11 @@ __device__ inline int walk_minimise(Eval &eval, int subpx, const double *quad, F
                 break;
             case P_TOP:
                 if (!skip_limit && ncalls >= UMPA_MAX_CALLS) { st = 0; phase = P_DONE; }   // Optim.cpp:267,477
+                // Not in the reference: with a NaN cost next to finite ones (a non-finite input pixel) its loop can step
+                // back and forth between two evaluated shifts for ever -- MAX_CALLS only counts evaluations.  Finite
+                // costs never revisit (a few visits here between two evaluations at most), so this changes no result;
+                // it turns a hung GPU into a failed pixel (err = 0).
+                else if (++idle > 16) { st = 0; phase = P_DONE; }
                 else { skip_limit = false; phase = P_LO; }
                 break;
             case P_LO:
@@ -218,6 +223,7 @@ __device__ inline int walk_minimise(Eval &eval, int subpx, const double *quad, F
         double v;
         const int se = eval(e0, e1, v, args);
         ncalls++;
+        idle = 0;
         if (se != UMPA_ST_OK) { st = se; break; }  // bound error: return at once (Optim.cpp:264,291,324,359)
 
         // ---- file the result ----
