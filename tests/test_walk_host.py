@@ -52,13 +52,13 @@ struct HostEval {
     }
 };
 extern "C" int walk_host(cost_fn fn, const void *m, int i, int j, const double *abc, const double *poison, int ms, int subpx,
-                         const double *uv0, double *res /* f, t, v, uv0, uv1 */, double *d, double *a, int *ncalls)
+                         const double *quad, const double *uv0, double *res /* f, t, v, uv0, uv1 */, double *d, double *a, int *ncalls)
 {
     HostEval ev{fn, m, i, j, abc, poison, ms};
     FitArgs args{0., 0.};
     double f = 0., uv[2] = {uv0[0], uv0[1]};
     for (int t = 0; t < 16; t++) a[t] = 0.;
-    const int st = walk_minimise(ev, subpx, (const double *)nullptr, args, f, uv, d, a, *ncalls);
+    const int st = walk_minimise(ev, subpx, quad, args, f, uv, d, a, *ncalls);
     res[0] = f; res[1] = args.t; res[2] = args.v; res[3] = uv[0]; res[4] = uv[1];
     return st;
 }
@@ -87,7 +87,7 @@ def _build(tmp, tag, extra=()):
     L = C.CDLL(so)
     dp = C.POINTER(C.c_double)
     L.walk_host.restype = C.c_int
-    L.walk_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, dp, dp, C.c_int, C.c_int, dp, dp, dp, dp,
+    L.walk_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, dp, dp, C.c_int, C.c_int, dp, dp, dp, dp, dp,
                             C.POINTER(C.c_int)]
     return L
 
@@ -95,6 +95,16 @@ def _build(tmp, tag, extra=()):
 @pytest.fixture(scope="module")
 def walk_lib(tmp_path_factory):
     return _build(str(tmp_path_factory.mktemp("walk")), "guard")
+
+
+def _quad():
+    """400 * pinv(A) for the basis [1, i, j, i^2, ij, j^2] on {-1..2}^2 (Optim.cpp:169-174; capi.cu quad_matrix)"""
+    ii, jj = np.mgrid[-1:3, -1:3].astype(float)
+    A = np.stack([np.ones(16), ii.ravel(), jj.ravel(), ii.ravel() ** 2, (ii * jj).ravel(), jj.ravel() ** 2], axis=1)
+    return np.ascontiguousarray(np.round(400. * np.linalg.pinv(A)), dtype=np.float64)
+
+
+QUAD = _quad()
 
 
 def _run(L, o, i, j, abc=None, poison=None, subpx=-1, uv=(0., 0.)):
@@ -105,11 +115,11 @@ def _run(L, o, i, j, abc=None, poison=None, subpx=-1, uv=(0., 0.)):
     res, d, a, n = np.zeros(5), np.zeros(25), np.zeros(16), C.c_int(0)
     st = L.walk_host(fn, o._h, int(i), int(j), abc_a.ctypes.data_as(dp),
                      poison.ctypes.data_as(dp) if poison is not None else None, o.max_shift, subpx,
-                     uv_a.ctypes.data_as(dp), res.ctypes.data_as(dp), d.ctypes.data_as(dp), a.ctypes.data_as(dp), C.byref(n))
+                     QUAD.ctypes.data_as(dp), uv_a.ctypes.data_as(dp), res.ctypes.data_as(dp), d.ctypes.data_as(dp), a.ctypes.data_as(dp), C.byref(n))
     return st, res, d, a, n.value
 
 
-@pytest.mark.parametrize("name", ["df_noisy", "nodf_noisy", "df_clean", "df_subpx0", "df_dxdy", "df_assign_ref", "dfk_clean"])
+@pytest.mark.parametrize("name", ["df_noisy", "nodf_noisy", "df_clean", "df_subpx0", "df_subpx1", "df_dxdy", "df_assign_ref", "dfk_clean"])
 def test_walk_header_reproduces_the_oracle_walk(walk_lib, name):
     c = load_case(name)
     o = port.OracleModel(c["kind"], c["sam"], c["ref"], window_size=c["Nw"], max_shift=c["max_shift"])
