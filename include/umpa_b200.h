@@ -189,6 +189,11 @@ UMPA_API int umpa_set_profiling(umpa_model *m, int enable);
 UMPA_API int umpa_last_stage_ms(umpa_model *m, float *ms, int n);
 /* bytes of device memory currently owned by the handle */
 UMPA_API int64_t umpa_device_bytes(const umpa_model *m);
+/* Freed frame / scratch blocks are cached for the next model (callers build one model per projection; the
+ * reference's constructor is free, UMPA/model.pyx:138-296).  The cache is capped at UMPA_POOL_GB (default: a
+ * quarter of the device memory) and emptied when the library's own cudaMalloc fails; umpa_pool_trim() empties
+ * it on demand (e.g. before another library needs the memory) and returns the bytes released. */
+UMPA_API int64_t umpa_pool_trim(void);
 
 /* Host helpers of the pipelined upload (hoststage.cu), exposed for CPU-side tests: the centring constant of
  * a frame (mean over rows 0, step, 2 step, ...) and the FP64 -> centred FP32 conversion of `rows` rows of W

@@ -51,3 +51,14 @@ def test_live_reference_masked_and_stepped():
     sam = [d["sam"][k][py:py + h, px:px + w].copy() for k, ((py, px), (h, w)) in enumerate(zip(pos, shp))]
     ref = [d["ref"][k][py:py + h, px:px + w].copy() for k, ((py, px), (h, w)) in enumerate(zip(pos, shp))]
     _check("NoDF", sam, ref, "stepped", pos_list=[np.array(q) for q in pos], window_size=2, max_shift=4)
+
+
+def test_hook_test_convolve_against_the_reference():
+    """The product's numpy `test_convolve` hook (model.pyx:94-102 -> Utils.cpp:85-97) against the reference's own."""
+    from umpa_b200 import model as pm
+    rng = np.random.default_rng(5)
+    img = np.ascontiguousarray(rng.random((40, 37)))
+    for Nk in (1, 3, 8):
+        ker = np.ascontiguousarray(rng.random((2 * Nk + 1, 2 * Nk + 1)))
+        for (i, j) in ((Nk, Nk), (20, 18), (40 - Nk - 1, 37 - Nk - 1)):
+            np.testing.assert_allclose(pm.test_convolve(img, i, j, ker), R.test_convolve(img, i, j, ker), rtol=1e-13)

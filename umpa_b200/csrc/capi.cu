@@ -34,12 +34,31 @@ struct PoolBlock { void *p; size_t bytes; int dev; };
 std::mutex g_pool_mu;
 std::vector<PoolBlock> g_pool;
 size_t g_pool_bytes = 0;
+// Cap of the cache: UMPA_POOL_GB, else a quarter of the device memory (so that the caller's own allocator --
+// PyTorch's, another library's -- is not starved by idle blocks); umpa_pool_trim() empties it on demand.
 size_t pool_cap()
 {
-    const char *e = getenv("UMPA_POOL_GB");
-    return (size_t)((e ? atof(e) : 64.) * (double)(1ull << 30));
+    if (const char *e = getenv("UMPA_POOL_GB")) return (size_t)(atof(e) * (double)(1ull << 30));
+    static size_t cap = 0;
+    if (!cap) {
+        size_t fr = 0, tot = 0;
+        cap = cudaMemGetInfo(&fr, &tot) == cudaSuccess && tot ? tot / 4 : (size_t)32 << 30;
+    }
+    return cap;
 }
 }  // namespace
+
+size_t pool_trim()
+{
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    size_t freed = 0;
+    for (auto &b : g_pool) { cudaSetDevice(b.dev); cudaFree(b.p); freed += b.bytes; }
+    cudaSetDevice(cur);
+    g_pool.clear(); g_pool_bytes = 0;
+    return freed;
+}
 
 cudaError_t pool_malloc(void **p, size_t bytes)
 {
@@ -58,9 +77,7 @@ cudaError_t pool_malloc(void **p, size_t bytes)
     cudaError_t e = cudaMalloc(p, bytes);
     if (e != cudaSuccess) {                 // out of memory: drop the cache and retry once
         cudaGetLastError();
-        std::lock_guard<std::mutex> lk(g_pool_mu);
-        for (auto &b : g_pool) cudaFree(b.p);
-        g_pool.clear(); g_pool_bytes = 0;
+        pool_trim();
         e = cudaMalloc(p, bytes);
     }
     return e;
@@ -112,7 +129,11 @@ void pinned_small_give(void *p, bool own)
 int scratch_reserve(umpa_model *m, Scratch &s, size_t bytes)
 {
     if (s.bytes >= bytes && s.p) return UMPA_OK;
-    if (s.p) { pool_free(s.p, s.bytes); m->dev_bytes -= (int64_t)s.bytes; s.p = nullptr; s.bytes = 0; }
+    if (s.p) {
+        // kernels queued earlier (on any stream this model used) may still read the block
+        if (m->last_ev_set) cudaEventSynchronize(m->last_ev);
+        pool_free(s.p, s.bytes); m->dev_bytes -= (int64_t)s.bytes; s.p = nullptr; s.bytes = 0;
+    }
     cudaError_t e = pool_malloc(&s.p, bytes);
     if (e != cudaSuccess) {
         umpa_set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
@@ -125,6 +146,35 @@ int scratch_reserve(umpa_model *m, Scratch &s, size_t bytes)
 }
 
 namespace {
+
+// Every entry point that takes a model runs on the model's device, whatever device is current in the calling
+// thread (multi-GPU PyTorch code switches devices freely; __del__ may run under any of them), and restores it.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(const umpa_model *m)
+    {
+        if (m && cudaGetDevice(&prev) == cudaSuccess && prev != m->device) switched = cudaSetDevice(m->device) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
+// All launches of a model share its scratch (tables, aux images, constants, result buffer), so they are ordered:
+// a call first makes its stream(s) wait for the event the previous call recorded on ITS stream, whichever that
+// was -- match_device() on a torch stream followed by match() on the library's own streams, or two
+// match_device() calls on different torch streams, no longer race -- and records its own at the end.
+int order_after_last(umpa_model *m, cudaStream_t st)
+{
+    if (m->last_ev_set) UMPA_CUDA(cudaStreamWaitEvent(st, m->last_ev, 0));
+    return UMPA_OK;
+}
+int record_last(umpa_model *m, cudaStream_t st)
+{
+    if (!m->last_ev) UMPA_CUDA(cudaEventCreateWithFlags(&m->last_ev, cudaEventDisableTiming));
+    UMPA_CUDA(cudaEventRecord(m->last_ev, st));
+    m->last_ev_set = true;
+    return UMPA_OK;
+}
 
 // 400 * (A^T A)^-1 A^T for the quadratic basis [1,i,j,i^2,ij,j^2] on the 4x4 grid {-1..2}^2
 // (i = row).  The entries are integers (UMPA/lib/Optim.cpp:169-174 lists them); they are
@@ -368,7 +418,7 @@ int ensure_resident(umpa_model *m, cudaStream_t st)
             for (int k = 0; k < (int)srcs[a]->size(); k++) {
                 const size_t n = (size_t)m->dim[2 * k] * m->dim[2 * k + 1];
                 cudaError_t e = cudaMemcpyAsync(tmp + m->frame_off[k], (*srcs[a])[k], n * sizeof(float), cudaMemcpyHostToDevice, st);
-                if (e != cudaSuccess) { pool_free(tmp, tmp_bytes); UMPA_CUDA(e); }
+                if (e != cudaSuccess) { cudaStreamSynchronize(st); pool_free(tmp, tmp_bytes); UMPA_CUDA(e); }
             }
             int rc = widen_stack(dsts[a], tmp, m->stack_elems, st);
             if (rc) { cudaStreamSynchronize(st); pool_free(tmp, tmp_bytes); return rc; }
@@ -1010,7 +1060,8 @@ int umpa_create(umpa_model **out, int kind, int Na, const int32_t *dim, const in
 void umpa_destroy(umpa_model *m)
 {
     if (!m) return;
-    cudaDeviceSynchronize();      // blocks go back to the cache: nothing of this model may still be running
+    DeviceGuard dg(m);
+    cudaDeviceSynchronize();      // (the model's device) blocks go back to the cache: nothing of this model may still be running
     free_frames(m);
     for (Scratch *s : {&m->filtA, &m->filtB, &m->auxS, &m->auxR, &m->tabX, &m->tabM, &m->outbuf, &m->maskbad, &m->dirty})
         if (s->p) pool_free(s->p, s->bytes);
@@ -1019,12 +1070,14 @@ void umpa_destroy(umpa_model *m)
     if (m->arena) pool_free(m->arena, m->arena_bytes);
     for (int i = 0; i < 5; i++)
         if (m->ev[i]) cudaEventDestroy(m->ev[i]);
+    if (m->last_ev) cudaEventDestroy(m->last_ev);
     delete m;
 }
 
 // device stacks + pointer tables for a new set of frames (shared by the float64 and float32 entry points)
 static int alloc_frames(umpa_model *m, bool has_mask)
 {
+    if (m->last_ev_set) cudaEventSynchronize(m->last_ev);      // a match still in flight reads the old stacks
     free_frames(m);
     const int Na = m->Na;
     m->frame_off.assign(Na, 0);
@@ -1053,6 +1106,7 @@ int umpa_set_frames(umpa_model *m, const double *const *sam, const double *const
 {
     if (!m || !sam || !ref) { umpa_set_error("umpa_set_frames: NULL argument"); return UMPA_ERR_ARG; }
     if (on_device < 0 || on_device > 2) { umpa_set_error("umpa_set_frames: on_device must be 0, 1 or 2"); return UMPA_ERR_ARG; }
+    DeviceGuard dg(m);
     cudaStream_t st = (cudaStream_t)stream;
     const int Na = m->Na;
     const double *const *srcs[3] = {sam, ref, mask};
@@ -1083,6 +1137,7 @@ int umpa_set_frames(umpa_model *m, const double *const *sam, const double *const
 int umpa_set_frames_f32(umpa_model *m, const float *const *sam, const float *const *ref, const float *const *mask)
 {
     if (!m || !sam || !ref) { umpa_set_error("umpa_set_frames_f32: NULL argument"); return UMPA_ERR_ARG; }
+    DeviceGuard dg(m);
     const int Na = m->Na;
     const float *const *srcs[3] = {sam, ref, mask};
     for (int a = 0; a < 3; a++)
@@ -1101,6 +1156,8 @@ int umpa_set_frames_f32(umpa_model *m, const float *const *sam, const float *con
 int umpa_set_window(umpa_model *m, int Nw, const double *win)
 {
     if (!m || !win) { umpa_set_error("umpa_set_window: NULL argument"); return UMPA_ERR_ARG; }
+    DeviceGuard dg(m);
+    if (m->last_ev_set) cudaEventSynchronize(m->last_ev);      // a match in flight still reads the old window
     return install_window(m, Nw, win);
 }
 
@@ -1135,6 +1192,7 @@ int umpa_match(umpa_model *m, const int32_t roi[6], const double uv0[2], const d
 {
     if (!m || !out) { umpa_set_error("umpa_match: NULL argument"); return UMPA_ERR_ARG; }
     if (!m->frames_set) { umpa_set_error("umpa_match: frames were not set"); return UMPA_ERR_STATE; }
+    DeviceGuard dg(m);
     cudaStream_t st = (cudaStream_t)stream;
     RoiView v;
     int rc = make_roi(m, roi, uv0, &v);
@@ -1145,7 +1203,10 @@ int umpa_match(umpa_model *m, const int32_t roi[6], const double uv0[2], const d
     if ((rc = check_roi_bounds(m, v))) return rc;
     v.abc = abc; v.cover = cover; v.cover_threshold = cover_threshold;
     if (m->kind == UMPA_DFKERNEL && !abc) { umpa_set_error("abc array has to be provided"); return UMPA_ERR_ARG; }   // model.pyx:973-974
-    return match_view(m, v, *out, st);
+    if ((rc = order_after_last(m, st))) return rc;
+    rc = match_view(m, v, *out, st);
+    const int rr = record_last(m, st);             // also after a failure: whatever was queued still uses the scratch
+    return rc ? rc : rr;
 }
 
 int umpa_match_host(umpa_model *m, const int32_t roi[6], const double uv0[2], const double *abc, const double *cover,
@@ -1153,6 +1214,7 @@ int umpa_match_host(umpa_model *m, const int32_t roi[6], const double uv0[2], co
 {
     if (!m || !out) { umpa_set_error("umpa_match_host: NULL argument"); return UMPA_ERR_ARG; }
     if (!m->frames_set) { umpa_set_error("umpa_match_host: frames were not set"); return UMPA_ERR_STATE; }
+    DeviceGuard dg(m);
     RoiView v;
     int rc = make_roi(m, roi, uv0, &v);
     if (rc) return rc;
@@ -1162,6 +1224,10 @@ int umpa_match_host(umpa_model *m, const int32_t roi[6], const double uv0[2], co
     if ((rc = check_roi_bounds(m, v))) return rc;
     if (m->kind == UMPA_DFKERNEL && !abc) { umpa_set_error("abc array has to be provided"); return UMPA_ERR_ARG; }
     if ((rc = ensure_streams(m))) return rc;
+    // the library's streams are shared by the models of the process and non-blocking: order them after this
+    // model's last launch (e.g. a match_device() still running on a torch stream)
+    for (cudaStream_t s : {m->s_copy, m->s_comp, m->s_out})
+        if ((rc = order_after_last(m, s))) return rc;
     const size_t n = (size_t)v.N0 * v.N1;
     // one device block: f,T,dx,dy,df | debug_d | debug_a | abc | cover | err,ncalls
     const size_t nd = 5 * n + (out->debug_d ? 25 * n : 0) + (out->debug_a ? 16 * n : 0) + (abc ? 3 * n : 0) + (cover ? n : 0);
@@ -1180,12 +1246,16 @@ int umpa_match_host(umpa_model *m, const int32_t roi[6], const double uv0[2], co
     v.abc = d_abc; v.cover = d_cover; v.cover_threshold = cover_threshold;
 
     // frames still on the host and the table path applies: pipeline upload / kernels / download
-    if (m->host_pending && m->path_opt != UMPA_PATH_LAZY && !getenv("UMPA_NO_STREAMING") && table_eligible(m, v, nullptr))
-        return streamed_match(m, v, d, *out);      // (float32 frames: it picks the plain or the host-staged pipeline)
-
-    if ((rc = match_view(m, v, d, m->s_comp))) return rc;
-    if ((rc = download_outputs(*out, d, n, m->s_comp))) return rc;
+    if (m->host_pending && m->path_opt != UMPA_PATH_LAZY && !getenv("UMPA_NO_STREAMING") && table_eligible(m, v, nullptr)) {
+        rc = streamed_match(m, v, d, *out);        // (float32 frames: it picks the plain or the host-staged pipeline)
+        record_last(m, m->s_comp);                 // (it returns with its three streams drained)
+        return rc;
+    }
+    rc = match_view(m, v, d, m->s_comp);
+    if (!rc) rc = download_outputs(*out, d, n, m->s_comp);
+    record_last(m, m->s_comp);
     cudaError_t e = cudaStreamSynchronize(m->s_comp);
+    if (rc) return rc;
     if (e != cudaSuccess) { umpa_set_error("match failed on the device: %s", cudaGetErrorString(e)); return UMPA_ERR_CUDA; }
     return UMPA_OK;
 }
@@ -1194,6 +1264,8 @@ int umpa_cost(umpa_model *m, int i, int j, int si, int sj, const double abc[3], 
 {
     if (!m || !values) { umpa_set_error("umpa_cost: NULL argument"); return UMPA_ERR_ARG; }
     if (!m->frames_set) { umpa_set_error("umpa_cost: frames were not set"); return UMPA_ERR_STATE; }
+    DeviceGuard dg(m);
+    if (m->last_ev_set) cudaEventSynchronize(m->last_ev);
     if (int rc = ensure_resident(m, nullptr)) return rc;
     return lazy_cost(m, i, j, si, sj, abc, values, status);
 }
@@ -1203,6 +1275,8 @@ int umpa_min(umpa_model *m, int i, int j, double *values, double uv[2], double d
 {
     if (!m || !values || !uv) { umpa_set_error("umpa_min: NULL argument"); return UMPA_ERR_ARG; }
     if (!m->frames_set) { umpa_set_error("umpa_min: frames were not set"); return UMPA_ERR_STATE; }
+    DeviceGuard dg(m);
+    if (m->last_ev_set) cudaEventSynchronize(m->last_ev);
     if (int rc = ensure_resident(m, nullptr)) return rc;
     return lazy_min(m, i, j, values, uv, dbg_d, dbg_a, ncalls, ok);
 }
@@ -1211,14 +1285,20 @@ int umpa_coverage(umpa_model *m, const int32_t roi[6], double *out, int on_devic
 {
     if (!m || !out) { umpa_set_error("umpa_coverage: NULL argument"); return UMPA_ERR_ARG; }
     if (!m->frames_set) { umpa_set_error("umpa_coverage: frames were not set"); return UMPA_ERR_STATE; }
+    DeviceGuard dg(m);
     cudaStream_t st = (cudaStream_t)stream;
     RoiView v;
     int rc = make_roi(m, roi, nullptr, &v);
     if (rc) return rc;
+    if ((rc = order_after_last(m, st))) return rc;
     if (m->masked && (rc = ensure_resident(m, st))) return rc;      // only the masked coverage reads frame data
     if (v.N0 <= 0 || v.N1 <= 0) return UMPA_OK;
     const size_t n = (size_t)v.N0 * v.N1;
-    if (on_device) return coverage_map(m, v, out, st);
+    if (on_device) {
+        rc = coverage_map(m, v, out, st);
+        record_last(m, st);
+        return rc;
+    }
     double *d = nullptr;
     UMPA_CUDA(cudaMalloc(&d, n * sizeof(double)));
     rc = coverage_map(m, v, d, st);
@@ -1260,6 +1340,7 @@ int umpa_last_stage_ms(umpa_model *m, float *ms, int n)
 {
     if (!m || !ms) { umpa_set_error("NULL argument"); return UMPA_ERR_ARG; }
     if (!m->ev_valid) return 0;
+    DeviceGuard dg(m);
     if (cudaEventSynchronize(m->ev[4]) != cudaSuccess) return 0;
     int k = 0;
     for (; k < 4 && k < n; k++) cudaEventElapsedTime(&ms[k], m->ev[k], m->ev[k + 1]);
@@ -1267,6 +1348,8 @@ int umpa_last_stage_ms(umpa_model *m, float *ms, int n)
 }
 
 int64_t umpa_device_bytes(const umpa_model *m) { return m ? m->dev_bytes : 0; }
+
+int64_t umpa_pool_trim(void) { return (int64_t)pool_trim(); }
 
 }  // extern "C"
 

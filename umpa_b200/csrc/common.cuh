@@ -125,6 +125,9 @@ struct umpa_model {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
     int64_t dev_bytes = 0;
+    // recorded on the stream of the model's last launch; the next call waits for it (capi.cu: order_after_last)
+    cudaEvent_t last_ev = nullptr;
+    bool last_ev_set = false;
 };
 
 int scratch_reserve(umpa_model *m, Scratch &s, size_t bytes);
@@ -132,6 +135,7 @@ cudaError_t pool_malloc(void **p, size_t bytes);   // cached cudaMalloc / cudaFr
 void *pinned_small_take(size_t bytes, bool *own);  // pinned host memory for constants on their way to the device
 void pinned_small_give(void *p, bool own);
 void pool_free(void *p, size_t bytes);
+size_t pool_trim();                                // frees every cached block; returns the bytes released
 
 // implemented in lazy_path.cu
 int lazy_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st);

@@ -135,12 +135,27 @@ __global__ void center_inplace(const double *means64, int Na, int H, int W, int 
 
 // ------------------------------------------------------------------ moments
 
+// The aux images hold, per raw pixel q, everything of a cost evaluation that depends on ONE window position
+// only, already rebuilt from the centred FP32 sums in FP64 (T3 = w (*) sum R'^2, P3 = sum c_k a'_k,
+// U = sum d_k a'_k, M2 = sum a'_k^2, and T1, P1, V for the sample):
+//     t3 = T3 + 2 P3 + sw sum c_k^2                  t1 = T1 + 2 P1 + sw sum d_k^2
+//     t2 = M2/sw^2 + 2 P3/sw + sum c_k^2             (sum_k m_k^2, Model.cpp:770)
+//     rden = 1/(t2 t3 - (sw t2)^2)  (DF: the determinant of the 2x2 solve, Model.cpp:849)  or 1/t3 (NoDF)
+//     linq = U + sw sum c_k d_k
+// so that an evaluation is one 32-byte gather + the two table entries, ~15 FP64 operations and no division.
+struct __align__(16) AuxS { double t1, V; };
+struct __align__(32) AuxR { double t3, t2, rden, linq; };
+
 struct MomentsParams {
     const float *sam, *ref;      // centred stacks [Na][H][pitch]
     float *fa, *fb;              // filtered stacks a_k (from ref), b_k (from sam); nullptr for NoDF
-    float4 *auxS, *auxR;         // [H][pitch]
+    AuxS *auxS;                  // [H][pitch]: what a cost evaluation needs of the sample stack at a pixel
+    AuxR *auxR;                  // [H][pitch]: ... and of the reference stack (see the structs above)
     const float *g;              // 1-D window factor, K
     const float *mean_s, *mean_r;
+    const double *consts;        // device: sum_k c_k d_k, sum_k c_k^2, sum_k d_k^2
+    double sw, inv_sw, inv_sw2;  // sum of the (FP32) window and its inverses
+    int kind;
     int Na, Nw, H, W, pitch;
     int ty0, tx0;                // first tile (in tile units) of the bounding box
 };
@@ -295,10 +310,17 @@ moments_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_constant__
     col_pass(0, t3);
     col_pass(1, t1);
     if (inside) {
+        const double cd = __ldg(p.consts), cc = __ldg(p.consts + 1), dd = __ldg(p.consts + 2);
 #pragma unroll
         for (int x = 0; x < 4; x++) {
-            p.auxR[opix + x] = make_float4(t3[x], p3[x], uu[x], m2[x]);
-            p.auxS[opix + x] = make_float4(t1[x], p1[x], vv[x], 0.f);
+            AuxR r;
+            r.t3 = (double)t3[x] + 2. * (double)p3[x] + p.sw * cc;
+            r.t2 = (double)m2[x] * p.inv_sw2 + 2. * (double)p3[x] * p.inv_sw + cc;
+            const double t6 = p.sw * r.t2;
+            r.rden = 1. / (p.kind == UMPA_DF ? r.t2 * r.t3 - t6 * t6 : r.t3);
+            r.linq = (double)uu[x] + p.sw * cd;
+            p.auxR[opix + x] = r;
+            p.auxS[opix + x] = AuxS{(double)t1[x] + 2. * (double)p1[x] + p.sw * dd, (double)vv[x]};
         }
     }
 }
@@ -313,121 +335,96 @@ template <int NW> size_t moments_smem()
 
 struct WalkParams {
     const float *tabX, *tabM;       // cross / mean tables; tabM nullptr for NoDF
-    const float4 *auxS, *auxR;      // [H][pitch], raw coordinates
+    const AuxS *auxS;               // [H][pitch], raw coordinates
+    const AuxR *auxR;
     int pitch;
     int rowsX, colsX, rowsM, colsM; // padded plane geometry of the two tables
     unsigned planeX, planeM;        // rows * cols
     int oy, ox;                     // raw coords of output pixel (0,0) of the dense region
     int dxX, dxM;                   // column of that pixel inside the cross / mean table (TMA alignment shift)
-    int kind, Na, max_shift, subpx;
+    int Na, max_shift, subpx;
     double sw;                      // sum of window
     const double *consts;           // device: sum_k c_k d_k, c_k^2, d_k^2
-    double inv_sw, inv_sw2, inv_Na;
+    double inv_sw, inv_Na;
     const double *quad;
     const float *ktab;              // DFKernel: pixel-major rows [t5c(S^2) | t3c(S^2) | sigma-1] (kernel_path.cu)
     int kstride;                    // floats per row
     double swk;                     // exact sum of the FP32 2-D window kernel_path.cu applies
 };
 
+// One cost evaluation from the tables (the walk's functor).
 // RS = reference_shift (assign_coordinates = 'ref', Model.cpp:408-421 / 688-701): the SAMPLE window
 // moves by -s and the reference window stays at the pixel.  The tables are the same sums with the
 // roles of the stacks swapped (table_match feeds the sample stack as the moving operand) and the shift
-// negated; in the assembly the reference-derived aux image is then read at the pixel and the
-// sample-derived one at p - s.
-template <bool RS>
+// negated; in the assembly the reference's aux record is then read at the pixel and the sample's at p - s.
+// KIND is a template parameter so that no evaluation tests the model kind.
+template <bool RS, int KIND>
 struct TableEval {
     const WalkParams &w;
-    int ty, tx;                     // table coords of this pixel
-    double c0, c1, c2;              // pixel-only terms: (t1, V, -) or, RS, (t3, U, t2)
-    const float *krow;              // DFKernel: this pixel's table row
-    double cd, cc, dd;
-    const float4 *pAux;             // moving aux image at this pixel (shift 0)
-    const float *pX, *pM;           // this pixel in plane 0 of the cross / mean table
+    AuxS ps;                        // sample record: at the pixel (!RS) -- or the last one fetched at p - s (RS)
+    AuxR pr;                        // reference record: at the pixel (RS) -- or the last one fetched at p + s (!RS)
+    const AuxS *pS;                 // RS: the sample's aux image at this pixel (shift 0)
+    const AuxR *pR;                 // !RS: the reference's aux image at this pixel
+    const float *pX, *pM;           // this pixel in plane 0 of the cross / mean table (DFKernel: pX = its table row)
+    double sig, k5, k3;             // DFKernel: sigma, sigma swk sum c_k d_k, sigma^2 swk sum c_k^2
 
-    struct Raw { float4 aux; float x, m, sg; }; // what one evaluation reads: three independent gathers (+ sigma-1, DFKernel)
-
-    __device__ int operator()(int si, int sj, double &cst, FitArgs &args) const
+    __device__ static int out_of_bounds(int si, int sj, int ms)      // error_status bits of Model.cpp:654-681 (cold path)
     {
-        const int se = status(si, sj);
-        if (se != UMPA_ST_OK) return se;
-        cst = cost(fetch(si, sj), args);
-        return UMPA_ST_OK;
-    }
-
-    __device__ int status(int si, int sj) const
-    {
-        const int ms = w.max_shift;
         if (si <= -ms || si >= ms) return UMPA_ST_BOUND;
         if (sj <= -ms) return UMPA_ST_BOUND | UMPA_ST_DIM;
-        if (sj >= ms) return UMPA_ST_BOUND | UMPA_ST_DIM | UMPA_ST_POS;
-        return UMPA_ST_OK;
+        return UMPA_ST_BOUND | UMPA_ST_DIM | UMPA_ST_POS;
     }
 
-    // the three gathers of one evaluation (shift must be in bounds)
-    __device__ Raw fetch(int si, int sj) const
+    __device__ __forceinline__ int operator()(int si, int sj, double &cst, FitArgs &args)
     {
         const int ms = w.max_shift, S = 2 * ms - 1;
         const int ti = RS ? -si : si, tj = RS ? -sj : sj;
-        const unsigned sidx = (unsigned)((ti + ms - 1) * S + (tj + ms - 1));
-        Raw r;
-        r.sg = 0.f;
-        if (w.kind == UMPA_DFKERNEL) {
-            r.x = __ldg(krow + sidx);
-            r.m = __ldg(krow + S * S + sidx);
-            r.sg = __ldg(krow + 2 * S * S);
-            r.aux = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (RS) r.aux = __ldg(pAux + (ti * w.pitch + tj));          // the sample's (T1, P1, V, -) at p - s
-            return r;
-        }
-        // per-pixel base pointers + one 32x32->64 multiply per table (plane sizes fit 32 bits)
-        r.aux = __ldg(pAux + (ti * w.pitch + tj));
-        r.x = __ldg(pX + (size_t)sidx * w.planeX);
-        r.m = w.kind == UMPA_DF ? __ldg(pM + (size_t)sidx * w.planeM) : 0.f;
-        return r;
-    }
-
-    __device__ double cost(const Raw &r, FitArgs &args) const
-    {
-        if (w.kind == UMPA_DFKERNEL) {
+        const unsigned a = (unsigned)(ti + ms - 1), b = (unsigned)(tj + ms - 1);
+        if (a >= (unsigned)S || b >= (unsigned)S) return out_of_bounds(si, sj, ms);
+        const unsigned sidx = a * (unsigned)S + b;
+        const int q = ti * w.pitch + tj;           // the moving window's pixel relative to this one
+        if (KIND == UMPA_DFKERNEL) {
             // t3 = sum w B^2, t5 = sum w B S with B = k_p (*) R (Model.cpp:1076-1099), rebuilt from the
-            // centred FP32 sums: B = B' + sigma c_k.  RS: t1 and the sample's V come from the sample's aux
-            // image at p - s (r.aux), not from the pixel.
-            const double sig = 1. + (double)r.sg;
-            const double V = RS ? (double)r.aux.z : c1;
-            const double t1 = RS ? (double)r.aux.x + 2. * (double)r.aux.y + w.sw * dd : c0;
-            const double t5 = (double)r.x + sig * (V + w.swk * cd);
-            const double t3 = (double)r.m + sig * sig * w.swk * cc;
+            // centred FP32 sums: B = B' + sigma c_k.  RS: t1 and the sample's V belong to p - s.
+            const float x = __ldg(pX + sidx), m = __ldg(pX + S * S + sidx);
+            if (RS) {
+                const double2 v = __ldg(reinterpret_cast<const double2 *>(pS + q));
+                ps.t1 = v.x; ps.V = v.y;
+            }
+            const double t5 = (double)x + sig * ps.V + k5;
+            const double t3 = (double)m + k3;
             args.t = t5 / t3;
-            return (t1 - t5 * args.t) * w.inv_Na;
+            cst = (ps.t1 - t5 * args.t) * w.inv_Na;
+            return UMPA_ST_OK;
         }
-        const float4 mv = r.aux;
-        double t1, t2, t3, lin;
-        if (!RS) {                  // mv = (T3, P3, U, M2) of the reference at p + s
-            t1 = c0;
-            t3 = (double)mv.x + 2. * (double)mv.y + w.sw * cc;
-            lin = (double)mv.z + c1 + w.sw * cd;
-            t2 = (double)mv.w * w.inv_sw2 + 2. * (double)mv.y * w.inv_sw + cc;
-        } else {                    // mv = (T1, P1, V, -) of the sample at p - s
-            t1 = (double)mv.x + 2. * (double)mv.y + w.sw * dd;
-            t3 = c0;
-            lin = c1 + (double)mv.z + w.sw * cd;
-            t2 = c2;
+        // the gathers of one evaluation: one aux record + one entry per table (plane sizes fit 32 bits)
+        const float x = __ldg(pX + (size_t)sidx * w.planeX);
+        const float m = KIND == UMPA_DF ? __ldg(pM + (size_t)sidx * w.planeM) : 0.f;
+        if (RS) {
+            const double2 v = __ldg(reinterpret_cast<const double2 *>(pS + q));
+            ps.t1 = v.x; ps.V = v.y;
+        } else {
+            const double2 v0 = __ldg(reinterpret_cast<const double2 *>(pR + q));
+            const double2 v1 = __ldg(reinterpret_cast<const double2 *>(pR + q) + 1);
+            pr.t3 = v0.x; pr.t2 = v0.y; pr.rden = v1.x; pr.linq = v1.y;
         }
-        const double t5 = (double)r.x + lin;
-        if (w.kind == UMPA_DF) {
-            const double t6 = w.sw * t2;
-            const double t4 = (double)r.m * w.inv_sw + lin;
-            const double rden = 1. / (t2 * t3 - t6 * t6);
-            const double Kc = (t2 * t5 - t4 * t6) * rden;
-            const double beta = (t3 * t4 - t5 * t6) * rden;
+        const double lin = pr.linq + ps.V;         // U + V + sw sum c_k d_k
+        const double t5 = (double)x + lin;
+        if (KIND == UMPA_DF) {
+            const double t6 = w.sw * pr.t2;
+            const double t4 = (double)m * w.inv_sw + lin;
+            const double Kc = (pr.t2 * t5 - t4 * t6) * pr.rden;
+            const double beta = (pr.t3 * t4 - t5 * t6) * pr.rden;
             args.t = beta + Kc;
-            args.v = Kc;                  // dark field = Kc / t, divided once at the end
+            args.v = Kc;                           // dark field = Kc / t, divided once at the end
             // the reference's residual t1 + b^2 t2 + K^2 t3 - 2 b t4 - 2 K t5 + 2 b K t6 (Model.cpp:855-858) at the
             // solution of the normal equations (b t2 + K t6 = t4, b t6 + K t3 = t5) is t1 - b t4 - K t5
-            return (t1 - beta * t4 - Kc * t5) * w.inv_Na;
+            cst = (ps.t1 - beta * t4 - Kc * t5) * w.inv_Na;
+            return UMPA_ST_OK;
         }
-        args.t = t5 / t3;
-        return (t1 - t5 * args.t) * w.inv_Na;
+        args.t = t5 * pr.rden;                     // NoDF: rden = 1 / t3
+        cst = (ps.t1 - t5 * args.t) * w.inv_Na;
+        return UMPA_ST_OK;
     }
 };
 
@@ -443,7 +440,7 @@ struct SharedGrid {
     __device__ __forceinline__ double &operator[](int n) const { return base[n * WALK_NT]; }
 };
 
-template <bool RS>
+template <bool RS, int KIND>
 __global__ void __launch_bounds__(WALK_NT, WALK_MINB) table_walk_kernel(WalkParams w, RoiView roi, umpa_outputs out)
 {
     __shared__ double d_sm[25][WALK_NT];
@@ -454,24 +451,49 @@ __global__ void __launch_bounds__(WALK_NT, WALK_MINB) table_walk_kernel(WalkPara
     if (roi.cover && roi.cover[n] < roi.cover_threshold) return;
     if (roi.dirty && (roi.dirty[n] != 0) != (roi.dirty_want != 0)) return;   // mixed path: the lazy kernel owns this pixel
     const int ty = roi.step0 * xi, tx = roi.step1 * xj;
-    const float4 s = __ldg((RS ? w.auxR : w.auxS) + (size_t)(w.oy + ty) * w.pitch + (w.ox + tx));
-    const double cd = __ldg(w.consts), cc = __ldg(w.consts + 1), dd = __ldg(w.consts + 2);
-    // pixel-only terms: (t1, V) from the sample's aux image, or (RS) (t3, U, t2) from the reference's
-    TableEval<RS> eval{w, ty, tx, (double)s.x + 2. * (double)s.y + w.sw * (RS ? cc : dd), (double)s.z,
-                       RS ? (double)s.w * w.inv_sw2 + 2. * (double)s.y * w.inv_sw + cc : 0.,
-                       w.ktab ? w.ktab + n * (size_t)w.kstride : nullptr, cd, cc, dd,
-                       (RS ? w.auxS : w.auxR) + (size_t)(w.oy + ty) * w.pitch + (w.ox + tx),
-                       w.tabX + (size_t)ty * w.colsX + tx + w.dxX,
-                       w.tabM ? w.tabM + (size_t)ty * w.colsM + tx + w.dxM : nullptr};
+    const size_t pix = (size_t)(w.oy + ty) * w.pitch + (w.ox + tx);
+    TableEval<RS, KIND> eval{w};
+    eval.pS = w.auxS + pix; eval.pR = w.auxR + pix;
+    if (RS) {
+        const double2 v0 = __ldg(reinterpret_cast<const double2 *>(eval.pR));
+        const double2 v1 = __ldg(reinterpret_cast<const double2 *>(eval.pR) + 1);
+        eval.pr = AuxR{v0.x, v0.y, v1.x, v1.y};
+        eval.ps = AuxS{0., 0.};
+    } else {
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(eval.pS));
+        eval.ps = AuxS{v.x, v.y};
+        eval.pr = AuxR{0., 0., 0., 0.};
+    }
+    eval.sig = eval.k5 = eval.k3 = 0.;
+    if (KIND == UMPA_DFKERNEL) {
+        const int S = 2 * w.max_shift - 1;
+        eval.pX = w.ktab + n * (size_t)w.kstride;
+        eval.pM = nullptr;
+        eval.sig = 1. + (double)__ldg(eval.pX + 2 * S * S);
+        eval.k5 = eval.sig * w.swk * __ldg(w.consts);
+        eval.k3 = eval.sig * eval.sig * w.swk * __ldg(w.consts + 1);
+    } else {
+        eval.pX = w.tabX + (size_t)ty * w.colsX + tx + w.dxX;
+        eval.pM = KIND == UMPA_DF ? w.tabM + (size_t)ty * w.colsM + tx + w.dxM : nullptr;
+    }
     FitArgs args{0., 0.};
     SharedGrid d{&d_sm[0][threadIdx.x]};
     double a[16], uv[2] = {roi.uv0[0], roi.uv0[1]}, f = 0.;
     int ncalls;
+    WalkCache wc;
 #pragma unroll
     for (int t = 0; t < 16; t++) a[t] = 0.;
-    const int st = walk_minimise(eval, w.subpx, w.quad, args, f, uv, d, a, ncalls);
-    if (w.kind == UMPA_DF && args.t != 0.) args.v = args.v / args.t;
-    store_pixel(out, n, w.kind, st, f, args, uv, d, a, ncalls, true);
+    const int st = walk_minimise(eval, w.subpx, w.quad, args, f, uv, d, a, ncalls, wc);
+    if (KIND == UMPA_DF && args.t != 0.) args.v = args.v / args.t;
+    store_pixel(out, n, KIND, st, f, args, uv, d, wc, a, ncalls, true);
+}
+
+template <bool RS>
+void launch_walk(int kind, dim3 grid, const WalkParams &w, const RoiView &roi, const umpa_outputs &out, cudaStream_t st)
+{
+    if (kind == UMPA_DF) table_walk_kernel<RS, UMPA_DF><<<grid, WALK_NT, 0, st>>>(w, roi, out);
+    else if (kind == UMPA_NODF) table_walk_kernel<RS, UMPA_NODF><<<grid, WALK_NT, 0, st>>>(w, roi, out);
+    else table_walk_kernel<RS, UMPA_DFKERNEL><<<grid, WALK_NT, 0, st>>>(w, roi, out);
 }
 
 // ------------------------------------------------------------------ host side
@@ -771,8 +793,8 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         }
     }
     const size_t img = (size_t)H * pitch;
-    if ((rc = scratch_reserve(m, m->auxS, img * sizeof(float4)))) return rc;
-    if ((rc = scratch_reserve(m, m->auxR, img * sizeof(float4)))) return rc;
+    if ((rc = scratch_reserve(m, m->auxS, img * sizeof(AuxS)))) return rc;
+    if ((rc = scratch_reserve(m, m->auxR, img * sizeof(AuxR)))) return rc;
     if (df) {
         if ((rc = scratch_reserve(m, m->filtA, (size_t)Na * img * sizeof(float)))) return rc;
         if ((rc = scratch_reserve(m, m->filtB, (size_t)Na * img * sizeof(float)))) return rc;
@@ -787,8 +809,10 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         MomentsParams mp{};
         mp.sam = m->d_sam32; mp.ref = m->d_ref32;
         mp.fa = df ? (float *)m->filtA.p : nullptr; mp.fb = df ? (float *)m->filtB.p : nullptr;
-        mp.auxS = (float4 *)m->auxS.p; mp.auxR = (float4 *)m->auxR.p;
+        mp.auxS = (AuxS *)m->auxS.p; mp.auxR = (AuxR *)m->auxR.p;
         mp.g = m->d_g; mp.mean_s = m->d_mean_s; mp.mean_r = m->d_mean_r;
+        mp.consts = m->d_consts; mp.kind = m->kind;
+        mp.sw = m->win_sum; mp.inv_sw = 1. / mp.sw; mp.inv_sw2 = 1. / (mp.sw * mp.sw);
         mp.Na = Na; mp.Nw = m->Nw; mp.H = H; mp.W = m->W; mp.pitch = pitch;
         const int ylo = std::max(0, oy - HS), yhi = std::min(H, oy + rows + HS);
         const int xlo = std::max(0, ox - HS), xhi = std::min(m->W, ox + cols + HS);
@@ -848,17 +872,17 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
                 for (int b = 0; b < m->K; b++) swk += (double)((float)m->g[a] * (float)m->g[b]);
             w.swk = swk;
         }
-        w.auxS = (const float4 *)m->auxS.p; w.auxR = (const float4 *)m->auxR.p;
+        w.auxS = (const AuxS *)m->auxS.p; w.auxR = (const AuxR *)m->auxR.p;
         w.pitch = pitch; w.rowsX = px.rows_p; w.colsX = px.cols_p; w.rowsM = pm.rows_p; w.colsM = pm.cols_p;
         w.planeX = (unsigned)px.rows_p * (unsigned)px.cols_p; w.planeM = (unsigned)pm.rows_p * (unsigned)pm.cols_p;
         w.oy = oy; w.ox = ox; w.dxX = dxX; w.dxM = dxM;
-        w.kind = m->kind; w.Na = Na; w.max_shift = m->max_shift; w.subpx = m->subpx;
+        w.Na = Na; w.max_shift = m->max_shift; w.subpx = m->subpx;
         w.sw = m->win_sum; w.quad = m->d_quad;
-        w.inv_sw = 1. / w.sw; w.inv_sw2 = 1. / (w.sw * w.sw); w.inv_Na = 1. / (double)Na;
+        w.inv_sw = 1. / w.sw; w.inv_Na = 1. / (double)Na;
         w.consts = m->d_consts;
         dim3 grid((roi.N1 + WALK_NT - 1) / WALK_NT, roi.N0);
-        if (m->refshift) table_walk_kernel<true><<<grid, WALK_NT, 0, st>>>(w, roi, out);
-        else table_walk_kernel<false><<<grid, WALK_NT, 0, st>>>(w, roi, out);
+        if (m->refshift) launch_walk<true>(m->kind, grid, w, roi, out, st);
+        else launch_walk<false>(m->kind, grid, w, roi, out, st);
         UMPA_CUDA(cudaGetLastError());
         m->last_launches++;
         if ((rc = stage_check("walk", st))) return rc;

@@ -99,10 +99,15 @@ __device__ inline double subpixel_quadratic(const double *__restrict__ c_quad, c
 }
 
 // ---- the walk --------------------------------------------------------------------------
-// d: 5x5 cache of costs centred on the current integer shift (row-major, centre 12, -1 =
-// not evaluated).  axis 0 scans the column shift, axis 1 the row shift.  `keep` is the
-// reference's args_copy: the fit parameters of the best shift seen so far -- deliberately
-// NOT refreshed on a restart (Optim.cpp:364-377), which the reference's outputs depend on.
+// The reference keeps d, a 5x5 cache of costs centred on the current integer shift (row-major, centre 12,
+// -1 = not evaluated), and physically shifts it by one row / column on every step.  Here the cache is a
+// RING: the 25 storage cells are addressed modulo 5 from an origin (b0, b1) that moves with the centre, and
+// which cells hold an evaluated cost is a 25-bit register mask in the reference's (logical) order -- a step
+// rotates the mask and moves the origin, nothing is copied and nothing has to be initialised.
+// walk_cache_get() reads the cache the way the reference would have left it.
+// axis 0 scans the column shift, axis 1 the row shift.  `keep` is the reference's args_copy: the fit
+// parameters of the best shift seen so far -- deliberately NOT refreshed on a restart (Optim.cpp:364-377),
+// which the reference's outputs depend on.
 //
 // The reference calls the cost function from four places (centre, minus neighbour, plus
 // neighbour, 4x4 fill).  On a GPU that would serialise the lanes of a warp that happen to be
@@ -113,143 +118,128 @@ __device__ inline double subpixel_quadratic(const double *__restrict__ c_quad, c
 // is exactly the reference's.
 // Eval: int operator()(int si, int sj, double &cost, FitArgs &args) -> error_status bits.
 // Grid: anything indexable by [int] yielding double& (a local array, or a shared-memory column).
+struct WalkCache {
+    unsigned known;                 // bit 5 r + c: logical entry (r, c) holds an evaluated cost
+    int b0, b1;                     // storage row / column of logical row / column 0
+};
+
+__device__ __forceinline__ int walk_cell(int b0, int b1, int r, int c)
+{
+    int pr = b0 + r, pc = b1 + c;
+    pr = pr >= 5 ? pr - 5 : pr;
+    pc = pc >= 5 ? pc - 5 : pc;
+    return 5 * pr + pc;
+}
+
+// logical entry n (0..24) of the cache as the reference holds it: the cost, or -1 when not evaluated
+template <class Grid>
+__device__ __forceinline__ double walk_cache_get(Grid d, const WalkCache &wc, int n)
+{
+    const int r = (n * 13) >> 6;                   // n / 5 for n < 64
+    return ((wc.known >> n) & 1u) ? d[walk_cell(wc.b0, wc.b1, r, n - 5 * r)] : -1.;
+}
+
 template <class Eval, class Grid>
 __device__ inline int walk_minimise(Eval &eval, int subpx, const double *quad, FitArgs &args, double &out,
-                                    double *uv, Grid d, double *a, int &ncalls)
+                                    double *uv, Grid d, double *a, int &ncalls, WalkCache &wc)
 {
-    enum { P_INIT, P_TOP, P_LO, P_HI, P_DECIDE, P_FILL, P_DONE };
+    enum { R_CENTRE, R_LO, R_HI, R_FILL };         // what the pending evaluation is for
     const double tol = 1e-8;                       // absolute, Optim.cpp:243
     constexpr unsigned COL0 = 0x108421u, COL4 = 0x1084210u, ALL = 0x1ffffffu;
     int settled0 = 0, settled1 = 0, axis = 0, st = UMPA_ST_OK;
-    int phase = P_INIT, ip = 0, jp = 0, idle = 0;
-    bool up_m = false, up_p = false, skip_limit = false, finished = false;
-    // which entries of d hold an evaluated cost (the reference tests d < -0.5; a register bit is cheaper
-    // than a shared-memory load and lets the 4x4 fill find its next missing entry with one ffs)
+    int ip = 0, jp = 0, idle = 0, b0 = 0, b1 = 0;
+    bool fill = false, skip_limit = false, finished = false;
     unsigned known = 0;
     FitArgs keep = args;
-#pragma unroll
-    for (int n = 0; n < 25; n++) d[n] = -1.;
     ncalls = 0;
     int c0 = (int)round(uv[0]), c1 = (int)round(uv[1]);
+    int req = R_CENTRE, sr = 2, sc = 2;            // the pending evaluation: logical cell (sr, sc) = shift (c0 + sr - 2, c1 + sc - 2)
+    double dc = 0.;                                // d[12], the cost at the current centre
 
     while (true) {
-        // ---- advance this lane's state until it needs a cost value (or is done) ----
-        bool want = false;
-        int e0 = 0, e1 = 0, slot = 12;
-        while (!want && phase != P_DONE) {
-            switch (phase) {
-            case P_INIT:
-                want = true; e0 = c0; e1 = c1; slot = 12;
-                break;
-            case P_TOP:
-                if (!skip_limit && ncalls >= UMPA_MAX_CALLS) { st = 0; phase = P_DONE; }   // Optim.cpp:267,477
-                // Not in the reference: with a NaN cost next to finite ones (a non-finite input pixel) its loop can step
-                // back and forth between two evaluated shifts for ever -- MAX_CALLS only counts evaluations.  Finite
-                // costs never revisit (a few visits here between two evaluations at most), so this changes no result;
-                // it turns a hung GPU into a failed pixel (err = 0).
-                else if (++idle > 16) { st = 0; phase = P_DONE; }
-                else { skip_limit = false; phase = P_LO; }
-                break;
-            case P_LO:
-                slot = axis ? 7 : 11;
-                if (!((known >> slot) & 1u)) { want = true; e0 = c0 - axis; e1 = c1 - (1 - axis); }
-                else { up_m = d[slot] > d[12] + tol; phase = P_HI; }
-                break;
-            case P_HI:
-                slot = axis ? 17 : 13;
-                if (!((known >> slot) & 1u)) { want = true; e0 = c0 + axis; e1 = c1 + (1 - axis); }
-                else { up_p = d[slot] > d[12] - tol; phase = P_DECIDE; }
-                break;
-            case P_DECIDE: {
-                const int lo = axis ? 7 : 11, hi = axis ? 17 : 13;
-                if (up_m && up_p) {
-                    const int dir = d[lo] < d[hi] ? -1 : 1;
-                    if (axis) settled1 = dir; else settled0 = dir;
-                    if ((axis ? settled0 : settled1) == 0) { axis = 1 - axis; phase = P_TOP; }
-                    else {
-                        ip = d[17] < d[7] ? 1 : 0;
-                        jp = d[13] < d[11] ? 1 : 0;
-                        phase = P_FILL;
-                    }
-                } else {
-                    uv[0] = c0; uv[1] = c1;        // best so far, Optim.cpp:421-423
-                    out = d[12];
-                    bool plus = up_m;
-                    if (!up_p && !up_m) plus = d[hi] < d[lo];      // local maximum: go downhill
-                    if (plus) {
-                        if (axis) {
-                            c0 += 1;
-                            for (int n = 0; n < 20; n++) d[n] = d[n + 5];
-                            for (int n = 20; n < 25; n++) d[n] = -1.;
-                            known >>= 5;
-                        } else {
-                            c1 += 1;
-                            for (int n = 0; n < 24; n++) d[n] = d[n + 1];
-                            for (int r = 0; r < 5; r++) d[5 * r + 4] = -1.;
-                            known = (known >> 1) & ~COL4;
-                        }
-                    } else {
-                        if (axis) {
-                            c0 -= 1;
-                            for (int n = 24; n >= 5; n--) d[n] = d[n - 5];
-                            for (int n = 0; n < 5; n++) d[n] = -1.;
-                            known = (known << 5) & ALL;
-                        } else {
-                            c1 -= 1;
-                            for (int n = 24; n >= 1; n--) d[n] = d[n - 1];
-                            for (int r = 0; r < 5; r++) d[5 * r] = -1.;
-                            known = (known << 1) & ~COL0 & ALL;
-                        }
-                    }
-                    if (axis) settled0 = 0; else settled1 = 0;
-                    phase = P_TOP;
-                }
-                break;
-            }
-            default: {                             // P_FILL: next missing entry of the 4x4 block (row-major)
-                const unsigned block = 0x7bdefu << (5 * ip + jp);       // 4 rows of 4 bits, 5 apart
-                const unsigned pending = block & ~known;
-                if (pending) {
-                    slot = __ffs(pending) - 1;
-                    want = true; e0 = c0 + slot / 5 - 2; e1 = c1 + slot % 5 - 2;
-                } else { finished = true; phase = P_DONE; }
-                break;
-            }
-            }
-        }
-        if (!want) break;
-
         // ---- the one evaluation site ----
         double v;
-        const int se = eval(e0, e1, v, args);
+        const int se = eval(c0 + sr - 2, c1 + sc - 2, v, args);
         ncalls++;
         idle = 0;
         if (se != UMPA_ST_OK) { st = se; break; }  // bound error: return at once (Optim.cpp:264,291,324,359)
 
         // ---- file the result ----
-        d[slot] = v;
-        known |= 1u << slot;
-        if (phase == P_INIT) { keep = args; phase = P_TOP; }
-        else if (phase == P_LO) { up_m = v > d[12] + tol; if (!up_m) keep = args; phase = P_HI; }
-        else if (phase == P_HI) { up_p = v > d[12] - tol; if (!up_p) keep = args; phase = P_DECIDE; }
-        else if (v < d[12]) {                      // P_FILL, lower value off-axis: hard restart there
-            c0 = e0; c1 = e1;
-#pragma unroll
-            for (int t = 0; t < 25; t++) d[t] = -1.;
-            d[12] = v;
-            known = 1u << 12;
+        if (req == R_FILL && v < dc) {             // 4x4 fill, lower value off-axis: hard restart there (Optim.cpp:364-377)
+            c0 += sr - 2; c1 += sc - 2;
+            sr = sc = 2;
+            known = 0;
             args = keep;
             settled0 = settled1 = 0;
             skip_limit = true;
-            phase = P_TOP;
+            fill = false;
+            req = R_CENTRE;                        // (keep is NOT refreshed: see above)
+        } else if (req == R_CENTRE || (req == R_LO && !(v > dc + tol)) || (req == R_HI && !(v > dc - tol)))
+            keep = args;                           // Optim.cpp:262, 294-296, 325-327
+        if (sr == 2 && sc == 2) dc = v;
+        d[walk_cell(b0, b1, sr, sc)] = v;
+        known |= 1u << (5 * sr + sc);
+
+        // ---- advance this lane until it needs the next cost value (or is done) ----
+        bool done = false;
+        while (true) {
+            if (fill) {                            // next missing entry of the 4x4 block (row-major)
+                const unsigned pending = (0x7bdefu << (5 * ip + jp)) & ~known;    // 4 rows of 4 bits, 5 apart
+                if (!pending) { finished = true; done = true; break; }
+                const int slot = __ffs(pending) - 1;
+                sr = (slot * 13) >> 6;             // slot / 5 for slot < 64
+                sc = slot - 5 * sr;
+                req = R_FILL;
+                break;
+            }
+            // head of the reference's loop (Optim.cpp:267); a restart jumps past the test (goto start)
+            if (!skip_limit && ncalls >= UMPA_MAX_CALLS) { st = 0; done = true; break; }   // Optim.cpp:267,477
+            // Not in the reference: with a NaN cost next to finite ones (a non-finite input pixel) its loop can step
+            // back and forth between two evaluated shifts for ever -- MAX_CALLS only counts evaluations.  Finite
+            // costs never revisit (a few visits here between two evaluations at most), so this changes no result;
+            // it turns a hung GPU into a failed pixel (err = 0).
+            if (++idle > 16) { st = 0; done = true; break; }
+            skip_limit = false;
+            // minus / plus neighbour along the axis: logical cells (2, 1) / (2, 3) or (1, 2) / (3, 2)
+            const int lo = axis ? 7 : 11, hi = axis ? 17 : 13;
+            if (!((known >> lo) & 1u)) { sr = 2 - axis; sc = 1 + axis; req = R_LO; break; }
+            if (!((known >> hi) & 1u)) { sr = 2 + axis; sc = 3 - axis; req = R_HI; break; }
+            const double dl = d[walk_cell(b0, b1, 2 - axis, 1 + axis)], dh = d[walk_cell(b0, b1, 2 + axis, 3 - axis)];
+            const bool up_m = dl > dc + tol, up_p = dh > dc - tol;
+            if (up_m && up_p) {                    // bracketed on this axis
+                const int dir = dl < dh ? -1 : 1;
+                if (axis) settled1 = dir; else settled0 = dir;
+                if ((axis ? settled0 : settled1) == 0) { axis = 1 - axis; continue; }
+                ip = d[walk_cell(b0, b1, 3, 2)] < d[walk_cell(b0, b1, 1, 2)] ? 1 : 0;
+                jp = d[walk_cell(b0, b1, 2, 3)] < d[walk_cell(b0, b1, 2, 1)] ? 1 : 0;
+                fill = true;
+                continue;
+            }
+            uv[0] = c0; uv[1] = c1;                // best so far, Optim.cpp:421-423
+            out = dc;
+            bool plus = up_m;
+            if (!up_p && !up_m) plus = dh < dl;    // local maximum: go downhill
+            // one step along the axis (Optim.cpp:431-474): the cache moves with the centre
+            if (plus) {
+                dc = dh;
+                if (axis) { c0 += 1; b0 = b0 == 4 ? 0 : b0 + 1; known >>= 5; }
+                else { c1 += 1; b1 = b1 == 4 ? 0 : b1 + 1; known = (known >> 1) & ~COL4; }
+            } else {
+                dc = dl;
+                if (axis) { c0 -= 1; b0 = b0 == 0 ? 4 : b0 - 1; known = (known << 5) & ALL; }
+                else { c1 -= 1; b1 = b1 == 0 ? 4 : b1 - 1; known = (known << 1) & ~COL0 & ALL; }
+            }
+            if (axis) settled0 = 0; else settled1 = 0;
         }
+        if (done) break;
     }
+    wc.known = known; wc.b0 = b0; wc.b1 = b1;
 
     if (finished) {                                // minimum bracketed on both axes: sub-pixel fit
 #pragma unroll
         for (int r = 0; r < 4; r++)
 #pragma unroll
-            for (int q = 0; q < 4; q++) a[4 * r + q] = d[5 * (ip + r) + jp + q];
+            for (int q = 0; q < 4; q++) a[4 * r + q] = d[walk_cell(b0, b1, ip + r, jp + q)];
         args = keep;
         uv[0] = 1. - ip;
         uv[1] = 1. - jp;
@@ -266,7 +256,7 @@ __device__ inline int walk_minimise(Eval &eval, int subpx, const double *quad, F
 // Writes one pixel's results the way Model*::min packs `values` (Model.cpp:573-576, 934-938).
 template <class Grid>
 __device__ __forceinline__ void store_pixel(const umpa_outputs &o, size_t n, int kind, int st, double f,
-                                            const FitArgs &args, const double *uv, Grid d,
+                                            const FitArgs &args, const double *uv, Grid d, const WalkCache &wc,
                                             const double *a, int ncalls, bool have_a)
 {
     if (o.f) o.f[n] = f;
@@ -277,7 +267,7 @@ __device__ __forceinline__ void store_pixel(const umpa_outputs &o, size_t n, int
     if (o.err) o.err[n] = (st & UMPA_ST_OK) ? 1 : 0;
     if (o.ncalls) o.ncalls[n] = ncalls;
     if (o.debug_d)
-        for (int t = 0; t < 25; t++) o.debug_d[25 * n + t] = d[t];
+        for (int t = 0; t < 25; t++) o.debug_d[25 * n + t] = walk_cache_get(d, wc, t);
     if (o.debug_a) {
 #pragma unroll
         for (int t = 0; t < 16; t++) o.debug_a[16 * n + t] = have_a ? a[t] : 0.;

@@ -30,7 +30,13 @@ from .geometry import Geometry
 DEBUG = True      # mirrors `DEF DEBUG = True` (model.pyx:26)
 
 __all__ = ["UMPAModelBase", "UMPAModelNoDF", "UMPAModelDF", "UMPAModelDFKernel",
-           "spm", "spmq", "gaussian_kernel_test", "test_CostArgsDFKernel"]
+           "spm", "spmq", "gaussian_kernel_test", "test_convolve", "test_CostArgsDFKernel", "pool_trim"]
+
+
+def pool_trim():
+    """Release the device blocks the library caches between models (umpa_pool_trim); returns the bytes freed.
+    Call it when another allocator in the process (PyTorch's, ...) needs the memory."""
+    return int(_capi.lib().umpa_pool_trim())
 
 
 def _as_ptr_array(ptrs):
@@ -135,6 +141,10 @@ class UMPAModelBase:
             _capi.check(L.umpa_set_frames(self._h, ptrs(sams), ptrs(refs),
                                           ptrs(masks) if masks is not None else None,
                                           1 if self._on_device else 2, self._stream()))
+        if self._on_device:
+            # umpa_set_frames(on_device=1) has copied (and synchronised): the float64 device copies made by
+            # _frame() are not needed any more (host frames are kept: their upload is deferred)
+            self._frames_keepalive = None
         self._geo.set_ROI(ROI)
 
     # ------------------------------------------------------------------ plumbing
@@ -221,6 +231,12 @@ class UMPAModelBase:
         new_Nw = int(new_Nw)
         if new_Nw < 0:
             raise RuntimeError("Nw must be non-negative.")
+        if self._max_shift + new_Nw + self.safe_crop > self._padding:
+            # The reference keeps the old padding (model.pyx:702-704) and then reads outside its frames -- a host
+            # over-read there, an illegal address that poisons the CUDA context here: refuse instead.
+            raise RuntimeError("Nw = %d needs padding %d but the model was built with padding %d (window_size %d); "
+                               "build a new model instead." % (new_Nw, self._max_shift + new_Nw + self.safe_crop,
+                                                               self._padding, self._padding - self._max_shift - self.safe_crop))
         win = self._make_window(new_Nw)
         _capi.check(_capi.lib().umpa_set_window(self._h, new_Nw, _dp(win)))
         self._window, self._Nw = win, new_Nw
@@ -338,7 +354,43 @@ class UMPAModelBase:
         out["_keepalive"] = (abc_t, cover_t)
         return out
 
-    def _match(self, step=None, dxdy=None, ROI=None, num_threads=None, quiet=False, abc=None, debug=None):
+    def _match(self, step=None, input_values=None, dxdy=None, ROI=None, num_threads=None, quiet=False):
+        """The reference's generic match routine (model.pyx:334-497), same signature and result:
+        {'values': (N0, N1, Nparam) float64, 'err', 'debug_d', 'debug_a', 'debug_Ncalls'}.  `input_values`
+        (same shape, float64) is the array the results are written into; for UMPAModelDFKernel its last three
+        entries per pixel are the blur parameters (a, b, c) (model.pyx:436-455, 982-984).  Pixels the coverage
+        gate skips keep their input values (model.pyx:480-481)."""
+        if (ROI is not None) and (step is not None):
+            s0, s1 = self._convert_ROI_slice(ROI, None)
+        else:
+            s0, s1 = self._convert_ROI_slice(ROI, step)
+        shp = self._shape_of(s0, s1) + (self.Nparam,)
+        abc = None
+        if input_values is not None:
+            if tuple(input_values.shape) != shp:
+                raise RuntimeError("Input values have the wrong shape: "
+                                   "%s, should be %s" % (input_values.shape, shp))
+            if input_values.dtype != np.float64:
+                raise RuntimeError("Input values have the wrong type: "
+                                   "%s, should be %s" % (input_values.dtype, np.float64))
+            values = input_values
+        else:
+            values = np.zeros(shp, dtype=np.float64)
+        if self._kind == _capi.DFKERNEL:
+            abc = np.ascontiguousarray(values[:, :, 4:7])
+        res = self._match_maps(step=step, dxdy=dxdy, ROI=ROI, num_threads=num_threads, quiet=quiet, abc=abc,
+                               debug=True)
+        done = np.ones(shp[:2], dtype=bool)
+        if self._masked or not self._uniform:      # the gate of model.pyx:427-431, 480
+            cover = self.coverage(ROI=(s0, s1))
+            done = ~(cover < .1 * cover.max() / self._Na)
+        keys = ("f", "T", "dx", "dy") + (("df",) if self._kind == _capi.DF else ())
+        for n, k in enumerate(keys):
+            values[:, :, n][done] = res[k][done]
+        return {"values": values, "err": res["err"], "debug_d": res["debug_d"], "debug_a": res["debug_a"],
+                "debug_Ncalls": res["debug_Ncalls"]}
+
+    def _match_maps(self, step=None, dxdy=None, ROI=None, num_threads=None, quiet=False, abc=None, debug=None):
         """Host-to-host match through umpa_match_host: result maps land in pinned host memory.  The
         first call on host frames pipelines upload, kernels and download in row bands."""
         if (ROI is not None) and (step is not None):
@@ -429,7 +481,7 @@ class UMPAModelNoDF(UMPAModelBase):
         return (v[0], v[1])
 
     def match(self, step=None, dxdy=None, ROI=None, num_threads=None, quiet=False, debug=None):
-        return self._match(step=step, dxdy=dxdy, ROI=ROI, num_threads=num_threads, quiet=quiet, debug=debug)
+        return self._match_maps(step=step, dxdy=dxdy, ROI=ROI, num_threads=num_threads, quiet=quiet, debug=debug)
 
 
 class UMPAModelDF(UMPAModelBase):
@@ -446,7 +498,7 @@ class UMPAModelDF(UMPAModelBase):
         return (v[0], v[1], v[2])
 
     def match(self, step=None, dxdy=None, ROI=None, num_threads=None, quiet=False, debug=None):
-        return self._match(step=step, dxdy=dxdy, ROI=ROI, num_threads=num_threads, quiet=quiet, debug=debug)
+        return self._match_maps(step=step, dxdy=dxdy, ROI=ROI, num_threads=num_threads, quiet=quiet, debug=debug)
 
     @property
     def Im(self):
@@ -479,8 +531,8 @@ class UMPAModelDFKernel(UMPAModelBase):
             raise RuntimeError('abc array has to be provided')
         elif tuple(abc.shape) != sh + (3,):
             raise RuntimeError('Wrong array shape for abc: %s, should be %s' % (abc.shape, sh + (3,)))
-        return self._match(step=step, dxdy=dxdy, ROI=ROI, num_threads=num_threads, quiet=quiet, abc=abc,
-                           debug=debug)
+        return self._match_maps(step=step, dxdy=dxdy, ROI=ROI, num_threads=num_threads, quiet=quiet, abc=abc,
+                                debug=debug)
 
 
 # ---------------------------------------------------------------------- module hooks (model.pyx:31-114)
@@ -531,6 +583,19 @@ def gaussian_kernel_test(Nk, a, b, c):
     """model.pyx:82-92"""
     i, j = np.mgrid[-Nk:Nk + 1, -Nk:Nk + 1].astype(float)
     return np.exp(-a * i * i - b * i * j - c * j * j)
+
+
+def test_convolve(image, i, j, kernel):
+    """model.pyx:94-102 -> convolve (Utils.cpp:85-97): sum_kl kernel[k, l] * image[i + k - Nk, j + l - Nk].
+    Like the reference there is no bounds check beyond what numpy slicing gives."""
+    image = np.asarray(image, dtype=np.float64)
+    kernel = np.asarray(kernel, dtype=np.float64)
+    Nk = (kernel.shape[0] - 1) // 2
+    i, j = int(i), int(j)
+    return float((kernel[:2 * Nk + 1, :2 * Nk + 1] * image[i - Nk:i + Nk + 1, j - Nk:j + Nk + 1]).sum())
+
+
+test_convolve.__test__ = False
 
 
 def test_CostArgsDFKernel(i, j, a, b, c):
