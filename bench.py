@@ -13,11 +13,14 @@ Printed JSON (one line, rank 0):
   e2e          same metric through the public drop-in API with HOST buffers: per step the float64
                stacks go host(pinned)->device, are converted, matched, and the result maps come
                back to pinned host memory.
-  roofline     dominant kernel (cross-correlation shift table): ALGORITHMIC flops
-               2*S^2*Na*K^2 per output pixel / measured kernel time, against the
-               FP32-FMA peak measured on this GPU in this run by an FFMA probe.  The kernel
-               executes ~K^2/ (1+2K/Na) times fewer FMAs than that (frame-sum first, filter once),
-               so `frac` can exceed 1; `executed_*` report what the SMs really did.
+  roofline     the kernel with the largest share of the step: its BINDING resource (the largest of executed FP32
+               FMAs / measured FFMA peak, DRAM bytes / measured copy bandwidth, shared-memory wavefronts / cycle,
+               issued instructions / issue slots) as achieved / peak = frac <= ~1; per kernel the live CUDA-event
+               time x the per-launch counters of the committed ncu capture (profiles/r02_kernels.json).  The
+               direct-form figure of SURVEY.md 8d (2*S^2*Na*K^2 flop/px) is reported beside it as
+               `algorithmic_speedup` / `frac_alg_step`: the kernels execute ~13x fewer FMAs than that form.
+  parity       the maps of this run against the UNMODIFIED reference on the block of rows the cpu_baseline leg
+               computes anyway (tests/helpers.py::fp32_parity_stats).
   cpu_baseline the reference's own OpenMP CPU path (oracle/_ref, built from /root/reference) or
                the C port, timed on this box's host cores on a bounded ROI of the same workload.
 """
@@ -42,11 +45,9 @@ CONFIGS = {
     "cfg5": dict(kind="NoDF", Na=4, H=2048, W=2048, Nw=6, ms=4, desc="UMPAModelNoDF 4x2048^2 Nw=6 max_shift=4"),
 }
 SAFE_CROP = {"NoDF": 0, "DF": 0, "DFKernel": 8}
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
-# `ncu --set full` capture of the same command (profiles/r01f_final_kernels_ncu_summary.txt): the cross-table
-# kernel reads the two FP32 stacks once (0.88 GB with the tile halos) and writes the 81-plane table (1.31 GB).
-NCU_TRAFFIC = {("cfg2", 1): 880.3e6 + 1.3138e9}
-NCU_TRAFFIC_SOURCE = "profiles/r01f_final_kernels_ncu_summary.txt (ncu --set full, shift_table_kernel<9,3,2>)"
+# Per-launch counters of the kernels of one config-2 step (N = 1), from `ncu --set full` of `python tools/prof_step.py cfg2`
+# (tools/ncu_kernels.py writes the file; everything in `roofline` that is not a live time comes from it).
+NCU_KERNELS = os.path.join(ROOT, "profiles", "r02_kernels.json")
 
 
 def algorithmic_flops_per_px(cfg):
@@ -59,20 +60,13 @@ def algorithmic_flops_per_px(cfg):
 
 
 def executed_fma_per_px_cross(cfg):
-    """FMAs the cross-table kernel executes per output pixel: Na per (extended-tile pixel, shift)
-    plus the separable filter (row pass on the extended rows, column pass).  Tile geometry of
-    table_path.cu: extended tile 16 x 32, output tile (16-2Nw) x (32-2Nw)."""
+    """FMAs the cross-table kernel executes per output pixel (streaming chunks, shift_table.cuh): Na per (chunk
+    pixel, shift) -- the chunk is 32 columns wide for 32 - 2 Nw output columns; the window halo in y is paid once
+    per row segment, i.e. not at all to first order -- plus the separable filter (row pass on the chunk columns,
+    column pass on the outputs)."""
     S, K, Na, Nw = 2 * cfg["ms"] - 1, 2 * cfg["Nw"] + 1, cfg["Na"], cfg["Nw"]
-    # extended tile height as plan_tiles (table_path.cu) picks it
-    def _cost(eh):
-        sh = 3 if S <= 9 else (2 if S <= 17 else 1)
-        g = min(384 // (eh * 8), -(-S // sh))
-        return eh / float(eh - 2 * Nw) * (1. + .15 * (-(-S // (g * sh)) - 1))
-    eh = min((e for e in (16, 24, 32, 48) if e - 2 * Nw >= 2), key=lambda e: (_cost(e), e))
-    eh, ew = int(os.environ.get("UMPA_TAB_EH", eh)), 32
-    th, tw = eh - 2 * Nw, ew - 2 * Nw
-    per_tile = S * S * (Na * eh * ew + K * eh * tw + K * th * tw)
-    return per_tile / float(th * tw)
+    tw = (32 - 2 * Nw) & ~3
+    return S * S * ((Na + K) * 32. / tw + K)
 
 
 class ClockSampler:
@@ -163,7 +157,7 @@ def cpu_match(model, kind, roi, cores, cfg):
     else:
         res = model.match(ROI=roi, num_threads=cores, debug=False, **kw)
     dt = time.perf_counter() - t
-    return res["err"].size, dt
+    return res["err"].size, dt, res
 
 
 def centred_roi(cfg, n_px_target):
@@ -174,24 +168,28 @@ def centred_roi(cfg, n_px_target):
     return ((r0, r0 + rows, 1), (0, N1, 1)), rows * N1
 
 
-def run_cpu_sample(cfg, sam_np, ref_np, target_s, steps=1, warmup=0):
-    """Times the CPU path on a centred full-width row block sized for ~target_s per step."""
+def run_cpu_sample(cfg, sam_np, ref_np, target_s, steps=1, warmup=0, keep_result=False):
+    """Times the CPU path on a centred full-width row block sized for ~target_s per step.
+    keep_result: also return (roi, result dict of the last step) for the parity record."""
     cores = os.cpu_count() or 1
     model, kind = cpu_model(cfg, sam_np, ref_np)
     roi, npx = centred_roi(cfg, 20000)
-    _, dt = cpu_match(model, kind, roi, cores, cfg)                 # calibration (also warms caches)
+    _, dt, _ = cpu_match(model, kind, roi, cores, cfg)              # calibration (also warms caches)
     rate = npx / max(dt, 1e-6)
     roi, npx = centred_roi(cfg, rate * target_s)
     for _ in range(warmup):
         cpu_match(model, kind, roi, cores, cfg)
-    times = []
+    times, res = [], None
     for _ in range(steps):
-        n, dt = cpu_match(model, kind, roi, cores, cfg)
+        n, dt, res = cpu_match(model, kind, roi, cores, cfg)
         times.append(dt)
     t = float(np.mean(times))
     sample = "centred full-width block of %d rows (%d px) of %s, %d threads" % (
         roi[0][1] - roi[0][0], npx, cfg["desc"], cores)
-    return dict(value=npx / t, unit="output pixels/s", cores=cores, kind=kind, sample=sample), t, npx
+    base = dict(value=npx / t, unit="output pixels/s", cores=cores, kind=kind, sample=sample)
+    if keep_result:
+        return base, t, npx, roi, res
+    return base, t, npx
 
 
 def reference_arm(args, cfg):
@@ -218,6 +216,46 @@ def reference_arm(args, cfg):
 
 
 # ------------------------------------------------------------------------------ our arm
+
+STAGES = ("moments", "cross_table", "mean_table", "walk")
+
+
+def kernel_roofline(cfg_name, world, stage_ms, fma_peak, hbm_gbs, sm_mhz, sms):
+    """Per kernel of the step: live CUDA-event time x the per-launch counters of the committed ncu capture ->
+    fraction of each resource; the kernel's `frac` is its binding (largest) one.  Returns (per-kernel dict, source)."""
+    try:
+        ncu = json.load(open(NCU_KERNELS))
+    except Exception:
+        return None, None
+    if cfg_name != ncu.get("config", "cfg2") or world != 1:
+        return None, None
+    pick = {}
+    for name, k in ncu["kernels"].items():
+        if name.startswith("moments"):
+            pick["moments"] = (name, k)
+        elif name.startswith("shift_table_kernel") and name.rstrip(">").endswith("-1"):
+            pick["mean_table"] = (name, k)
+        elif name.startswith("shift_table_kernel") or name.startswith("ktable"):
+            pick["cross_table"] = (name, k)
+        elif name.startswith("table_walk"):
+            pick["walk"] = (name, k)
+    out = {}
+    for st, ms in zip(STAGES, stage_ms):
+        if st not in pick or ms <= 0.:
+            continue
+        name, k = pick[st]
+        scale = k["ncu_duration_ns"] * 1e-6 / ms                 # same work, profiled duration vs live duration
+        dram = k["dram_read_bytes"] + k["dram_write_bytes"]
+        fr = {"fma_pipe": k["fma_pipe_pct"] / 100. * scale,
+              "hbm": dram / (ms * 1e-3) / 1e9 / hbm_gbs,
+              "shared_memory": k["smem_wavefronts"] / (sms * k["sm_cycles"]) * scale,
+              "issue_slots": k["issue_active_pct"] / 100. * scale}
+        bound = max(fr, key=fr.get)
+        out[st] = {"kernel": name, "ms": ms, "ncu_ms": k["ncu_duration_ns"] * 1e-6, "dram_bytes": dram,
+                   "warp_inst": k["warp_inst"], "smem_wavefronts": k["smem_wavefronts"],
+                   "fractions": fr, "bound": bound, "frac": fr[bound]}
+    return out, "profiles/%s (%s; ncu --set full of `%s`)" % (os.path.basename(NCU_KERNELS), ncu.get("source"), ncu.get("command"))
+
 
 def ours(args, cfg):
     import torch
@@ -265,21 +303,30 @@ def ours(args, cfg):
     if cfg["kind"] == "DFKernel":
         from umpa_b200 import synth
         kw["abc"] = synth.blur_abc(N0, N1, as_numpy=False).to(dev)
+    keys = ("f", "T", "dx", "dy") + (("df",) if cfg["kind"] == "DF" else ()) + ("err", "debug_Ncalls")
 
     # ---- device-resident metric -------------------------------------------------
+    # one step = one match of this rank's row band; for N > 1 followed by the gather of the maps on rank 0
+    # (the only inter-GPU traffic of the path: north_star / SURVEY 8d "gathered on GPU 0")
     sm = ShardedMatcher(cls, list(sam), list(ref), rank, world, window_size=cfg["Nw"], max_shift=cfg["ms"])
     band_rows = sm.band[1] - sm.band[0]
     lo, hi = sm.band[0], sm.band[1] + 2 * pad
+
+    def step():
+        o = sm.match_device(**kw)
+        if world > 1:
+            o = sm.gather(o, keys=keys, dst=0)
+        return o
     launches = 0
     for _ in range(args.warmup):
-        out = sm.match_device(**kw)
+        out = step()
     info = sm.model.last_match_info if sm.model is not None else {"path": "none", "kernel_launches": 0}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     with ClockSampler(local) as clk:
         e0.record()
         for _ in range(args.steps):
-            out = sm.match_device(**kw)
+            out = step()
             launches += info["kernel_launches"]
         e1.record()
         torch.cuda.synchronize()
@@ -287,9 +334,29 @@ def ours(args, cfg):
     ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     value = total_px / (ms * 1e-3)
     launches = int(sum_over_ranks(launches))
-    err_ok = float(sum_over_ranks(float((out["err"] == 1).sum().item()) if out else 0.)) / total_px
+    err_ok = None
+    if rank == 0:
+        err_ok = float((out["err"] == 1).sum().item()) / total_px          # rank 0 holds the whole map (gathered for N > 1)
+    gather = None
+    if world > 1:                                 # the gather alone, and the match alone
+        loc = sm.match_device(**kw)
+        g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        barrier()
+        g0.record()
+        for _ in range(args.steps):
+            sm.match_device(**kw)
+        g1.record()
+        for _ in range(args.steps):
+            sm.gather(loc, keys=keys, dst=0)
+        g2.record()
+        torch.cuda.synchronize()
+        barrier()
+        gather = {"match_ms": max_over_ranks(g0.elapsed_time(g1) / args.steps),
+                  "gather_ms": max_over_ranks(g1.elapsed_time(g2) / args.steps),
+                  "bytes_to_rank0": int(sum_over_ranks(0. if rank == 0 else float(sum(loc[k].numel() * loc[k].element_size() for k in keys if k in loc)))),
+                  "how": "two torch.distributed.gather calls (packed float64 maps, packed int32 maps) over NCCL, inside the timed step"}
 
-    # ---- stage times of the dominant kernel (events inside the library, same stream) -------
+    # ---- stage times of the kernels (events inside the library, same stream) -------
     stage_ms = None
     if sm.model is not None and info["path"] == "table":
         _capi.check(_capi.lib().umpa_set_profiling(sm.model._h, 1))
@@ -305,6 +372,9 @@ def ours(args, cfg):
     peak = C.c_double(0.)
     sms = C.c_int(0)
     _capi.check(_capi.lib().umpa_fma_peak(C.byref(peak), C.byref(sms)))
+    out_host = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out_host = {k: v.cpu().numpy() for k, v in out.items() if k in keys}
 
     # ---- end to end through the drop-in API with host buffers --------------------------------
     e2e = None
@@ -317,7 +387,7 @@ def ours(args, cfg):
         kw_h = {}
         if "abc" in kw:
             kw_h["abc"] = kw["abc"][sm.band[0]:sm.band[1]].cpu().numpy()
-        del sm
+        del sm, out
         steps_e = max(2, min(args.steps, 10))
         d2h = 0
 
@@ -328,7 +398,11 @@ def ours(args, cfg):
             r = m.match(quiet=True, debug=False, **kw_h)
             stream_info.update(m.last_stream_info)
             return sum(v.nbytes for v in r.values())
-        for _ in range(max(3, args.warmup)):     # (the first calls pin staging / result buffers and measure the host rates)
+        barrier()
+        t0 = time.perf_counter()
+        d2h = one()                              # the first host-to-host call of the process (pins staging / result buffers)
+        first_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+        for _ in range(max(3, args.warmup)):     # (the first calls also measure the host rates)
             d2h = one()
         barrier()
         t0 = time.perf_counter()
@@ -338,7 +412,7 @@ def ours(args, cfg):
         t_e = (time.perf_counter() - t0) / steps_e
         barrier()
         t_e = max_over_ranks(t_e)
-        e2e = {"value": total_px / t_e, "unit": "output pixels/s", "ms_per_step": 1e3 * t_e,
+        e2e = {"value": total_px / t_e, "unit": "output pixels/s", "ms_per_step": 1e3 * t_e, "first_call_ms": first_ms,
                "h2d_bytes_per_step": int(sum_over_ranks(float(sam_np.nbytes + ref_np.nbytes))),
                "d2h_bytes_per_step": int(sum_over_ranks(float(d2h))), "steps": steps_e,
                "api": "%s(sam, ref, window_size, max_shift).match(debug=False) on pinned host float64 arrays"
@@ -371,16 +445,27 @@ def ours(args, cfg):
                                  "h2d_bytes_per_step": int(sum_over_ranks(float(s32.nbytes + r32.nbytes))),
                                  "note": "same call, frames given as float32 numpy arrays (widened and centred on the GPU)"}
 
-    # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------------------
-    cpu = None
+    # ---- CPU baseline + parity against it (rank 0, N=1 only) ------------------------------------
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cpu, _, _ = run_cpu_sample(cfg, sam.cpu().numpy(), ref.cpu().numpy(), args.cpu_seconds)
+            cpu, _, _, roi, res = run_cpu_sample(cfg, sam.cpu().numpy(), ref.cpu().numpy(), args.cpu_seconds, keep_result=True)
         except Exception as e:      # the baseline must never take the GPU number down with it
             cpu = {"value": None, "unit": "output pixels/s", "cores": os.cpu_count(), "kind": "unavailable",
                    "sample": "failed: %r" % (e,)}
+            res = None
+        if res is not None and "debug_d" in res:
+            # the block the reference just computed against the same rows of the device-resident maps of the timed steps
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from helpers import fp32_parity_stats
+            (r0, r1, _), (c0, c1, _) = roi
+            got = {k: v[r0:r1, c0:c1] for k, v in out_host.items()}
+            parity = fp32_parity_stats(got, res)
+            parity["against"] = "%s on rows [%d, %d) x cols [%d, %d) of the output" % (cpu["kind"], r0, r1, c0, c1)
 
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     peaks = {}
     try:
@@ -388,45 +473,52 @@ def ours(args, cfg):
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.)
+    clocks = clk.summary()
+    alg_bytes = 2. * cfg["Na"] * cfg["H"] * cfg["W"] * 4 + 6 * 4. * total_px
     roof = None
     if stage_ms is not None:
-        px_rank = band_rows * N1                         # rank 0's launch processes its band
-        t_cross = stage_ms[1] * 1e-3
-        f_alg = algorithmic_flops_per_px(cfg)
         dfk = cfg["kind"] == "DFKernel"
-        if dfk:     # the blur-table kernel executes the direct form: patch blur + t5 partials + q3 (kernel_path.cu)
-            S_, K_ = 2 * cfg["ms"] - 1, 2 * cfg["Nw"] + 1
-            f_exe = 2. * cfg["Na"] * ((K_ + S_ - 1) ** 2 * 17 ** 2 + (K_ + S_ - 1) * K_ * K_ * S_ + (K_ + S_ - 1) ** 2)
-            kname = "ktable_kernel<Nw=%d,S=%d> (per-pixel blur tables)" % (cfg["Nw"], S_)
-            note = ("achieved = SURVEY 8d direct-form flop/px x px / kernel time; the kernel executes that form "
-                    "(blur of the (K+S-1)^2 patch per frame; executed/algorithmic <= %.2f: kernel taps below 1e-10 of "
-                    "the pixel's largest tap are zero and the blur loops stop at the last non-zero row / column)")
+        names = ["moments", "blur_table" if dfk else "cross_table", "mean_table", "walk"]
+        px_rank = band_rows * N1                         # rank 0's launches process its band
+        f_alg = algorithmic_flops_per_px(cfg)
+        kern, src = kernel_roofline(args.config, world, stage_ms, peak.value, hbm_peak, clocks.get("sm_mhz") or 1965., sms.value)
+        top = int(np.argmax(stage_ms))
+        roof = {"stage_ms": dict(zip(names, stage_ms)), "kernels": kern, "source": src,
+                "peaks": {"fp32_fma_tflops": peak.value, "fp32_fma_source": "FFMA probe measured in this run on this GPU (umpa_fma_peak)",
+                          "hbm_gbs": hbm_peak, "hbm_source": "MEASURED_PEAKS.json" if peaks else "fallback of B200_PROFILING.md",
+                          "shared_memory": "128 B (one wavefront) per SM and cycle", "issue_slots": "4 per SM and cycle"},
+                # the direct form of SURVEY.md 8d, for the record: the kernels do the same sums with far fewer FMAs
+                "algorithmic_flop_per_px": f_alg,
+                "frac_alg_step": f_alg * px_rank / (sum(stage_ms) * 1e-3) / 1e12 / peak.value,
+                "note_alg": "frac_alg_step = direct-form flops (2*S^2*Na*K^2 per px, SURVEY 8d) / step time / FFMA peak; "
+                            "above 1 because the frames are summed before the window filter (exact algebra)"}
+        if kern:
+            st = STAGES[top]
+            k = kern[st]
+            unit = {"fma_pipe": "TFLOP/s", "hbm": "GB/s", "shared_memory": "wavefronts/cycle/SM", "issue_slots": "inst/cycle/SM"}[k["bound"]]
+            pk = {"fma_pipe": peak.value, "hbm": hbm_peak, "shared_memory": 1., "issue_slots": 4.}[k["bound"]]
+            roof.update({"kernel": k["kernel"], "bound": k["bound"], "achieved": k["frac"] * pk, "peak": pk, "unit": unit,
+                         "frac": k["frac"], "traffic": k["dram_bytes"], "kernel_ms": k["ms"]})
+            tot = sum(v["dram_bytes"] for v in kern.values())
+            roof["step"] = {"dram_bytes": tot, "algorithmic_bytes": alg_bytes, "traffic_over_algorithmic": tot / alg_bytes,
+                            "hbm_floor_ms_of_traffic": tot / hbm_peak / 1e6, "hbm_floor_ms_algorithmic": alg_bytes / hbm_peak / 1e6,
+                            "step_ms": sum(stage_ms)}
+            if not dfk:
+                f_exe = 2. * executed_fma_per_px_cross(cfg) + (2. * (2 * cfg["ms"] - 1) ** 2 * cfg["Na"] if cfg["kind"] == "DF" else 0.)
+                roof["algorithmic_speedup"] = f_alg / f_exe
         else:
-            f_exe = 2. * executed_fma_per_px_cross(cfg)
-            kname = "shift_table_kernel<S=%d,Nw=%d> (cross table)" % (2 * cfg["ms"] - 1, cfg["Nw"])
-            note = ("achieved = 2*S^2*Na*K^2 flop/px (SURVEY 8d, direct form) x px / kernel time; the kernel "
-                    "sums over frames first and filters once, so it executes %.0fx fewer FMAs")
-        ach = f_alg * px_rank / t_cross / 1e12
-        exe = f_exe * px_rank / t_cross / 1e12
-        roof = {"bound": "fp32_fma", "kernel": kname,
-                "achieved": ach, "peak": peak.value, "unit": "TFLOP/s", "frac": ach / peak.value,
-                "peak_source": "FFMA probe measured in this run on this GPU (umpa_fma_peak); nominal %.1f"
-                               % (sms.value * 128 * 2 * (peaks.get("sm_max_mhz", 1965.) * 1e6) / 1e12),
-                "traffic": NCU_TRAFFIC.get((args.config, world)), "traffic_source": NCU_TRAFFIC_SOURCE
-                if (args.config, world) in NCU_TRAFFIC else None, "kernel_ms": stage_ms[1],
-                "executed_tflops": exe, "executed_frac": exe / peak.value,
-                "note": note % ((f_exe / f_alg) if dfk else (f_alg / f_exe)),
-                "stage_ms": {"moments": stage_ms[0], "blur_table" if dfk else "cross_table": stage_ms[1],
-                             "mean_table": stage_ms[2], "walk": stage_ms[3]}}
-    alg_bytes = 2. * cfg["Na"] * cfg["H"] * cfg["W"] * 4 + 6 * 4. * total_px
+            roof.update({"kernel": names[top], "bound": None, "achieved": None, "peak": None, "unit": None, "frac": None,
+                         "traffic": None, "kernel_ms": stage_ms[top],
+                         "note": "no ncu capture committed for this configuration / GPU count: stage times only"})
     line = {"metric": "output pixels/s", "value": value, "unit": "output pixels/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["desc"], "output_px": total_px, "sharding": "row bands x%d + %d-row halo" % (world, pad),
                        "path": info["path"], "l2": "inputs (%.0f MB FP32 stacks) larger than the 126 MB L2, no flush" % (alg_bytes / 1e6),
-                       "inputs_resident": "mean-centred FP32 stacks in HBM; result maps (f,T,dx,dy,df f64; err,Ncalls i32) left in HBM",
+                       "inputs_resident": "mean-centred FP32 stacks in HBM; result maps (f,T,dx,dy,df f64; err,Ncalls i32) left in HBM"
+                                          + (" of rank 0 (gathered over NCCL inside the timed step)" if world > 1 else ""),
                        "err_ok_fraction": err_ok},
-            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roof,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "gather": gather, "parity": parity,
             "roofline_hbm_step": {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9 / world, "peak": hbm_peak,
                                   "unit": "GB/s", "frac": alg_bytes / (ms * 1e-3) / 1e9 / world / hbm_peak,
                                   "note": "algorithmic bytes of the whole step (stacks once + 6 maps) per GPU-second"},

@@ -124,6 +124,70 @@ def sensitivity(d, a, eps, trials=12, seed=0):
     return dp, dv
 
 
+def fp32_parity_stats(got, exp, tol=1e-4, eps=3e-6, noise_floor=3e-6, max_probe=400):
+    """Everything the parity criteria of SURVEY.md 8(d) ask for, as numbers (no assertion): how `got` (the FP32 table
+    path) differs from `exp` (the reference, with its debug arrays).  JSON-serialisable.
+      err_mismatch      pixels whose err flag differs
+      ncalls_mismatch   ok-pixels whose number of cost evaluations differs (the integer walk took another route) ...
+      walk_ties         ... of which the reference's own cache shows a neighbour within 1e-5 of the cost scale of the
+                        centre (its `> d +- 1e-8` test is a coin flip there); walk_unexplained = the rest
+      T_ties / df_ties  ok-pixels (walk equal) whose T / df differs by more than tol: same tie criterion; *_unexplained
+      exceptions        ok-pixels (walk equal) with dx, dy beyond tol*max(1,|ref|) or f beyond tol*|ref| + floor
+      excused           ... of which the reference's own sub-pixel answer moves by more than tol/2 when its 4x4 block is
+                        perturbed at the eps level (ill-conditioned refinement); unexcused = the rest
+      <k>_max, <k>_p999 largest / 99.9th-percentile deviation of k in {dx, dy, T, df, f} over the compared pixels"""
+    err_g, err_e = np.asarray(got["err"]), np.asarray(exp["err"])
+    st = {"n_px": int(err_e.size), "n_ok": int((err_e == 1).sum()), "err_mismatch": int((err_g != err_e).sum()),
+          "tol": tol}
+    ok = (err_e == 1) & (err_g == 1)
+    dpos = exp["debug_d"][err_e == 1]
+    cost_scale = float(np.median(dpos[dpos > 0])) if (dpos > 0).any() else 1.
+    st["cost_scale"] = cost_scale
+
+    def near_tie(i, j):
+        d5 = exp["debug_d"][i, j]
+        vals = [abs(d5[n] - d5[12]) for n in (7, 11, 13, 17) if d5[n] > -.5]
+        return bool(vals) and min(vals) <= 1e-5 * cost_scale
+
+    nc = ok & (np.asarray(got["debug_Ncalls"]) != exp["debug_Ncalls"])
+    st["ncalls_mismatch"] = int(nc.sum())
+    ties = sum(1 for i, j in np.argwhere(nc) if near_tie(i, j))
+    st["walk_ties"], st["walk_unexplained"] = ties, int(nc.sum()) - ties
+    ok = ok & ~nc
+    for k in ("T", "df"):
+        if k not in exp or k not in got:
+            continue
+        rel = np.abs(np.asarray(got[k]) - exp[k]) / np.maximum(np.abs(exp[k]), .25)
+        bad = ok & ~(rel <= tol)
+        t = sum(1 for i, j in np.argwhere(bad) if near_tie(i, j))
+        st[k + "_ties"], st[k + "_unexplained"] = t, int(bad.sum()) - t
+        st[k + "_max"] = float(rel[ok].max()) if ok.any() else 0.
+        st[k + "_p999"] = float(np.percentile(rel[ok], 99.9)) if ok.any() else 0.
+    bad = np.zeros(err_e.shape, dtype=bool)
+    for k in ("dx", "dy"):
+        rel = np.abs(np.asarray(got[k]) - exp[k]) / np.maximum(1., np.abs(exp[k]))
+        bad |= ok & ~(rel <= tol)
+        st[k + "_max"] = float(rel[ok].max()) if ok.any() else 0.
+        st[k + "_p999"] = float(np.percentile(rel[ok], 99.9)) if ok.any() else 0.
+    df_ = np.abs(np.asarray(got["f"]) - exp["f"])
+    relf = df_ / np.maximum(np.abs(exp["f"]), 1e-300)
+    st["f_max"] = float(relf[ok].max()) if ok.any() else 0.
+    st["f_p999"] = float(np.percentile(relf[ok], 99.9)) if ok.any() else 0.
+    bad_f = ok & ~(df_ <= tol * np.abs(exp["f"]) + noise_floor * cost_scale)
+    idx = np.argwhere(bad | bad_f)
+    st["exceptions"] = int(len(idx))
+    excused = probed = 0
+    for i, j in idx[:max_probe]:
+        probed += 1
+        dp, dv = sensitivity(exp["debug_d"][i, j], exp["debug_a"][i, j], eps)
+        if bad[i, j]:
+            excused += dp > tol / 2
+        else:
+            excused += dv > (tol * abs(exp["f"][i, j]) + noise_floor * cost_scale) / 2
+    st["excused"], st["unexcused"], st["probed"] = int(excused), int(probed - excused), int(probed)
+    return st
+
+
 def compare_fp32(got, exp, tol=1e-4, eps=3e-6, max_exception_frac=0.03, noise_floor=3e-6, label=""):
     """Parity check of the FP32 table path (tolerances of BASELINE.json north_star):
     err map and Ncalls (the integer walk) must be EQUAL; T, df within tol relative; dx, dy within

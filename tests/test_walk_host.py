@@ -57,11 +57,12 @@ extern "C" int walk_host(cost_fn fn, const void *m, int i, int j, const double *
     HostEval ev{fn, m, i, j, abc, poison, ms};
     FitArgs args{0., 0.};
     double f = 0., uv[2] = {uv0[0], uv0[1]};
-    for (int t = 0; t < 16; t++) a[t] = 0.;
     double cells[25];                                     // the ring storage; d receives the cache in the reference's order
-    WalkCache wc;
-    const int st = walk_minimise(ev, subpx, quad, args, f, uv, cells, a, *ncalls, wc);
-    for (int t = 0; t < 25; t++) d[t] = walk_cache_get(cells, wc, t);
+    WalkState ws;
+    const int st = walk_search(ev, args, f, uv, cells, *ncalls, ws);
+    for (int t = 0; t < 25; t++) d[t] = walk_cache_get(cells, ws, t);
+    for (int t = 0; t < 16; t++) a[t] = ws.finished ? walk_block_get(cells, ws, t >> 2, t & 3) : 0.;
+    if (ws.finished) walk_refine(subpx, quad, cells, ws, f, uv);
     res[0] = f; res[1] = args.t; res[2] = args.v; res[3] = uv[0]; res[4] = uv[1];
     return st;
 }

@@ -260,13 +260,13 @@ lazy_match_kernel(LazyView m, RoiView roi, umpa_outputs out, double *kern_ws, in
     }
     LazyEval<KIND> eval{m, roi.off0 + roi.step0 * xi, roi.off1 + roi.step1 * xj, kern, ks};
     FitArgs args{0., 0.};
-    double d[25], a[16], uv[2] = {roi.uv0[0], roi.uv0[1]}, f = 0.;
+    double d[25], uv[2] = {roi.uv0[0], roi.uv0[1]}, f = 0.;
     int ncalls;
-    WalkCache wc;
-#pragma unroll
-    for (int t = 0; t < 16; t++) a[t] = 0.;
-    const int st = walk_minimise(eval, m.subpx, m.quad, args, f, uv, d, a, ncalls, wc);
-    store_pixel(out, n, m.kind, st, f, args, uv, d, wc, a, ncalls, true);
+    WalkState ws;
+    const int st = walk_search(eval, args, f, uv, d, ncalls, ws);
+    store_debug(out, n, d, ws);                    // (before the fit: it reuses the cache's cells)
+    if (ws.finished) walk_refine(m.subpx, m.quad, d, ws, f, uv);
+    store_pixel(out, n, m.kind, st, f, args, uv, ncalls);
 }
 
 __global__ void lazy_cost_kernel(LazyView m, int i, int j, int si, int sj, double a, double b, double c,
@@ -286,16 +286,17 @@ __global__ void lazy_min_kernel(LazyView m, int i, int j, double *io, double *ke
     if (m.kind == UMPA_DFKERNEL) build_blur_kernel(io[4], io[5], io[6], kern, 1);
     LazyEval<> eval{m, i, j, kern, 1};
     FitArgs args{0., 0.};
-    double d[25], a[16], uv[2] = {io[7], io[8]}, f = 0.;
+    double d[25], uv[2] = {io[7], io[8]}, f = 0.;
     int ncalls;
-    WalkCache wc;
-    for (int t = 0; t < 16; t++) a[t] = 0.;
-    const int st = walk_minimise(eval, m.subpx, m.quad, args, f, uv, d, a, ncalls, wc);
+    WalkState ws;
+    const int st = walk_search(eval, args, f, uv, d, ncalls, ws);
+    for (int t = 0; t < 25; t++) io[9 + t] = walk_cache_get(d, ws, t);
+    for (int t = 0; t < 16; t++) io[34 + t] = ws.finished ? walk_block_get(d, ws, t >> 2, t & 3) : 0.;
+    if (ws.finished) walk_refine(m.subpx, m.quad, d, ws, f, uv);
     io[0] = f; io[1] = args.t; io[2] = uv[1]; io[3] = uv[0];
     if (m.kind == UMPA_DF) io[4] = args.v;
     io[7] = uv[0]; io[8] = uv[1];
-    for (int t = 0; t < 25; t++) io[9 + t] = walk_cache_get(d, wc, t);
-    for (int t = 0; t < 16; t++) io[34 + t] = a[t];
+
     io[50] = ncalls; io[51] = st;
 }
 

@@ -15,13 +15,20 @@ constexpr int SMEM_CAP = 227 * 1024;
 //
 // table[s][p] = sum_k A_k(p+s) * B_k(p)   (FILTER: then window-filtered over p)
 //
-// One CTA owns an output tile TH x TW and produces ALL S*S shifts for it.  Work split:
-//   * the extended tile (EH = TH + 2*halo rows, 32 columns = TW + 2*halo) is cut into strips of
-//     4 consecutive pixels; a thread owns one strip -> 8 strips per row, so every quarter
-//     warp reads one contiguous 128 B shared-memory line (conflict-free LDS.128);
+// A persistent CTA works through a list of ITEMS; an item is a column strip (TW outputs wide) times a segment
+// of output rows, processed top to bottom in CHUNKS of EH rows.  Per chunk the CTA produces ALL S*S shifts:
+//   * the chunk (EH rows x 32 columns = TW + 2*halo) is cut into strips of 4 consecutive pixels; a thread owns
+//     one strip -> 8 strips per row, so every quarter warp reads one contiguous 128 B shared-memory line
+//     (conflict-free LDS.128);
 //   * G warp groups work on the same frame at the same time, group g accumulating shift rows
 //     [ (pass*G+g)*SH, +SH ): SH*S*4 FP32 accumulators per thread live in registers across all
 //     frames, so each frame tile is streamed through shared memory exactly once per pass;
+//   * the FMAs are Blackwell's packed FFMA2 (fma.rn.f32x2): the products A(q) * B(x) and A(q) * B(x+1) of one
+//     reference value with two neighbouring sample pixels belong to the shifts q - x and q - x - 1, so one
+//     instruction with A(q) as the broadcast scalar operand and the pair (B(x), B(x+1)) -- a natural register
+//     pair of the LDS.128 -- does both: 20 issue slots per shift row instead of 36.  The FMA pipe does the same
+//     work either way (measured, tools/probe/ffma2_probe.cu); what it buys is issue slots next to the ten LDS.128
+//     per frame: 605 -> 505 cycles per frame and SM, against 480 from shared-memory bandwidth;
 //   * frames arrive by TMA (cp.async.bulk.tensor, 3-D map over [Na][H][pitch], zero fill out
 //     of bounds) into a ring of NST stages of FB frames each (one box per stack and stage),
 //     guarded by full/empty mbarriers; thread 0 is the producer, nobody executes a per-frame
@@ -30,24 +37,33 @@ constexpr int SMEM_CAP = 227 * 1024;
 //     registers (shuffles inside the 8-lane row group), row-filtered strips to the group's slice of
 //     shared memory, named barrier per group, column pass per thread (K float4 loads), float4
 //     stores to the table.
+//   * STREAMING: the column pass of an output row needs the row-filtered chunk rows r .. r+2*halo.  The last
+//     2*halo row-filtered rows of a chunk are kept in shared memory (`carry`, all S*S planes) for the next chunk
+//     of the same item, so a chunk of EH rows yields EH output rows: the window halo in y is paid once per
+//     segment instead of once per tile (config 2: 12 of 16 rows -> 16 of 16).  Where the carry does not fit
+//     (large S * Nw) the host makes every segment one chunk high (EH - 2*halo rows): the classic halo tile.
 
 struct TableParams {
-    float *table;                // [S*S][rows_p][cols_p]
+    float *table;                // entry (row, shift, col) at table[row * row_stride + shift * plane_stride + col]:
+                                 // the S*S shifts of one pixel row lie next to each other (and the two tables of a DF
+                                 // model next to each other), so a walk touches ONE region of a few hundred KB
+    size_t row_stride;           // floats between consecutive pixel rows
+    int plane_stride;            // floats between consecutive shifts of one row (the common row pitch of the tables)
     const float *g;              // window factor (FILTER only)
     int Na, Nw;
     int oy, ox;                  // raw coordinates of table element (0,0)
-    int rows_p, cols_p;          // padded table plane
-    int TH, TW;                  // output tile
-    int EH;                      // extended tile rows (ext cols are EXT_W)
+    int rows, cols_p;            // table rows (exact), padded columns (nstrips * TW)
+    int TW;                      // output columns per strip
+    int EH;                      // chunk rows (chunk columns are EXT_W)
+    int seg_rows, nseg, nstrips; // items: nstrips x nseg segments of seg_rows output rows (the last one may be shorter)
     int AH, AP;                  // A tile rows, pitch (= TMA box width)
     int G, npass, nstage;
     int a_stage_floats, stage_floats;   // per-stage layout: A tile then B tile (128 B aligned)
-    int tiles_x, tiles_y;               // tile grid (the kernel is persistent over it)
     int FB;                             // frames per TMA box / ring stage
     int dbg;                            // experiments only (UMPA_TAB_DBG): 1 = skip the epilogue, 2 = skip the FMA loop
 };
 
-constexpr int EXT_W = 32;          // extended tile width: one 128 B line per row
+constexpr int EXT_W = 32;          // chunk width: one 128 B line per row
 constexpr int MAX_NT = 384;        // threads per CTA (3 groups x 16 rows x 8 strips)
 constexpr int MAX_STAGES = 8;
 
@@ -100,17 +116,17 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     constexpr int NA4 = (DELTA + S + 3 + 3) / 4;     // float4 loads covering DELTA+S+3 floats of an A row
     constexpr bool FILTER = NWT >= 0;
     constexpr int K = FILTER ? 2 * NWT + 1 : 1;
+    constexpr int HALO = FILTER ? NWT : 0, H2 = 2 * HALO;
     __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
 
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int halo = FILTER ? NWT : 0;
     const int TG = p.EH * (EXT_W / 4);               // threads per group
     const int grp = tid / TG, lt = tid - grp * TG;
-    const int er = lt >> 3, ec = (lt & 7) << 2;      // strip: extended row, first extended column
+    const int er = lt >> 3, ec = (lt & 7) << 2;      // strip: chunk row, first chunk column
     float *cbuf = sm + (size_t)p.nstage * p.stage_floats;                // [G*S][EH][EXT_W] (FILTER only)
+    float *carry = cbuf + (size_t)p.G * S * p.EH * EXT_W;                // [S*S][H2][EXT_W] (FILTER, segments of > 1 chunk)
     const uint32_t stage_bytes = (uint32_t)(p.FB * (p.AH * p.AP + p.EH * EXT_W)) * sizeof(float);
     const int a_frame = p.AH * p.AP, b_frame = p.EH * EXT_W;             // one frame inside a stage
-    const size_t plane_sz = (size_t)p.rows_p * p.cols_p;
 
     float gk[K];
 #pragma unroll
@@ -122,23 +138,26 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     }
     __syncthreads();
 
-    // ---- persistent CTA: tiles blockIdx.x, +gridDim.x, ... ; the frame ring runs across tiles ----
-    const int ntiles = p.tiles_x * p.tiles_y;
-    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // ---- persistent CTA: items blockIdx.x, +gridDim.x, ... ; the frame ring runs across chunks and items ----
+    // item -> (strip, segment); neighbouring CTAs work on neighbouring strips at the same time (shared x halos in L2)
+    const int nitems = p.nstrips * p.nseg;
+    auto seg_rows_of = [&](int item) { const int r0 = (item / p.nstrips) * p.seg_rows; return min(p.seg_rows, p.rows - r0); };
+    auto chunks_of = [&](int rows) { return (rows + H2 + p.EH - 1) / p.EH; };
     // A ring stage holds FB consecutive frames (one TMA box per stack): a box costs ~450-500 cycles of
     // TMA-unit time whatever its size (measured: A only, B only and both take the same time with the FMA
     // loop and the epilogue switched off), so one box per frame capped the kernel at ~515 cycles per frame.
     const int nbox = (p.Na + p.FB - 1) / p.FB;       // boxes per pass over the frames (the last one may run past Na: zero fill)
-    const int per_tile = p.npass * nbox;
-    const int total = my_tiles * per_tile;
+    const int per_chunk = p.npass * nbox;
 
-    // producer state (thread 0): next (tile, frame) to request, and where
-    int pr_issued = 0, pr_tile = blockIdx.x, pr_left = per_tile, pr_frame = 0, pr_stage = 0;
+    // producer state (thread 0): next (item, chunk, frame) to request, and where
+    int total = 0, pr_issued = 0, pr_item = blockIdx.x, pr_chunks = 0, pr_left = per_chunk, pr_frame = 0, pr_stage = 0;
     int pr_ax = 0, pr_ay = 0, pr_bx = 0, pr_by = 0;
-    auto pr_coords = [&]() {
-        const int tyi = pr_tile / p.tiles_x, txi = pr_tile - tyi * p.tiles_x;
-        pr_by = p.oy + tyi * p.TH - halo; pr_bx = p.ox + txi * p.TW - halo;
+    auto pr_coords = [&]() {                         // first chunk of pr_item
+        if (pr_item >= nitems) return;
+        const int seg = pr_item / p.nstrips, strip = pr_item - seg * p.nstrips;
+        pr_by = p.oy + seg * p.seg_rows - HALO; pr_bx = p.ox + strip * p.TW - HALO;
         pr_ay = pr_by - HS; pr_ax = pr_bx - HS - DELTA;
+        pr_chunks = chunks_of(seg_rows_of(pr_item));
     };
     auto issue_next = [&]() {
         float *As = sm + (size_t)pr_stage * p.stage_floats, *Bs = As + p.a_stage_floats;
@@ -149,9 +168,14 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         if (++pr_stage == p.nstage) pr_stage = 0;
         pr_frame += p.FB;
         if (pr_frame >= p.Na) pr_frame = 0;
-        if (--pr_left == 0) { pr_left = per_tile; pr_tile += gridDim.x; pr_coords(); }
+        if (--pr_left == 0) {                        // next chunk of the item, or the next item
+            pr_left = per_chunk;
+            if (--pr_chunks > 0) { pr_by += p.EH; pr_ay += p.EH; }
+            else { pr_item += gridDim.x; pr_coords(); }
+        }
     };
     if (tid == 0) {
+        for (int it = blockIdx.x; it < nitems; it += gridDim.x) total += chunks_of(seg_rows_of(it)) * per_chunk;
         pr_coords();
         for (int n = 0; n < p.nstage && n < total; n++) issue_next();
     }
@@ -159,20 +183,37 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     int stage = 0, phase = 0;                        // consumer ring position
     int prev_stage = 0, prev_phase = 0;
     bool first = true;
-    float acc[SH][S][4];
+    // Accumulators of one thread: strip pixels x = 0..3, shift rows sh < SH, shift columns sj < S.  For the pixel
+    // pair (x0, x0+1), x0 = 2 xp, the FFMA2 pair t (1 <= t < S) holds (shift t of pixel x0, shift t-1 of pixel
+    // x0+1): both are fed by reference element DELTA + t + x0.  Shift 0 of x0 and shift S-1 of x0+1 have no
+    // partner (plain FFMA).  ACC(sh, sj, x) names the register of one (shift, pixel).
+    float2 accp[SH][2][S - 1];
+    float accs[SH][2][2];
+#define ACC(SH_, SJ_, PX_) (((PX_) & 1) ? ((SJ_) == S - 1 ? accs[SH_][(PX_) >> 1][1] : accp[SH_][(PX_) >> 1][(SJ_)].y) \
+                                        : ((SJ_) == 0 ? accs[SH_][(PX_) >> 1][0] : accp[SH_][(PX_) >> 1][(SJ_) - 1].x))
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int tyi = tile / p.tiles_x, txi = tile - tyi * p.tiles_x;
-        const int ty0 = tyi * p.TH, tx0 = txi * p.TW;                    // table coords of the tile
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int seg = item / p.nstrips, strip = item - seg * p.nstrips;
+      const int row0 = seg * p.seg_rows, tx0 = strip * p.TW;             // table coords of the item
+      const int item_rows = min(p.seg_rows, p.rows - row0), nchunk = chunks_of(item_rows);
+      for (int chunk = 0; chunk < nchunk; chunk++) {
+        // output row of this thread in this chunk: the column pass ends at its own chunk row (taps er-H2 .. er)
+        const int r_out = chunk * p.EH + er - H2;
+        const bool store = r_out >= 0 && r_out < item_rows && ec < p.TW;
+        // FILTER: the column pass works on groups of four chunk rows e4 .. e4+3 (output rows r_out4 .. r_out4+3)
+        const int e4 = er & ~3, r_out4 = chunk * p.EH + e4 - H2;
+        const bool any_store = r_out4 + 3 >= 0 && r_out4 < item_rows && ec < p.TW;
         for (int pass = 0; pass < p.npass; pass++) {
             const int si0 = (pass * p.G + grp) * SH; // first shift row of this thread in this pass
             const bool work = si0 < S;
 #pragma unroll
             for (int a = 0; a < SH; a++)
 #pragma unroll
-                for (int b = 0; b < S; b++)
+                for (int b = 0; b < 2; b++) {
 #pragma unroll
-                    for (int c = 0; c < 4; c++) acc[a][b][c] = 0.f;
+                    for (int c = 0; c < S - 1; c++) accp[a][b][c] = make_float2(0.f, 0.f);
+                    accs[a][b][0] = accs[a][b][1] = 0.f;
+                }
 
             for (int box = 0; box < nbox; box++) {
                 if (tid == 0 && !first && pr_issued < total) {           // refill the stage the previous box used
@@ -187,7 +228,7 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                     const float *As = sm + (size_t)stage * p.stage_floats + fr * a_frame;
                     const float *Bs = sm + (size_t)stage * p.stage_floats + p.a_stage_floats + fr * b_frame;
                     const float4 b4 = *reinterpret_cast<const float4 *>(Bs + er * EXT_W + ec);
-                    const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+                    const float2 bp[2] = {make_float2(b4.x, b4.y), make_float2(b4.z, b4.w)};
                     const float *arow0 = As + (er + si0) * p.AP + ec;
 #pragma unroll
                     for (int sh = 0; sh < SH; sh++) {
@@ -200,10 +241,15 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                                 av[4 * v] = t.x; av[4 * v + 1] = t.y; av[4 * v + 2] = t.z; av[4 * v + 3] = t.w;
                             }
 #pragma unroll
-                            for (int sj = 0; sj < S; sj++)
+                            for (int xp = 0; xp < 2; xp++) {
+                                accs[sh][xp][0] = fmaf(bp[xp].x, av[DELTA + 2 * xp], accs[sh][xp][0]);
 #pragma unroll
-                                for (int x = 0; x < 4; x++)
-                                    acc[sh][sj][x] = fmaf(bv[x], av[DELTA + sj + x], acc[sh][sj][x]);
+                                for (int t = 1; t < S; t++) {
+                                    const float a = av[DELTA + t + 2 * xp];
+                                    accp[sh][xp][t - 1] = __ffma2_rn(make_float2(a, a), bp[xp], accp[sh][xp][t - 1]);
+                                }
+                                accs[sh][xp][1] = fmaf(bp[xp].y, av[DELTA + S + 2 * xp], accs[sh][xp][1]);
+                            }
                         }
                     }
                   }
@@ -215,33 +261,35 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
             // ---------------- epilogue of this pass ----------------
             if (p.dbg & 1) {
-                if (work && tid == 0x7fffffff) p.table[0] = acc[0][0][0];      // keeps the accumulators alive
+                if (work && tid == 0x7fffffff) p.table[0] = ACC(0, 0, 0);      // keeps the accumulators alive
             } else if (!FILTER) {
-                if (work) {
+                if (work && store) {
 #pragma unroll
                     for (int sh = 0; sh < SH; sh++) {
                         const int si = si0 + sh;
-                        if (si < S && ec < p.TW) {
-                            float *dst = p.table + (size_t)(si * S) * plane_sz + (size_t)(ty0 + er) * p.cols_p + tx0 + ec;
+                        if (si < S) {
+                            float *dst = p.table + (size_t)(row0 + r_out) * p.row_stride + (size_t)(si * S) * p.plane_stride + tx0 + ec;
 #pragma unroll
                             for (int sj = 0; sj < S; sj++)
-                                *reinterpret_cast<float4 *>(dst + sj * plane_sz) =
-                                    make_float4(acc[sh][sj][0], acc[sh][sj][1], acc[sh][sj][2], acc[sh][sj][3]);
+                                *reinterpret_cast<float4 *>(dst + sj * p.plane_stride) =
+                                    make_float4(ACC(sh, sj, 0), ACC(sh, sj, 1), ACC(sh, sj, 2), ACC(sh, sj, 3));
                         }
                     }
                 }
             } else {
                 // Separable window filter, one shift row (S planes per group) at a time.
-                //  row pass: in registers; the 8 lanes of a quarter warp hold one extended row, output x
+                //  row pass: in registers; the 8 lanes of a quarter warp hold one chunk row, output x
                 //            needs columns x .. x+2Nw = own strip + the next NSH strips (shuffles; lanes past
                 //            the row end only feed outputs x >= TW, which are never stored);
-                //  column pass: through the group's slice of cbuf (conflict-free float4 lines), each thread
-                //            filters its own strip over rows er .. er+2Nw and stores one float4 of the table.
+                //  column pass: through the group's slice of cbuf (conflict-free float4 lines): each thread filters
+                //            its own strip over the chunk rows er-2Nw .. er and stores one float4 of the table; the
+                //            first 2Nw rows of a chunk reach back into the previous chunk's rows (carry);
+                //  carry:    the threads of the last 2Nw rows then copy their row-filtered strips to the carry.
                 // Only the 128 threads of a group share data: named barrier per group, no __syncthreads.
                 constexpr int NSH = (K - 1 + 3) / 4;
                 const int plane = p.EH * EXT_W;
                 float *cg = cbuf + (size_t)grp * S * plane + er * EXT_W + ec;
-                const bool store = er < p.TH && ec < p.TW;
+                const bool keep = chunk + 1 < nchunk && er >= p.EH - H2;
 #pragma unroll
                 for (int sh = 0; sh < SH; sh++) {
                     const int si = si0 + sh;
@@ -249,12 +297,11 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
                     for (int sj = 0; sj < S; sj++) {
                         float c[4 + 4 * NSH];
-#pragma unroll
-                        for (int x = 0; x < 4; x++) c[x] = acc[sh][sj][x];
+                        c[0] = ACC(sh, sj, 0); c[1] = ACC(sh, sj, 1); c[2] = ACC(sh, sj, 2); c[3] = ACC(sh, sj, 3);
 #pragma unroll
                         for (int d = 1; d <= NSH; d++)
 #pragma unroll
-                            for (int x = 0; x < 4; x++) c[4 * d + x] = __shfl_down_sync(0xffffffffu, acc[sh][sj][x], d, 8);
+                            for (int x = 0; x < 4; x++) c[4 * d + x] = __shfl_down_sync(0xffffffffu, c[x], d, 8);
                         float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                         for (int v = 0; v < K; v++)
@@ -263,25 +310,60 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                         *reinterpret_cast<float4 *>(cg + sj * plane) = make_float4(o[0], o[1], o[2], o[3]);
                     }
                     asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(TG) : "memory");
-                    if (store) {
-                        float *dst = p.table + (size_t)(si * S) * plane_sz + (size_t)(ty0 + er) * p.cols_p + tx0 + ec;
+                    // Column pass, FOUR output rows per thread: the four threads of a strip (chunk rows e4 .. e4+3,
+                    // one quarter warp each) share out the S planes, and each filters its planes for all four rows:
+                    // the H2+4 row-filtered lines an output group needs are read once (one LDS.128 per line and
+                    // strip) instead of once per output row -- 8 instead of 20 wavefronts per plane and warp for K = 5.
+                    if (any_store) {
+                        float *dst0 = p.table + (size_t)(row0 + r_out4) * p.row_stride + (size_t)(si * S) * p.plane_stride + tx0 + ec;
+                        const float *cw = cbuf + (size_t)grp * S * plane + ec;             // chunk rows of this group's planes
+                        const float *cr = carry + (size_t)(si * S) * (H2 * EXT_W) + ec;    // rows of the previous chunk
 #pragma unroll
-                        for (int sj = 0; sj < S; sj++) {
-                            float o[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int n = 0; n < (S + 3) / 4; n++) {
+                            const int sj = (er & 3) + 4 * n;
+                            if (sj >= S) break;
+                            float o[4][4];
 #pragma unroll
-                            for (int u = 0; u < K; u++) {
-                                const float4 t = *reinterpret_cast<const float4 *>(cg + sj * plane + u * EXT_W);
-                                o[0] = fmaf(gk[u], t.x, o[0]); o[1] = fmaf(gk[u], t.y, o[1]);
-                                o[2] = fmaf(gk[u], t.z, o[2]); o[3] = fmaf(gk[u], t.w, o[3]);
+                            for (int i = 0; i < 4; i++)
+#pragma unroll
+                                for (int x = 0; x < 4; x++) o[i][x] = 0.f;
+#pragma unroll
+                            for (int t = 0; t < H2 + 4; t++) {                             // chunk row e4 - H2 + t
+                                const int q = e4 + t;                                      // (row of [carry rows | chunk rows])
+                                // (rows above the first chunk of a segment only feed output rows that are not stored:
+                                //  any valid address will do -- there may be no carry buffer at all)
+                                const float *src = q >= H2 || chunk == 0 ? cw + sj * plane + max(q - H2, 0) * EXT_W
+                                                                         : cr + (sj * H2 + q) * EXT_W;
+                                const float4 v = *reinterpret_cast<const float4 *>(src);
+#pragma unroll
+                                for (int i = 0; i < 4; i++) {
+                                    const int u = t - i;                                   // tap of output row i
+                                    if (u >= 0 && u < K) {
+                                        o[i][0] = fmaf(gk[u], v.x, o[i][0]); o[i][1] = fmaf(gk[u], v.y, o[i][1]);
+                                        o[i][2] = fmaf(gk[u], v.z, o[i][2]); o[i][3] = fmaf(gk[u], v.w, o[i][3]);
+                                    }
+                                }
                             }
-                            *reinterpret_cast<float4 *>(dst + sj * plane_sz) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+                            for (int i = 0; i < 4; i++)
+                                if (r_out4 + i >= 0 && r_out4 + i < item_rows)
+                                    *reinterpret_cast<float4 *>(dst0 + (size_t)i * p.row_stride + sj * p.plane_stride) =
+                                        make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
                         }
                     }
                     asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(TG) : "memory");
+                    if (H2 > 0 && keep) {                        // (after the barrier: the readers of the old carry are done)
+                        float *cr = carry + ((size_t)(si * S) * H2 + (er - (p.EH - H2))) * EXT_W + ec;
+#pragma unroll
+                        for (int sj = 0; sj < S; sj++)
+                            *reinterpret_cast<float4 *>(cr + sj * (H2 * EXT_W)) = *reinterpret_cast<const float4 *>(cg + sj * plane);
+                    }
                 }
             }
         }
+      }
     }
+#undef ACC
 }
 
 // compile-time choice of the per-thread shift-row block: keeps SH*S*4 accumulators <= ~120

@@ -334,14 +334,16 @@ template <int NW> size_t moments_smem()
 // ------------------------------------------------------------------ table-driven walk
 
 struct WalkParams {
-    const float *tabX, *tabM;       // cross / mean tables; tabM nullptr for NoDF
+    const float *tabX;              // the tables: entry (row, shift, col) of the cross table at
+                                    // tabX[row * row_stride + shift * tpitch + col], of the mean table (DF) m_off floats
+                                    // further (shift_table.cuh: TableParams)
+    size_t row_stride;
+    int tpitch, m_off;
     const AuxS *auxS;               // [H][pitch], raw coordinates
     const AuxR *auxR;
     int pitch;
-    int rowsX, colsX, rowsM, colsM; // padded plane geometry of the two tables
-    unsigned planeX, planeM;        // rows * cols
     int oy, ox;                     // raw coords of output pixel (0,0) of the dense region
-    int dxX, dxM;                   // column of that pixel inside the cross / mean table (TMA alignment shift)
+    int dxX;                        // column of that pixel inside the cross table (TMA alignment shift)
     int Na, max_shift, subpx;
     double sw;                      // sum of window
     const double *consts;           // device: sum_k c_k d_k, c_k^2, d_k^2
@@ -365,10 +367,10 @@ struct TableEval {
     AuxR pr;                        // reference record: at the pixel (RS) -- or the last one fetched at p + s (!RS)
     const AuxS *pS;                 // RS: the sample's aux image at this pixel (shift 0)
     const AuxR *pR;                 // !RS: the reference's aux image at this pixel
-    const float *pX, *pM;           // this pixel in plane 0 of the cross / mean table (DFKernel: pX = its table row)
+    const float *pX;                // this pixel at shift 0 of the cross table (DFKernel: its table row)
     double sig, k5, k3;             // DFKernel: sigma, sigma swk sum c_k d_k, sigma^2 swk sum c_k^2
 
-    __device__ static int out_of_bounds(int si, int sj, int ms)      // error_status bits of Model.cpp:654-681 (cold path)
+    __device__ __noinline__ static int out_of_bounds(int si, int sj, int ms)      // error_status bits of Model.cpp:654-681 (cold path)
     {
         if (si <= -ms || si >= ms) return UMPA_ST_BOUND;
         if (sj <= -ms) return UMPA_ST_BOUND | UMPA_ST_DIM;
@@ -397,9 +399,10 @@ struct TableEval {
             cst = (ps.t1 - t5 * args.t) * w.inv_Na;
             return UMPA_ST_OK;
         }
-        // the gathers of one evaluation: one aux record + one entry per table (plane sizes fit 32 bits)
-        const float x = __ldg(pX + (size_t)sidx * w.planeX);
-        const float m = KIND == UMPA_DF ? __ldg(pM + (size_t)sidx * w.planeM) : 0.f;
+        // the gathers of one evaluation: one aux record + one entry per table, a fixed distance apart
+        const float *px = pX + sidx * (unsigned)w.tpitch;
+        const float x = __ldg(px);
+        const float m = KIND == UMPA_DF ? __ldg(px + w.m_off) : 0.f;
         if (RS) {
             const double2 v = __ldg(reinterpret_cast<const double2 *>(pS + q));
             ps.t1 = v.x; ps.V = v.y;
@@ -430,7 +433,7 @@ struct TableEval {
 
 constexpr int WALK_NT = 128;
 #ifndef WALK_MINB
-#define WALK_MINB 6
+#define WALK_MINB 7
 #endif
 
 // d (the 5x5 cost cache) lives in shared memory, one column per thread: dynamic indexing
@@ -468,24 +471,22 @@ __global__ void __launch_bounds__(WALK_NT, WALK_MINB) table_walk_kernel(WalkPara
     if (KIND == UMPA_DFKERNEL) {
         const int S = 2 * w.max_shift - 1;
         eval.pX = w.ktab + n * (size_t)w.kstride;
-        eval.pM = nullptr;
         eval.sig = 1. + (double)__ldg(eval.pX + 2 * S * S);
         eval.k5 = eval.sig * w.swk * __ldg(w.consts);
         eval.k3 = eval.sig * eval.sig * w.swk * __ldg(w.consts + 1);
     } else {
-        eval.pX = w.tabX + (size_t)ty * w.colsX + tx + w.dxX;
-        eval.pM = KIND == UMPA_DF ? w.tabM + (size_t)ty * w.colsM + tx + w.dxM : nullptr;
+        eval.pX = w.tabX + (size_t)ty * w.row_stride + tx + w.dxX;
     }
     FitArgs args{0., 0.};
     SharedGrid d{&d_sm[0][threadIdx.x]};
-    double a[16], uv[2] = {roi.uv0[0], roi.uv0[1]}, f = 0.;
+    double uv[2] = {roi.uv0[0], roi.uv0[1]}, f = 0.;
     int ncalls;
-    WalkCache wc;
-#pragma unroll
-    for (int t = 0; t < 16; t++) a[t] = 0.;
-    const int st = walk_minimise(eval, w.subpx, w.quad, args, f, uv, d, a, ncalls, wc);
+    WalkState ws;
+    const int st = walk_search(eval, args, f, uv, d, ncalls, ws);
+    store_debug(out, n, d, ws);                    // (before the fit: it reuses the cache's cells)
+    if (ws.finished) walk_refine(w.subpx, w.quad, d, ws, f, uv);
     if (KIND == UMPA_DF && args.t != 0.) args.v = args.v / args.t;
-    store_pixel(out, n, KIND, st, f, args, uv, d, wc, a, ncalls, true);
+    store_pixel(out, n, KIND, st, f, args, uv, ncalls);
 }
 
 template <bool RS>
@@ -586,60 +587,87 @@ int row_block_of(int S) { return S <= 9 ? 3 : (S <= 17 ? 2 : 1); }
 
 int ctas_per_sm() { const char *e = getenv("UMPA_TAB_CTAS"); return e ? std::max(1, atoi(e)) : 1; }
 
-// Tile geometry of one table kernel.  Returns dynamic smem bytes (0 = unsupported) and the block size.
-size_t plan_tiles(TableParams &p, int S, bool filter, int *nt)
+// Geometry of one table kernel: chunk height, warp groups, frame ring, and how the table is cut into items (column
+// strips x row segments, shift_table.cuh).  Returns dynamic smem bytes (0 = unsupported) and the block size.
+size_t plan_tiles(TableParams &p, int S, bool filter, int *nt, int rows, int cols, int ctas)
 {
-    const int HS = (S - 1) / 2, halo = filter ? p.Nw : 0;
+    const int HS = (S - 1) / 2, halo = filter ? p.Nw : 0, H2 = 2 * halo;
     const int delta = (4 - HS % 4) % 4;
     const int NA4 = (delta + S + 3 + 3) / 4, SH = row_block_of(S);
-    p.TW = (EXT_W - 2 * halo) & ~3;
+    p.TW = (EXT_W - H2) & ~3;
     if (p.TW < 8) return 0;
-    // Extended tile height (EH rows x 8 strips = EH*8 threads per group).  A tall tile wastes less on the window
-    // halo (TH/EH) but leaves room for fewer groups, i.e. more passes over the frames.  Cost model fitted to
-    // measurements (config 5, Nw=6: EH 16/24/32/48 -> 2.14/1.20/1.19/1.02 ms; config 4, Nw=3, S=15: 16/24 ->
-    // 28.9/24.8 ms; config 2 stays at 16): rows computed per useful row, +15 % per extra pass.
-    p.EH = 16;
-    if (filter) {
-        double best = 1e30;
-        for (int eh : {16, 24, 32, 48}) {
-            if (eh - 2 * halo < 2) continue;
-            const int g = std::min(MAX_NT / (eh * 8), (S + SH - 1) / SH);
-            const int np = (S + g * SH - 1) / (g * SH);
-            const double cost = (double)eh / (eh - 2 * halo) * (1. + .15 * (np - 1));
-            if (cost < best - 1e-9) { best = cost; p.EH = eh; }
-        }
-    }
-    if (const char *e = getenv("UMPA_TAB_EH")) p.EH = atoi(e);          // tuning knobs (experiments only)
-    p.TH = p.EH - 2 * halo;
-    if (p.TH < 2) return 0;
-    p.G = std::min(MAX_NT / (p.EH * 8), (S + SH - 1) / SH);
-    if (const char *e = getenv("UMPA_TAB_G")) p.G = std::min(p.G, atoi(e));
-    p.npass = (S + p.G * SH - 1) / (p.G * SH);
-    p.AH = p.EH + 2 * HS;
+    p.rows = rows;
+    p.nstrips = (cols + p.TW - 1) / p.TW;
+    p.cols_p = p.nstrips * p.TW;
     p.AP = EXT_W - 4 + 4 * NA4;
-    *nt = p.G * p.EH * 8;
     auto up32 = [](int floats) { return (floats + 31) & ~31; };      // 128 B
-    const size_t cbuf = filter ? (size_t)p.G * S * p.EH * EXT_W * sizeof(float) : 0;
     const size_t budget = SMEM_CAP - 2048;
-    // frames per TMA box = per ring stage (see shift_table.cuh: a box costs the same TMA time whatever its
-    // size): split the Na frames into the fewest boxes of at most 9 frames, as long as 3 stages fit
-    // (2 at least).  Measured on config 2: FB 1 / 2 / 5 / 9 -> cross table 1.51 / 1.22 / 1.08 / 1.04 ms.
-    const int nboxes = (p.Na + 8) / 9;
-    p.FB = (p.Na + nboxes - 1) / nboxes;
-    if (const char *e = getenv("UMPA_TAB_FB")) p.FB = std::max(1, std::min(32, atoi(e)));
-    p.FB = std::max(1, std::min(p.FB, p.Na));
-    int ns = 0;
-    for (;; p.FB--) {
-        p.a_stage_floats = up32(p.FB * p.AH * p.AP);
-        p.stage_floats = p.a_stage_floats + up32(p.FB * p.EH * EXT_W);
-        ns = budget > cbuf ? (int)((budget - cbuf) / ((size_t)p.stage_floats * sizeof(float))) : 0;
-        if (ns >= 3 || p.FB == 1 || (ns >= 2 && p.FB <= 4)) break;
-    }
-    if (ns < 2) return 0;
-    p.nstage = std::min(ns, p.FB >= 4 ? 4 : MAX_STAGES);
+    // Candidates: chunk height EH (a tall chunk leaves room for fewer warp groups, i.e. more passes over the
+    // frames) x streaming or not.  STREAMING keeps the last 2*halo row-filtered rows of every shift plane in shared
+    // memory for the next chunk of the segment, so no chunk row is wasted on the window halo; without it every
+    // segment is one chunk and EH - 2*halo of its EH rows are outputs.  Cost model fitted to measurements: rows
+    // computed per useful row, +15 % per extra pass over the frames, and the TMA box cost (a box takes the same
+    // TMA time whatever its depth FB; config 2, FB 1 / 2 / 5 / 9 -> 1.51 / 1.22 / 1.08 / 1.04 ms ~ 1 + 0.5 / FB).
+    double best = 1e30;
+    TableParams bp = p;
+    size_t best_smem = 0;
+    const char *e_eh = getenv("UMPA_TAB_EH"), *e_st = getenv("UMPA_TAB_STREAM"), *e_fb = getenv("UMPA_TAB_FB"), *e_g = getenv("UMPA_TAB_G");
+    for (int eh : {16, 24, 32, 48})
+        for (int stream = (filter && halo > 0) ? 1 : 0; stream >= 0; stream--) {
+            if (e_eh && atoi(e_eh) != eh) continue;
+            if (e_st && filter && halo > 0 && atoi(e_st) != stream) continue;
+            if (!stream && eh - H2 < 2) continue;
+            TableParams q = p;
+            q.EH = eh;
+            q.G = std::min(MAX_NT / (eh * 8), (S + SH - 1) / SH);
+            if (e_g) q.G = std::max(1, std::min(q.G, atoi(e_g)));
+            if (q.G < 1) continue;
+            q.npass = (S + q.G * SH - 1) / (q.G * SH);
+            q.AH = eh + 2 * HS;
+            const size_t cbuf = filter ? (size_t)q.G * S * eh * EXT_W * sizeof(float) : 0;
+            const size_t carry = stream ? (size_t)S * S * H2 * EXT_W * sizeof(float) : 0;
+            if (cbuf + carry >= budget) continue;
+            // frames per TMA box = per ring stage: the fewest boxes of at most 9 frames, as long as 3 stages fit (2 at least)
+            const int nboxes = (p.Na + 8) / 9;
+            q.FB = (p.Na + nboxes - 1) / nboxes;
+            if (e_fb) q.FB = std::max(1, std::min(32, atoi(e_fb)));
+            q.FB = std::max(1, std::min(q.FB, p.Na));
+            int ns = 0;
+            for (;; q.FB--) {
+                q.a_stage_floats = up32(q.FB * q.AH * q.AP);
+                q.stage_floats = q.a_stage_floats + up32(q.FB * eh * EXT_W);
+                ns = (int)((budget - cbuf - carry) / ((size_t)q.stage_floats * sizeof(float)));
+                if (ns >= 3 || q.FB == 1 || (ns >= 2 && q.FB <= 4)) break;
+            }
+            if (ns < 2) continue;
+            q.nstage = std::min(ns, q.FB >= 4 ? 4 : MAX_STAGES);
+            const double cost = (stream ? 1. : (double)eh / (eh - H2)) * (1. + .15 * (q.npass - 1)) * (1. + .5 / q.FB);
+            if (cost < best - 1e-9) {
+                best = cost; bp = q;
+                bp.seg_rows = stream ? 0 : eh - H2;              // streaming: chosen below
+                best_smem = (size_t)q.nstage * q.stage_floats * sizeof(float) + cbuf + carry;
+            }
+        }
+    if (!best_smem) return 0;
+    p = bp;
     if (const char *e = getenv("UMPA_TAB_DBG")) p.dbg = atoi(e);
-    if (const char *e = getenv("UMPA_TAB_NST")) p.nstage = std::max(2, std::min(ns, atoi(e)));
-    return (size_t)p.nstage * p.stage_floats * sizeof(float) + cbuf;
+    if (const char *e = getenv("UMPA_TAB_NST")) p.nstage = std::max(2, std::min(p.nstage, atoi(e)));
+    if (p.seg_rows == 0) {
+        // streaming: segments per strip such that the slowest CTA has the fewest chunks (every segment pays the
+        // window halo once; every CTA works through ceil(items / ctas) items)
+        long best_span = -1;
+        int best_n = 1;
+        for (int n = 1; n <= std::max(1, rows / p.EH); n++) {
+            const int sr = (rows + n - 1) / n, nseg = (rows + sr - 1) / sr;
+            const long waves = ((long)p.nstrips * nseg + ctas - 1) / ctas, chunks = (sr + H2 + p.EH - 1) / p.EH;
+            if (best_span < 0 || waves * chunks < best_span) { best_span = waves * chunks; best_n = n; }
+        }
+        if (const char *e = getenv("UMPA_TAB_NSEG")) best_n = std::max(1, atoi(e));
+        p.seg_rows = (rows + best_n - 1) / best_n;
+    }
+    p.nseg = (rows + p.seg_rows - 1) / p.seg_rows;
+    *nt = p.G * p.EH * 8;
+    return best_smem;
 }
 
 }  // namespace
@@ -781,16 +809,18 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         if (!roi.abc) { umpa_set_error("abc array has to be provided"); return UMPA_ERR_ARG; }
         if ((rc = scratch_reserve(m, m->tabX, (size_t)roi.N0 * roi.N1 * ktable_row_floats(m->max_shift) * sizeof(float)))) return rc;
     } else {
-        smx = plan_tiles(px, S, true, &ntx);
-        smm = df ? plan_tiles(pm, S, false, &ntm) : 1;
+        const int ctas = m->sm_count * ctas_per_sm();
+        smx = plan_tiles(px, S, true, &ntx, rows, cols + dxX, ctas);
+        smm = df ? plan_tiles(pm, S, false, &ntm, rows, cols + dxM, ctas) : 1;
         if (!smx || !smm) { umpa_set_error("table path: tile does not fit shared memory"); return UMPA_ERR_UNSUPPORTED; }
-        auto padded = [](int n, int t) { return t * ((n + t - 1) / t); };
-        px.rows_p = padded(rows, px.TH); px.cols_p = padded(cols + dxX, px.TW);
-        if ((rc = scratch_reserve(m, m->tabX, (size_t)S * S * px.rows_p * px.cols_p * sizeof(float)))) return rc;
-        if (df) {
-            pm.rows_p = padded(rows, pm.TH); pm.cols_p = padded(cols + dxM, pm.TW);
-            if ((rc = scratch_reserve(m, m->tabM, (size_t)S * S * pm.rows_p * pm.cols_p * sizeof(float)))) return rc;
-        }
+        const int rows_alloc = rows;
+        int tpitch = px.cols_p;
+        if (df) tpitch = std::max(tpitch, pm.cols_p);
+        // one buffer, [row][table][shift][col]: everything a pixel's walk reads lies within one row's S*S
+        // (2 S*S for DF) segments -- a few hundred KB -- instead of S*S planes of the image size
+        px.plane_stride = pm.plane_stride = tpitch;
+        px.row_stride = pm.row_stride = (size_t)(df ? 2 : 1) * S * S * tpitch;
+        if ((rc = scratch_reserve(m, m->tabX, (size_t)rows_alloc * px.row_stride * sizeof(float)))) return rc;
     }
     const size_t img = (size_t)H * pitch;
     if ((rc = scratch_reserve(m, m->auxS, img * sizeof(AuxS)))) return rc;
@@ -837,8 +867,7 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         if ((rc = make_stack_map(&ma, mov, Na, H, m->W, pitch, px.AP, px.AH, px.FB))) return rc;
         if ((rc = make_stack_map(&mb, fix, Na, H, m->W, pitch, EXT_W, px.EH, px.FB))) return rc;
         px.table = (float *)m->tabX.p;
-        px.tiles_x = px.cols_p / px.TW; px.tiles_y = px.rows_p / px.TH;
-        dim3 grid(std::min(px.tiles_x * px.tiles_y, m->sm_count * ctas_per_sm()));
+        dim3 grid(std::min(px.nstrips * px.nseg, m->sm_count * ctas_per_sm()));
         if ((rc = dispatch_shift_table(true, S, ma, mb, px, grid, ntx, smx, st))) return rc;
         m->last_launches++;
         if ((rc = stage_check("cross table", st))) return rc;
@@ -852,9 +881,8 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         const float *fix = (const float *)(m->refshift ? m->filtA.p : m->filtB.p);
         if ((rc = make_stack_map(&ma, mov, Na, H, m->W, pitch, pm.AP, pm.AH, pm.FB))) return rc;
         if ((rc = make_stack_map(&mb, fix, Na, H, m->W, pitch, EXT_W, pm.EH, pm.FB))) return rc;
-        pm.table = (float *)m->tabM.p;
-        pm.tiles_x = pm.cols_p / pm.TW; pm.tiles_y = pm.rows_p / pm.TH;
-        dim3 grid(std::min(pm.tiles_x * pm.tiles_y, m->sm_count * ctas_per_sm()));
+        pm.table = (float *)m->tabX.p + (size_t)S * S * pm.plane_stride;
+        dim3 grid(std::min(pm.nstrips * pm.nseg, m->sm_count * ctas_per_sm()));
         if ((rc = dispatch_shift_table(false, S, ma, mb, pm, grid, ntm, smm, st))) return rc;
         m->last_launches++;
         if ((rc = stage_check("mean table", st))) return rc;
@@ -864,7 +892,9 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
     // 4. walk
     {
         WalkParams w{};
-        w.tabX = (const float *)m->tabX.p; w.tabM = df ? (const float *)m->tabM.p : nullptr;
+        w.tabX = (const float *)m->tabX.p;
+        w.row_stride = px.row_stride; w.tpitch = px.plane_stride;
+        w.m_off = S * S * px.plane_stride + dxM - dxX;
         if (dfk) {
             w.ktab = w.tabX; w.kstride = ktable_row_floats(m->max_shift);
             double swk = 0.;                           // exact sum of float(g_a) * float(g_b) as FP32 products
@@ -873,9 +903,8 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
             w.swk = swk;
         }
         w.auxS = (const AuxS *)m->auxS.p; w.auxR = (const AuxR *)m->auxR.p;
-        w.pitch = pitch; w.rowsX = px.rows_p; w.colsX = px.cols_p; w.rowsM = pm.rows_p; w.colsM = pm.cols_p;
-        w.planeX = (unsigned)px.rows_p * (unsigned)px.cols_p; w.planeM = (unsigned)pm.rows_p * (unsigned)pm.cols_p;
-        w.oy = oy; w.ox = ox; w.dxX = dxX; w.dxM = dxM;
+        w.pitch = pitch;
+        w.oy = oy; w.ox = ox; w.dxX = dxX;
         w.Na = Na; w.max_shift = m->max_shift; w.subpx = m->subpx;
         w.sw = m->win_sum; w.quad = m->d_quad;
         w.inv_sw = 1. / w.sw; w.inv_Na = 1. / (double)Na;

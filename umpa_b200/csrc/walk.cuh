@@ -4,6 +4,11 @@
 // spmin (Optim.cpp:41-130) and spmin_quad (Optim.cpp:155-185) for one CUDA thread per
 // pixel.  The cost function is a functor, so the same state machine runs on top of the
 // lazy FP64 evaluator (lazy_path.cu) and of the FP32 shift tables (table_path.cu).
+//
+// Two steps, so that a kernel can store the debug arrays in between and the refinement can reuse
+// the cache's storage:
+//   walk_search()   the integer walk; leaves the 5x5 cost cache and where the 4x4 block lies
+//   walk_refine()   the sub-pixel fit on that block (spline / quadratic / none)
 #pragma once
 #include "common.cuh"
 
@@ -11,45 +16,81 @@ struct FitArgs {            // what the reference keeps in CostArgs{NoDF,DF,DFKe
     double t, v;
 };
 
-// ---- cubic B-spline surface through a 4x4 block -----------------------------------
-// f(x,y) = sum_ij B_i(x) B_j(y) a[4i+j] / 36 with x along rows; B_* are the four uniform
-// cubic B-spline pieces on [0,1] for samples at -1,0,1,2.  BSPL[n][s]: coefficient of t^n
-// of piece s, times 6.
-__device__ __forceinline__ double bspl_coef(int n, int s)
+// ---- the cost cache -----------------------------------------------------------------------
+// The reference keeps d, a 5x5 cache of costs centred on the current integer shift (row-major, centre 12,
+// -1 = not evaluated), and physically shifts it by one row / column on every step.  Here the cache is a
+// RING: the 25 storage cells are addressed modulo 5 from an origin (b0, b1) that moves with the centre, and
+// which cells hold an evaluated cost is a 25-bit register mask in the reference's (logical) order -- a step
+// rotates the mask and moves the origin, nothing is copied and nothing has to be initialised.
+// walk_cache_get() reads the cache the way the reference would have left it.
+// Grid: anything indexable by [int] yielding double& (a local array, or a shared-memory column).
+struct WalkState {
+    unsigned known;                 // bit 5 r + c: logical entry (r, c) holds an evaluated cost
+    int b0, b1;                     // storage row / column of logical row / column 0
+    int c0, c1;                     // the integer shift the walk ended on (row, column)
+    int ip, jp;                     // corner of the 4x4 block inside the 5x5 cache (Optim.cpp:344-345)
+    bool finished;                  // minimum bracketed on both axes: the 4x4 block is complete
+};
+
+__device__ __forceinline__ int walk_cell(int b0, int b1, int r, int c)
 {
-    // {1,4,1,0}, {-3,0,3,0}, {3,-6,3,0}, {-1,3,-3,1}
-    const int tab[16] = {1, 4, 1, 0, -3, 0, 3, 0, 3, -6, 3, 0, -1, 3, -3, 1};
-    return (double)tab[4 * n + s];
+    int pr = b0 + r, pc = b1 + c;
+    pr = pr >= 5 ? pr - 5 : pr;
+    pc = pc >= 5 ? pc - 5 : pc;
+    return 5 * pr + pc;
 }
 
-__device__ inline double subpixel_spline(const double *a, double *pos)
+// logical entry n (0..24) of the cache as the reference holds it: the cost, or -1 when not evaluated
+template <class Grid>
+__device__ __forceinline__ double walk_cache_get(Grid d, const WalkState &ws, int n)
 {
-    // c[4m+n] multiplies x^n y^m
-    double tmp[16], c[16];
+    const int r = (n * 13) >> 6;                   // n / 5 for n < 64
+    return ((ws.known >> n) & 1u) ? d[walk_cell(ws.b0, ws.b1, r, n - 5 * r)] : -1.;
+}
+
+// entry (r, q) of the 4x4 block the sub-pixel fit works on (minimizer_debug.a, Optim.cpp:349-384)
+template <class Grid>
+__device__ __forceinline__ double walk_block_get(Grid d, const WalkState &ws, int r, int q)
+{
+    return d[walk_cell(ws.b0, ws.b1, ws.ip + r, ws.jp + q)];
+}
+
+// ---- cubic B-spline surface through the 4x4 block -----------------------------------
+// f(x,y) = sum_ij B_i(x) B_j(y) a[4i+j] / 36 with x along rows; B_* are the four uniform
+// cubic B-spline pieces on [0,1] for samples at -1,0,1,2; times 6 their coefficients are
+//     t^0: {1, 4, 1, 0}   t^1: {-3, 0, 3, 0}   t^2: {3, -6, 3, 0}   t^3: {-1, 3, -3, 1}
+// The 16 polynomial coefficients c[4m+n] (of x^n y^m) are built column by column of the block -- four block
+// entries in registers at a time -- and then live in the cache's own storage cells 0..15 (the block is not needed
+// any more; a kernel that reports the cache stores it BEFORE the refinement): the Newton iteration reads them back
+// row by row, so the fit needs ~50 registers instead of the ~100 of block + coefficients in registers.
+template <class Grid>
+__device__ inline double subpixel_spline(Grid d, const WalkState &ws, double *pos)
+{
+    double c[16];
 #pragma unroll
-    for (int n = 0; n < 4; n++)
+    for (int n = 0; n < 16; n++) c[n] = 0.;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            double s = 0.;
+    for (int j = 0; j < 4; j++) {
+        const double a0 = walk_block_get(d, ws, 0, j), a1 = walk_block_get(d, ws, 1, j);
+        const double a2 = walk_block_get(d, ws, 2, j), a3 = walk_block_get(d, ws, 3, j);
+        // x-powers of column sample j
+        const double t[4] = {a0 + 4. * a1 + a2, 3. * (a2 - a0), 3. * (a0 + a2) - 6. * a1, (a3 - a0) + 3. * (a1 - a2)};
+        const double B[4][4] = {{1., 4., 1., 0.}, {-3., 0., 3., 0.}, {3., -6., 3., 0.}, {-1., 3., -3., 1.}};
 #pragma unroll
-            for (int i = 0; i < 4; i++) s += bspl_coef(n, i) * a[4 * i + j];
-            tmp[4 * n + j] = s;               // x-power n, column sample j
+        for (int m = 0; m < 4; m++) {
+            if (B[m][j] == 0.) continue;
+#pragma unroll
+            for (int n = 0; n < 4; n++) c[4 * m + n] += B[m][j] * t[n];
         }
+    }
 #pragma unroll
-    for (int m = 0; m < 4; m++)
-#pragma unroll
-        for (int n = 0; n < 4; n++) {
-            double s = 0.;
-#pragma unroll
-            for (int j = 0; j < 4; j++) s += bspl_coef(m, j) * tmp[4 * n + j];
-            c[4 * m + n] = s;
-        }
+    for (int n = 0; n < 16; n++) d[n] = c[n];
     double x = pos[0], y = pos[1];
     for (int it = 0; it <= 20; it++) {
         double A[4], A1[4], A2[4];
 #pragma unroll
         for (int m = 0; m < 4; m++) {
-            const double c0 = c[4 * m], c1 = c[4 * m + 1], c2 = c[4 * m + 2], c3 = c[4 * m + 3];
+            const double c0 = d[4 * m], c1 = d[4 * m + 1], c2 = d[4 * m + 2], c3 = d[4 * m + 3];
             A[m] = c0 + x * (c1 + x * (c2 + x * c3));
             A1[m] = c1 + x * (2. * c2 + 3. * x * c3);
             A2[m] = 2. * c2 + 6. * x * c3;
@@ -71,25 +112,25 @@ __device__ inline double subpixel_spline(const double *a, double *pos)
     double f = 0., yp = 1.;
 #pragma unroll
     for (int m = 0; m < 4; m++) {
-        f += yp * (c[4 * m] + x * (c[4 * m + 1] + x * (c[4 * m + 2] + x * c[4 * m + 3])));
+        f += yp * (d[4 * m] + x * (d[4 * m + 1] + x * (d[4 * m + 2] + x * d[4 * m + 3])));
         yp *= y;
     }
     return f / 36.;
 }
 
-// ---- least-squares quadratic through a 4x4 block ------------------------------------
+// ---- least-squares quadratic through the 4x4 block ------------------------------------
 // p = 400 * pinv(A) a for the basis [1, i, j, i^2, ij, j^2] on i,j in {-1,0,1,2}
 // (i along rows).  The 6x16 integer matrix is 400*(A^T A)^-1 A^T, generated on the host
 // when a model is created (quad_matrix in capi.cu) and passed in as `quad` (device memory).
-__device__ inline double subpixel_quadratic(const double *__restrict__ c_quad, const double *a, double *pos)
+template <class Grid>
+__device__ inline double subpixel_quadratic(const double *__restrict__ c_quad, Grid d, const WalkState &ws, double *pos)
 {
-    double p[6];
+    double p[6] = {0., 0., 0., 0., 0., 0.};
 #pragma unroll
-    for (int r = 0; r < 6; r++) {
-        double s = 0.;
+    for (int n = 0; n < 16; n++) {
+        const double a = walk_block_get(d, ws, n >> 2, n & 3);
 #pragma unroll
-        for (int n = 0; n < 16; n++) s += c_quad[16 * r + n] * a[n];
-        p[r] = s;
+        for (int r = 0; r < 6; r++) p[r] += c_quad[16 * r + n] * a;
     }
     const double det = 4. * p[3] * p[5] - p[4] * p[4];
     // reference quirk kept: pos[0] gets the column solution, pos[1] the row solution
@@ -99,12 +140,6 @@ __device__ inline double subpixel_quadratic(const double *__restrict__ c_quad, c
 }
 
 // ---- the walk --------------------------------------------------------------------------
-// The reference keeps d, a 5x5 cache of costs centred on the current integer shift (row-major, centre 12,
-// -1 = not evaluated), and physically shifts it by one row / column on every step.  Here the cache is a
-// RING: the 25 storage cells are addressed modulo 5 from an origin (b0, b1) that moves with the centre, and
-// which cells hold an evaluated cost is a 25-bit register mask in the reference's (logical) order -- a step
-// rotates the mask and moves the origin, nothing is copied and nothing has to be initialised.
-// walk_cache_get() reads the cache the way the reference would have left it.
 // axis 0 scans the column shift, axis 1 the row shift.  `keep` is the reference's args_copy: the fit
 // parameters of the best shift seen so far -- deliberately NOT refreshed on a restart (Optim.cpp:364-377),
 // which the reference's outputs depend on.
@@ -117,33 +152,11 @@ __device__ inline double subpixel_quadratic(const double *__restrict__ c_quad, c
 // evaluations per pixel -- and therefore Ncalls, d, the 4x4 block and every tie decision --
 // is exactly the reference's.
 // Eval: int operator()(int si, int sj, double &cost, FitArgs &args) -> error_status bits.
-// Grid: anything indexable by [int] yielding double& (a local array, or a shared-memory column).
-struct WalkCache {
-    unsigned known;                 // bit 5 r + c: logical entry (r, c) holds an evaluated cost
-    int b0, b1;                     // storage row / column of logical row / column 0
-};
-
-__device__ __forceinline__ int walk_cell(int b0, int b1, int r, int c)
-{
-    int pr = b0 + r, pc = b1 + c;
-    pr = pr >= 5 ? pr - 5 : pr;
-    pc = pc >= 5 ? pc - 5 : pc;
-    return 5 * pr + pc;
-}
-
-// logical entry n (0..24) of the cache as the reference holds it: the cost, or -1 when not evaluated
-template <class Grid>
-__device__ __forceinline__ double walk_cache_get(Grid d, const WalkCache &wc, int n)
-{
-    const int r = (n * 13) >> 6;                   // n / 5 for n < 64
-    return ((wc.known >> n) & 1u) ? d[walk_cell(wc.b0, wc.b1, r, n - 5 * r)] : -1.;
-}
-
+// Returns the error_status bits; on UMPA_ST_OK with ws.finished the caller runs walk_refine().
 template <class Eval, class Grid>
-__device__ inline int walk_minimise(Eval &eval, int subpx, const double *quad, FitArgs &args, double &out,
-                                    double *uv, Grid d, double *a, int &ncalls, WalkCache &wc)
+__device__ inline int walk_search(Eval &eval, FitArgs &args, double &out, double *uv, Grid d, int &ncalls, WalkState &ws)
 {
-    enum { R_CENTRE, R_LO, R_HI, R_FILL };         // what the pending evaluation is for
+    enum { R_CENTRE = 1, R_LO = 2, R_HI = 4, R_FILL = 8 };    // what the pending evaluation is for
     const double tol = 1e-8;                       // absolute, Optim.cpp:243
     constexpr unsigned COL0 = 0x108421u, COL4 = 0x1084210u, ALL = 0x1ffffffu;
     int settled0 = 0, settled1 = 0, axis = 0, st = UMPA_ST_OK;
@@ -169,14 +182,19 @@ __device__ inline int walk_minimise(Eval &eval, int subpx, const double *quad, F
             c0 += sr - 2; c1 += sc - 2;
             sr = sc = 2;
             known = 0;
-            args = keep;
+            args = keep;                           // (keep is NOT refreshed: see above)
             settled0 = settled1 = 0;
             skip_limit = true;
             fill = false;
-            req = R_CENTRE;                        // (keep is NOT refreshed: see above)
-        } else if (req == R_CENTRE || (req == R_LO && !(v > dc + tol)) || (req == R_HI && !(v > dc - tol)))
-            keep = args;                           // Optim.cpp:262, 294-296, 325-327
-        if (sr == 2 && sc == 2) dc = v;
+            dc = v;
+        } else {
+            // keep = args after the centre, and after a minus / plus neighbour that is not higher than the centre
+            // (Optim.cpp:262, 294-296, 325-327; the two tests are not symmetric)
+            const bool take = req == R_CENTRE || ((req & (R_LO | R_HI)) && !(v > (req == R_LO ? dc + tol : dc - tol)));
+            keep.t = take ? args.t : keep.t;
+            keep.v = take ? args.v : keep.v;
+            dc = req == R_CENTRE ? v : dc;
+        }
         d[walk_cell(b0, b1, sr, sc)] = v;
         known |= 1u << (5 * sr + sc);
 
@@ -233,31 +251,38 @@ __device__ inline int walk_minimise(Eval &eval, int subpx, const double *quad, F
         }
         if (done) break;
     }
-    wc.known = known; wc.b0 = b0; wc.b1 = b1;
-
-    if (finished) {                                // minimum bracketed on both axes: sub-pixel fit
-#pragma unroll
-        for (int r = 0; r < 4; r++)
-#pragma unroll
-            for (int q = 0; q < 4; q++) a[4 * r + q] = d[walk_cell(b0, b1, ip + r, jp + q)];
-        args = keep;
-        uv[0] = 1. - ip;
-        uv[1] = 1. - jp;
-        if (subpx == 0) out = uv[0];                                   // reference quirk, Optim.cpp:399
-        else if (subpx == 1) out = subpixel_quadratic(quad, a, uv);
-        else out = subpixel_spline(a, uv);
-        uv[0] += c0 + ip - 1.;
-        uv[1] += c1 + jp - 1.;
-        st = UMPA_ST_OK;
-    }
+    ws.known = known; ws.b0 = b0; ws.b1 = b1; ws.c0 = c0; ws.c1 = c1; ws.ip = ip; ws.jp = jp;
+    ws.finished = finished;
+    if (finished) { args = keep; st = UMPA_ST_OK; }                    // Optim.cpp:386
     return st;
 }
 
-// Writes one pixel's results the way Model*::min packs `values` (Model.cpp:573-576, 934-938).
+// The sub-pixel fit on the completed 4x4 block (Optim.cpp:398-408).  May overwrite the cache's storage.
 template <class Grid>
+__device__ inline void walk_refine(int subpx, const double *quad, Grid d, const WalkState &ws, double &out, double *uv)
+{
+    uv[0] = 1. - ws.ip;
+    uv[1] = 1. - ws.jp;
+    if (subpx == 0) out = uv[0];                                       // reference quirk, Optim.cpp:399
+    else if (subpx == 1) out = subpixel_quadratic(quad, d, ws, uv);
+    else out = subpixel_spline(d, ws, uv);
+    uv[0] += ws.c0 + ws.ip - 1.;
+    uv[1] += ws.c1 + ws.jp - 1.;
+}
+
+// Writes one pixel's debug arrays (minimizer_debug.d / .a, model.pyx:488-491): before walk_refine().
+template <class Grid>
+__device__ __forceinline__ void store_debug(const umpa_outputs &o, size_t n, Grid d, const WalkState &ws)
+{
+    if (o.debug_d)
+        for (int t = 0; t < 25; t++) o.debug_d[25 * n + t] = walk_cache_get(d, ws, t);
+    if (o.debug_a)
+        for (int t = 0; t < 16; t++) o.debug_a[16 * n + t] = ws.finished ? walk_block_get(d, ws, t >> 2, t & 3) : 0.;
+}
+
+// Writes one pixel's results the way Model*::min packs `values` (Model.cpp:573-576, 934-938).
 __device__ __forceinline__ void store_pixel(const umpa_outputs &o, size_t n, int kind, int st, double f,
-                                            const FitArgs &args, const double *uv, Grid d, const WalkCache &wc,
-                                            const double *a, int ncalls, bool have_a)
+                                            const FitArgs &args, const double *uv, int ncalls)
 {
     if (o.f) o.f[n] = f;
     if (o.T) o.T[n] = args.t;
@@ -266,10 +291,4 @@ __device__ __forceinline__ void store_pixel(const umpa_outputs &o, size_t n, int
     if (o.df && kind == UMPA_DF) o.df[n] = args.v;
     if (o.err) o.err[n] = (st & UMPA_ST_OK) ? 1 : 0;
     if (o.ncalls) o.ncalls[n] = ncalls;
-    if (o.debug_d)
-        for (int t = 0; t < 25; t++) o.debug_d[25 * n + t] = walk_cache_get(d, wc, t);
-    if (o.debug_a) {
-#pragma unroll
-        for (int t = 0; t < 16; t++) o.debug_a[16 * n + t] = have_a ? a[t] : 0.;
-    }
 }

@@ -37,6 +37,7 @@ class ShardedMatcher:
         self.padding = int(max_shift) + int(window_size) + cls.safe_crop
         H = sam[0].shape[0]
         self.n_rows = H - 2 * self.padding
+        self.n_cols = sam[0].shape[1] - 2 * self.padding
         self.bands = row_bands(self.n_rows, self.world)
         self.band = self.bands[self.rank]
         lo, hi = band_input_rows(self.band, self.padding)
@@ -57,36 +58,48 @@ class ShardedMatcher:
 
     def gather(self, local, keys=("f", "T", "dx", "dy", "df", "err"), dst=0):
         """Concatenate the bands' maps on rank `dst` (returns None elsewhere)."""
-        return gather_bands(local, self.bands, self.rank, keys=keys, dst=dst)
+        return gather_bands(local, self.bands, self.rank, keys=keys, dst=dst, n_cols=self.n_cols)
 
 
-def gather_bands(local, bands, rank, keys=("f", "T", "dx", "dy", "df", "err"), dst=0):
-    """The only inter-GPU traffic of a sharded match: rank r contributes maps of shape
-    (bands[r][1]-bands[r][0], N1, ...); rank `dst` receives their row-wise concatenation.
-    One torch.distributed.gather per map (NCCL for CUDA tensors, gloo for CPU tensors)."""
+_INT_KEYS = ("err", "debug_Ncalls")
+
+
+def gather_bands(local, bands, rank, keys=("f", "T", "dx", "dy", "df", "err"), dst=0, n_cols=None):
+    """The only inter-GPU traffic of a sharded match (north_star: "a final gather of the output maps"): rank r
+    contributes maps of shape (bands[r][1]-bands[r][0], N1); rank `dst` receives their row-wise concatenation.
+
+    The float64 maps of a rank travel as ONE packed tensor and the int32 maps as another, so a gather is two
+    torch.distributed.gather calls whatever the number of maps (NCCL over NVLink for CUDA tensors, gloo for CPU
+    tensors); no Python objects are exchanged.  Every rank must pass the same `keys`; keys a model does not
+    produce (df for NoDF) are dropped by name on every rank alike.  n_cols: map width (needed by a rank whose
+    band is empty)."""
     import torch.distributed as dist
     world = len(bands)
+    rows = max(b[1] - b[0] for b in bands)                    # bands differ by at most one row: pad to the tallest
+    mine = bands[rank][1] - bands[rank][0]
+    some = next((local[k] for k in keys if local.get(k) is not None), None)
+    if some is not None:
+        n_cols = int(some.shape[1])
+        dev = some.device
+    else:
+        if n_cols is None:
+            raise ValueError("gather_bands: a rank with an empty band needs n_cols")
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
     out = {}
-    for k in keys:
-        t = local.get(k)
-        meta = [None] * world
-        dist.all_gather_object(meta, None if t is None else (tuple(t.shape[1:]), str(t.dtype).split(".")[-1]))
-        known = [m for m in meta if m is not None]
-        if not known:
+    for group, dtype in ((tuple(k for k in keys if k not in _INT_KEYS), torch.float64),
+                         (tuple(k for k in keys if k in _INT_KEYS), torch.int32)):
+        if not group:
             continue
-        tail, dtype = known[0][0], getattr(torch, known[0][1])
-        if t is None:               # a rank with an empty band still takes part
-            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-            t = torch.empty((0,) + tuple(tail), dtype=dtype, device=dev)
-        # gather wants equal shapes: bands differ by at most one row, pad to the tallest
-        rows = max(b[1] - b[0] for b in bands)
-        send = t.contiguous()
-        if send.shape[0] < rows:
-            send = torch.cat([send, send.new_zeros((rows - send.shape[0],) + tuple(tail))], dim=0)
-        parts = None
-        if rank == dst:
-            parts = [torch.empty((rows,) + tuple(tail), dtype=dtype, device=t.device) for _ in bands]
+        send = torch.zeros((len(group), rows, n_cols), dtype=dtype, device=dev)
+        for n, k in enumerate(group):
+            t = local.get(k)
+            if t is not None and mine:
+                send[n, :mine] = t
+        parts = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
         dist.gather(send, parts, dst=dst)
         if rank == dst:
-            out[k] = torch.cat([p_[:b[1] - b[0]] for p_, b in zip(parts, bands)], dim=0)
+            full = torch.cat([p_[:, :b[1] - b[0]] for p_, b in zip(parts, bands)], dim=1)
+            for n, k in enumerate(group):
+                if local.get(k) is not None or not mine:      # a map the model does not produce (df for NoDF) is dropped
+                    out[k] = full[n]
     return out if rank == dst else None
