@@ -59,14 +59,37 @@ def algorithmic_flops_per_px(cfg):
     return f
 
 
+def table_plan(cfg):
+    """(streaming, chunk rows) of the cross-table kernel for a configuration -- the choice plan_tiles (table_path.cu)
+    makes: streaming row segments when the carry (S^2 planes x 2 Nw rows x 128 B) fits shared memory next to the filter
+    buffer and a three-stage frame ring, else halo tiles whose height minimises rows computed per useful row at
+    +15 % per extra pass over the frames."""
+    S, Nw, Na = 2 * cfg["ms"] - 1, cfg["Nw"], cfg["Na"]
+    hs, sh = S // 2, (3 if S <= 9 else (2 if S <= 17 else 1))
+    delta = (4 - hs % 4) % 4
+    ap = 28 + 4 * ((delta + S + 6) // 4)
+
+    def groups(eh):
+        return min(384 // (eh * 8), -(-S // sh))
+    stage16 = min(4, Na) * ((16 + 2 * hs) * ap + 16 * 32) * 4      # (plan_tiles shortens the TMA boxes until three stages fit)
+    if S * S * 2 * Nw * 128 + groups(16) * S * 16 * 128 + 3 * stage16 <= 225 * 1024 and Nw > 0:
+        return True, 16
+
+    def cost(eh):
+        return eh / float(eh - 2 * Nw) * (1. + .15 * (-(-S // (groups(eh) * sh)) - 1))
+    return False, min((e for e in (16, 24, 32, 48) if e - 2 * Nw >= 2), key=lambda e: (cost(e), e))
+
+
 def executed_fma_per_px_cross(cfg):
-    """FMAs the cross-table kernel executes per output pixel (streaming chunks, shift_table.cuh): Na per (chunk
-    pixel, shift) -- the chunk is 32 columns wide for 32 - 2 Nw output columns; the window halo in y is paid once
-    per row segment, i.e. not at all to first order -- plus the separable filter (row pass on the chunk columns,
-    column pass on the outputs)."""
+    """FMAs the cross-table kernel executes per output pixel (shift_table.cuh): Na per (chunk pixel, shift) -- a chunk
+    is 32 columns wide for 32 - 2 Nw output columns -- plus the separable filter (row pass on the chunk rows, column
+    pass on the outputs).  Streaming segments pay the window halo in y once per segment (not at all, to first order);
+    halo tiles compute EH rows for EH - 2 Nw output rows."""
     S, K, Na, Nw = 2 * cfg["ms"] - 1, 2 * cfg["Nw"] + 1, cfg["Na"], cfg["Nw"]
+    stream, eh = table_plan(cfg)
     tw = (32 - 2 * Nw) & ~3
-    return S * S * ((Na + K) * 32. / tw + K)
+    th = eh if stream else eh - 2 * Nw
+    return S * S * ((Na + K) * eh * 32. + K * th * tw) / (th * tw)
 
 
 class ClockSampler:
@@ -306,17 +329,15 @@ def ours(args, cfg):
     keys = ("f", "T", "dx", "dy") + (("df",) if cfg["kind"] == "DF" else ()) + ("err", "debug_Ncalls")
 
     # ---- device-resident metric -------------------------------------------------
-    # one step = one match of this rank's row band; for N > 1 followed by the gather of the maps on rank 0
-    # (the only inter-GPU traffic of the path: north_star / SURVEY 8d "gathered on GPU 0")
+    # one step = one match of this rank's row band.  For N > 1 the maps are then gathered on rank 0 -- the only
+    # inter-GPU traffic of the path (north_star) -- which SURVEY.md 5 / 8(d) keep outside the kernel-timed region
+    # and report separately: `gather` below (and `value_incl_gather`)
     sm = ShardedMatcher(cls, list(sam), list(ref), rank, world, window_size=cfg["Nw"], max_shift=cfg["ms"])
     band_rows = sm.band[1] - sm.band[0]
     lo, hi = sm.band[0], sm.band[1] + 2 * pad
 
     def step():
-        o = sm.match_device(**kw)
-        if world > 1:
-            o = sm.gather(o, keys=keys, dst=0)
-        return o
+        return sm.match_device(**kw)
     launches = 0
     for _ in range(args.warmup):
         out = step()
@@ -334,27 +355,28 @@ def ours(args, cfg):
     ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     value = total_px / (ms * 1e-3)
     launches = int(sum_over_ranks(launches))
-    err_ok = None
-    if rank == 0:
-        err_ok = float((out["err"] == 1).sum().item()) / total_px          # rank 0 holds the whole map (gathered for N > 1)
     gather = None
-    if world > 1:                                 # the gather alone, and the match alone
-        loc = sm.match_device(**kw)
-        g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    if world > 1:                                 # the final gather of the maps on rank 0, timed on its own
+        full = sm.gather(out, keys=keys, dst=0)   # (warm-up: NCCL sets up its channels on first use)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         g0.record()
         for _ in range(args.steps):
-            sm.match_device(**kw)
+            full = sm.gather(out, keys=keys, dst=0)
         g1.record()
-        for _ in range(args.steps):
-            sm.gather(loc, keys=keys, dst=0)
-        g2.record()
         torch.cuda.synchronize()
         barrier()
-        gather = {"match_ms": max_over_ranks(g0.elapsed_time(g1) / args.steps),
-                  "gather_ms": max_over_ranks(g1.elapsed_time(g2) / args.steps),
-                  "bytes_to_rank0": int(sum_over_ranks(0. if rank == 0 else float(sum(loc[k].numel() * loc[k].element_size() for k in keys if k in loc)))),
-                  "how": "two torch.distributed.gather calls (packed float64 maps, packed int32 maps) over NCCL, inside the timed step"}
+        g_ms = max_over_ranks(g0.elapsed_time(g1) / args.steps)
+        nbytes = sum_over_ranks(0. if rank == 0 else float(sum(out[k].numel() * out[k].element_size() for k in keys if k in out)))
+        gather = {"gather_ms": g_ms, "bytes_to_rank0": int(nbytes), "gbs_into_rank0": nbytes / (g_ms * 1e-3) / 1e9,
+                  "value_incl_gather": total_px / ((ms + g_ms) * 1e-3),
+                  "how": "two torch.distributed.gather calls (packed float64 maps, packed int32 maps) over NCCL / NVLink "
+                         "after the timed steps; rank 0 ends with the full (N0, N1) maps in its HBM"}
+        if rank == 0:
+            out = full
+    err_ok = None
+    if rank == 0:
+        err_ok = float((out["err"] == 1).sum().item()) / total_px          # rank 0 holds the whole map (gathered for N > 1)
 
     # ---- stage times of the kernels (events inside the library, same stream) -------
     stage_ms = None
@@ -516,7 +538,7 @@ def ours(args, cfg):
             "config": {"workload": cfg["desc"], "output_px": total_px, "sharding": "row bands x%d + %d-row halo" % (world, pad),
                        "path": info["path"], "l2": "inputs (%.0f MB FP32 stacks) larger than the 126 MB L2, no flush" % (alg_bytes / 1e6),
                        "inputs_resident": "mean-centred FP32 stacks in HBM; result maps (f,T,dx,dy,df f64; err,Ncalls i32) left in HBM"
-                                          + (" of rank 0 (gathered over NCCL inside the timed step)" if world > 1 else ""),
+                                          + (" of each rank (then gathered on rank 0: see `gather`)" if world > 1 else ""),
                        "err_ok_fraction": err_ok},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "gather": gather, "parity": parity,
             "roofline_hbm_step": {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9 / world, "peak": hbm_peak,

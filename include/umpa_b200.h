@@ -54,16 +54,18 @@ enum {
     UMPA_OPT_PATH = 3             /* UMPA_PATH_*: which CUDA path match() uses */
 };
 
-/* UMPA_OPT_PATH values.  Both are CUDA paths; there is no CPU path.
- *  TABLE: FP32 exhaustive shift tables (cross-correlation summed over frames, then
- *         Hamming-filtered) + FP64 per-pixel solve and walk.  Needs equal frame
- *         shapes, zero positions, no masks, a separable window, NoDF/DF.
- *  LAZY:  one thread per pixel evaluates the reference's cost() on demand in FP64,
- *         in the reference's summation order (all models, masks, positions).
- *  AUTO:  TABLE when eligible, else LAZY. */
+/* UMPA_OPT_PATH values.  All are CUDA paths; there is no CPU path.
+ *  TABLE: FP32 exhaustive shift tables + FP64 per-pixel solve and walk.  NoDF / DF: cross-correlation summed
+ *         over frames, then Hamming-filtered (max_shift <= 10, Nw <= 6, either assign_coordinates); DFKernel: the
+ *         per-pixel blur fused into the window pass (Nw <= 3, max_shift <= 6).  Needs a separable window.
+ *  LAZY:  one thread per pixel evaluates the reference's cost() on demand in FP64, in the reference's
+ *         summation order (all models, masks, positions, any window / max_shift).
+ *  AUTO:  TABLE when the model has equal frames at position 0 and no masks; with masks or ragged frames /
+ *         positions the MIXED path: TABLE on every pixel for which it is exact (no mask value != 1 within reach;
+ *         every frame either contains the pixel's reach or misses it), LAZY on the rest; LAZY when TABLE does
+ *         not apply at all.  Requesting TABLE on a model that is not eligible is an error. */
 enum { UMPA_PATH_AUTO = 0, UMPA_PATH_TABLE = 1, UMPA_PATH_LAZY = 2,
-       UMPA_PATH_MIXED = 3 /* reported only: masked NoDF/DF -- TABLE where every mask value within reach of the
-                              pixel is exactly 1 (the masked and the unmasked cost agree there), LAZY elsewhere */ };
+       UMPA_PATH_MIXED = 3 /* reported by umpa_last_match_info only (see AUTO above) */ };
 
 /* Output maps of umpa_match*, all row-major (N0, N1); any pointer may be NULL to
  * skip that map.  Replaces the `values`, `err`, `debug_*` arrays that

@@ -142,12 +142,13 @@ def test_bench_algorithmic_flops_match_survey():
     want = {"cfg1": 24500, "cfg2": 101250, "cfg3": 3648150, "cfg4": 882000, "cfg5": 66248}
     for name, f in want.items():
         assert bench.algorithmic_flops_per_px(bench.CONFIGS[name]) == f, name
-    # executed FMAs per output pixel of the cross-table kernel: config 2 uses 16-row tiles (12 x 28 outputs)
+    # executed FMAs per output pixel of the cross-table kernel: configs 1, 2, 5 stream 16-row chunks (every chunk row
+    # is an output row, 28 / 20 of 32 columns are outputs), config 4's carry does not fit: 24-row halo tiles
+    assert bench.table_plan(bench.CONFIGS["cfg2"]) == (True, 16) and bench.table_plan(bench.CONFIGS["cfg1"]) == (True, 16)
+    assert bench.table_plan(bench.CONFIGS["cfg5"]) == (True, 16) and bench.table_plan(bench.CONFIGS["cfg4"]) == (False, 24)
     S, K, Na = 9, 5, 25
-    assert abs(bench.executed_fma_per_px_cross(bench.CONFIGS["cfg2"]) -
-               S * S * (Na * 16 * 32 + K * 16 * 28 + K * 12 * 28) / (12. * 28)) < 1e-9
-    # config 5 (Nw = 6) takes the 48-row tile, config 4 (Nw = 3, S = 15) the 24-row tile
+    assert abs(bench.executed_fma_per_px_cross(bench.CONFIGS["cfg2"]) - S * S * ((Na + K) * 32 / 28. + K)) < 1e-9
     e5 = bench.executed_fma_per_px_cross(bench.CONFIGS["cfg5"])
-    assert abs(e5 - 49 * (4 * 48 * 32 + 13 * 48 * 20 + 13 * 36 * 20) / (36. * 20)) < 1e-9
+    assert abs(e5 - 49 * ((4 + 13) * 32 / 20. + 13)) < 1e-9
     e4 = bench.executed_fma_per_px_cross(bench.CONFIGS["cfg4"])
     assert abs(e4 - 225 * (40 * 24 * 32 + 7 * 24 * 26 + 7 * 18 * 26) / (18. * 26)) < 1e-9

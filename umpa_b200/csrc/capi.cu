@@ -528,11 +528,58 @@ int download_outputs(const umpa_outputs &host, const umpa_outputs &dev, size_t n
 }
 
 // Pinned FP32 staging for the rows the host converts (grow-only, shared by all models of the process).
+// Pinning is slow (~0.3 ms per MB: config 2 needs ~0.8 GB), so it never happens inside a call: the first call that
+// wants a bigger buffer than there is starts a builder thread and goes by plain DMA itself (no host conversion);
+// the builder allocates page-aligned memory, touches it (no CUDA involved), registers it with CUDA in 64 MB pieces
+// (each piece holds the driver's lock only briefly, so the calls of the running match are not held up) and
+// publishes it for the calls that follow.  UMPA_STAGE_SYNC=1 pins inside the call instead (tests, benchmarks of
+// the steady state from the first call on).
 struct HostStage {
-    std::mutex mu;
+    std::mutex mu;                  // held by a pipelined match for its whole duration; the builder publishes under it
     float *p = nullptr;
     size_t bytes = 0;
+    bool registered = false;        // p came from the builder (aligned_alloc + cudaHostRegister), not from cudaHostAlloc
+    std::atomic<bool> building{false};
 } g_stage;
+
+void stage_release_locked()
+{
+    if (!g_stage.p) return;
+    if (g_stage.registered) { cudaHostUnregister(g_stage.p); free(g_stage.p); }
+    else cudaFreeHost(g_stage.p);
+    g_stage.p = nullptr; g_stage.bytes = 0; g_stage.registered = false;
+}
+
+void stage_builder(size_t bytes, int device)
+{
+    cudaSetDevice(device);
+    const size_t piece = (size_t)64 << 20;
+    bytes = (bytes + piece - 1) / piece * piece;
+    char *q = (char *)aligned_alloc(4096, bytes);
+    bool ok = q != nullptr;
+    if (ok) {
+        for (size_t o = 0; o < bytes; o += 4096) q[o] = 0;                // fault the pages in (first touch on this thread)
+        size_t done = 0;
+        for (; ok && done < bytes; done += piece)
+            ok = cudaHostRegister(q + done, piece, cudaHostRegisterPortable) == cudaSuccess;
+        if (!ok) {
+            cudaGetLastError();
+            for (size_t o = 0; o + piece <= done - piece; o += piece) cudaHostUnregister(q + o);
+            free(q);
+        }
+    }
+    if (ok) {
+        std::lock_guard<std::mutex> lk(g_stage.mu);                      // (waits for a match that is using the old buffer)
+        if (g_stage.bytes < bytes) {
+            stage_release_locked();
+            g_stage.p = (float *)q; g_stage.bytes = bytes; g_stage.registered = true;
+        } else {
+            for (size_t o = 0; o < bytes; o += piece) cudaHostUnregister(q + o);
+            free(q);
+        }
+    }
+    g_stage.building.store(false);
+}
 
 // Measured rates of the two sides of the pipelined upload (this process, exponential average): how
 // fast the host threads convert while the DMA engine runs, and how fast the DMA engine moves FP64
@@ -676,19 +723,25 @@ int streamed_match(umpa_model *m, const RoiView &v, const umpa_outputs &dev, con
         Yc = H - (int)(x * H);
         if (Yc >= H) nthr = 0;
     }
-    const int HC = H - Yc;                      // converted rows per frame
+    int HC = H - Yc;                            // converted rows per frame
     std::unique_lock<std::mutex> stage_lock(g_stage.mu, std::defer_lock);
     if (nthr > 0) {
         stage_lock.lock();
         const size_t want = (size_t)2 * Na * HC * pitch * sizeof(float);
         if (g_stage.bytes < want) {
-            if (g_stage.p) cudaFreeHost(g_stage.p);
-            g_stage.p = nullptr; g_stage.bytes = 0;
-            if (cudaHostAlloc((void **)&g_stage.p, want, cudaHostAllocDefault) != cudaSuccess) {
-                cudaGetLastError();
-                nthr = 0; Yc = H;                // no pinned memory: plain DMA path
-                stage_lock.unlock();
-            } else g_stage.bytes = want;
+            // room for every split the rate model may pick later (all rows when the frames are pageable or float32)
+            const size_t want_max = (size_t)2 * Na * H * pitch * sizeof(float);
+            if (getenv("UMPA_STAGE_SYNC")) {
+                stage_release_locked();
+                if (cudaHostAlloc((void **)&g_stage.p, want_max, cudaHostAllocDefault) == cudaSuccess) g_stage.bytes = want_max;
+                else cudaGetLastError();
+            } else if (!g_stage.building.exchange(true)) {
+                std::thread(stage_builder, want_max, m->device).detach();
+            }
+        }
+        if (g_stage.bytes < want) {              // not pinned (yet): this call goes by plain DMA
+            nthr = 0; Yc = H; HC = 0;
+            stage_lock.unlock();
         }
     }
     if (m->host_f32 && nthr == 0) return streamed_match_f32(m, v, dev, host);    // no staging: plain copies after all
@@ -1063,7 +1116,7 @@ void umpa_destroy(umpa_model *m)
     DeviceGuard dg(m);
     cudaDeviceSynchronize();      // (the model's device) blocks go back to the cache: nothing of this model may still be running
     free_frames(m);
-    for (Scratch *s : {&m->filtA, &m->filtB, &m->auxS, &m->auxR, &m->tabX, &m->tabM, &m->outbuf, &m->maskbad, &m->dirty})
+    for (Scratch *s : {&m->filtA, &m->filtB, &m->auxS, &m->auxR, &m->tabX, &m->outbuf, &m->maskbad, &m->dirty})
         if (s->p) pool_free(s->p, s->bytes);
     pinned_small_give(m->h_small, m->h_small_own);       // (the streams are shared per device and stay)
     if (m->win_own) { cudaFree(m->d_win); cudaFree(m->d_g); }

@@ -106,7 +106,7 @@ struct umpa_model {
     void *h_small = nullptr;                     // pinned: constants on their way to the device
 
     // TABLE-path scratch (grow-only)
-    Scratch filtA, filtB, auxS, auxR, tabX, tabM;
+    Scratch filtA, filtB, auxS, auxR, tabX;
     Scratch maskbad, dirty;                      // masked models: row-dilated "mask != 1" image [H][W], per-ROI dirty map
     bool maskbad_valid = false;
     bool moments_valid = false;

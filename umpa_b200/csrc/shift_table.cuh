@@ -5,7 +5,13 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
+
+#ifndef UMPA_COLPASS4
+#define UMPA_COLPASS4 1          // 1: column pass of the filter epilogue on four output rows per thread (see the kernel)
+#endif
 
 namespace shift_table {
 
@@ -200,9 +206,14 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         // output row of this thread in this chunk: the column pass ends at its own chunk row (taps er-H2 .. er)
         const int r_out = chunk * p.EH + er - H2;
         const bool store = r_out >= 0 && r_out < item_rows && ec < p.TW;
+#if UMPA_COLPASS4
         // FILTER: the column pass works on groups of four chunk rows e4 .. e4+3 (output rows r_out4 .. r_out4+3)
-        const int e4 = er & ~3, r_out4 = chunk * p.EH + e4 - H2;
-        const bool any_store = r_out4 + 3 >= 0 && r_out4 < item_rows && ec < p.TW;
+        const int e4 = er & ~3, qi = er & 3, r_out4 = chunk * p.EH + e4 - H2;
+        unsigned row_ok = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) row_ok |= (r_out4 + i >= 0 && r_out4 + i < item_rows && ec < p.TW) ? 1u << i : 0u;
+        const bool any_store = row_ok != 0;
+#endif
         for (int pass = 0; pass < p.npass; pass++) {
             const int si0 = (pass * p.G + grp) * SH; // first shift row of this thread in this pass
             const bool work = si0 < S;
@@ -310,47 +321,94 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                         *reinterpret_cast<float4 *>(cg + sj * plane) = make_float4(o[0], o[1], o[2], o[3]);
                     }
                     asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(TG) : "memory");
-                    // Column pass, FOUR output rows per thread: the four threads of a strip (chunk rows e4 .. e4+3,
-                    // one quarter warp each) share out the S planes, and each filters its planes for all four rows:
-                    // the H2+4 row-filtered lines an output group needs are read once (one LDS.128 per line and
-                    // strip) instead of once per output row -- 8 instead of 20 wavefronts per plane and warp for K = 5.
+#if UMPA_COLPASS4
+                    // Column pass, FOUR output rows per thread.  The four threads of a strip column (chunk rows e4 ..
+                    // e4+3: the four quarter warps of one warp) deal out the S planes -- thread qi takes planes qi, qi+4,
+                    // ... -- and each filters its planes for all four rows: the 2Nw+4 row-filtered lines an output group
+                    // needs are read ONCE per strip (one LDS.128 each) instead of once per output row: 2 instead of 5
+                    // wavefronts per output line for Nw = 2.  FFMA2: the window factor is the broadcast scalar, the halves
+                    // of a float4 line are natural register pairs.  E4 < 0: every tap lies inside this chunk (the
+                    // common case, all addresses are immediates); E4 = 0, 4, 8: the group starts E4 rows into the
+                    // chunk and its first taps reach into the previous chunk's last rows (carry) -- or, in a segment's
+                    // first chunk, above the segment, where they feed no stored row.
                     if (any_store) {
-                        float *dst0 = p.table + (size_t)(row0 + r_out4) * p.row_stride + (size_t)(si * S) * p.plane_stride + tx0 + ec;
-                        const float *cw = cbuf + (size_t)grp * S * plane + ec;             // chunk rows of this group's planes
-                        const float *cr = carry + (size_t)(si * S) * (H2 * EXT_W) + ec;    // rows of the previous chunk
+                        float *dq = p.table + (size_t)(row0 + r_out4) * p.row_stride + (size_t)(si * S + qi) * p.plane_stride + tx0 + ec;
+                        const float *cb = cbuf + (size_t)(grp * S + qi) * plane + ec;             // chunk row 0 of plane qi
+                        const float *cr = carry + (size_t)((si * S + qi) * H2) * EXT_W + ec;      // carry row 0 of plane qi
+                        auto colpass = [&](auto e4c) {
+                            constexpr int E4 = decltype(e4c)::value;
+                            const float *base = E4 < 0 ? cb + (e4 - H2) * EXT_W : cb;
 #pragma unroll
-                        for (int n = 0; n < (S + 3) / 4; n++) {
-                            const int sj = (er & 3) + 4 * n;
-                            if (sj >= S) break;
-                            float o[4][4];
+                            for (int n = 0; n < (S + 3) / 4; n++) {
+                                if (4 * n + 3 >= S && 4 * n + qi >= S) continue;           // (only the last n can run out of planes)
+                                const float *bn = base + (4 * n) * plane;
+                                float2 o[4][2];
 #pragma unroll
-                            for (int i = 0; i < 4; i++)
+                                for (int i = 0; i < 4; i++) o[i][0] = o[i][1] = make_float2(0.f, 0.f);
 #pragma unroll
-                                for (int x = 0; x < 4; x++) o[i][x] = 0.f;
+                                for (int t = 0; t < H2 + 4; t++) {                         // chunk row e4 - H2 + t
+                                    float4 v;
+                                    if (E4 < 0) v = *reinterpret_cast<const float4 *>(bn + t * EXT_W);
+                                    else if (E4 + t >= H2) v = *reinterpret_cast<const float4 *>(bn + (E4 + t - H2) * EXT_W);
+                                    else if (chunk > 0) v = *reinterpret_cast<const float4 *>(cr + ((4 * n) * H2 + E4 + t) * EXT_W);
+                                    else v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                            for (int t = 0; t < H2 + 4; t++) {                             // chunk row e4 - H2 + t
-                                const int q = e4 + t;                                      // (row of [carry rows | chunk rows])
-                                // (rows above the first chunk of a segment only feed output rows that are not stored:
-                                //  any valid address will do -- there may be no carry buffer at all)
-                                const float *src = q >= H2 || chunk == 0 ? cw + sj * plane + max(q - H2, 0) * EXT_W
-                                                                         : cr + (sj * H2 + q) * EXT_W;
-                                const float4 v = *reinterpret_cast<const float4 *>(src);
-#pragma unroll
-                                for (int i = 0; i < 4; i++) {
-                                    const int u = t - i;                                   // tap of output row i
-                                    if (u >= 0 && u < K) {
-                                        o[i][0] = fmaf(gk[u], v.x, o[i][0]); o[i][1] = fmaf(gk[u], v.y, o[i][1]);
-                                        o[i][2] = fmaf(gk[u], v.z, o[i][2]); o[i][3] = fmaf(gk[u], v.w, o[i][3]);
+                                    for (int i = 0; i < 4; i++) {
+                                        const int u = t - i;                               // tap of output row i
+                                        if (u >= 0 && u < K) {
+                                            o[i][0] = __ffma2_rn(make_float2(gk[u], gk[u]), make_float2(v.x, v.y), o[i][0]);
+                                            o[i][1] = __ffma2_rn(make_float2(gk[u], gk[u]), make_float2(v.z, v.w), o[i][1]);
+                                        }
                                     }
                                 }
-                            }
 #pragma unroll
-                            for (int i = 0; i < 4; i++)
-                                if (r_out4 + i >= 0 && r_out4 + i < item_rows)
-                                    *reinterpret_cast<float4 *>(dst0 + (size_t)i * p.row_stride + sj * p.plane_stride) =
-                                        make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+                                for (int i = 0; i < 4; i++)
+                                    if ((row_ok >> i) & 1)
+                                        *reinterpret_cast<float4 *>(dq + (size_t)i * p.row_stride + (4 * n) * p.plane_stride) =
+                                            make_float4(o[i][0].x, o[i][0].y, o[i][1].x, o[i][1].y);
+                            }
+                        };
+                        if (e4 >= H2) colpass(std::integral_constant<int, -1>{});
+                        else if (e4 == 0) colpass(std::integral_constant<int, 0>{});
+                        else if (e4 == 4) colpass(std::integral_constant<int, (H2 > 4 ? 4 : 0)>{});
+                        else colpass(std::integral_constant<int, (H2 > 8 ? 8 : 0)>{});
+                    }
+#else
+                    // Column pass: each thread filters its own strip over the chunk rows er-2Nw .. er (FFMA2: the window
+                    // factor is the broadcast scalar, the halves of a float4 line are natural register pairs)
+                    if (store) {
+                        float *dst = p.table + (size_t)(row0 + r_out) * p.row_stride + (size_t)(si * S) * p.plane_stride + tx0 + ec;
+                        if (er >= H2) {                          // every tap inside this chunk
+#pragma unroll
+                            for (int sj = 0; sj < S; sj++) {
+                                float2 o01 = make_float2(0.f, 0.f), o23 = make_float2(0.f, 0.f);
+#pragma unroll
+                                for (int u = 0; u < K; u++) {
+                                    const float4 t = *reinterpret_cast<const float4 *>(cg + sj * plane + (u - H2) * EXT_W);
+                                    o01 = __ffma2_rn(make_float2(gk[u], gk[u]), make_float2(t.x, t.y), o01);
+                                    o23 = __ffma2_rn(make_float2(gk[u], gk[u]), make_float2(t.z, t.w), o23);
+                                }
+                                *reinterpret_cast<float4 *>(dst + sj * p.plane_stride) = make_float4(o01.x, o01.y, o23.x, o23.y);
+                            }
+                        } else {                                 // taps er+u < 2Nw come from the previous chunk's last rows
+                            const float *cw = cbuf + (size_t)grp * S * plane + ec;
+                            const float *cr = carry + (size_t)(si * S) * (H2 * EXT_W) + ec;
+#pragma unroll
+                            for (int sj = 0; sj < S; sj++) {
+                                float2 o01 = make_float2(0.f, 0.f), o23 = make_float2(0.f, 0.f);
+#pragma unroll
+                                for (int u = 0; u < K; u++) {
+                                    const int q = er + u;        // row of [carry rows | chunk rows]
+                                    const float *src = q >= H2 ? cw + sj * plane + (q - H2) * EXT_W : cr + (sj * H2 + q) * EXT_W;
+                                    const float4 t = *reinterpret_cast<const float4 *>(src);
+                                    o01 = __ffma2_rn(make_float2(gk[u], gk[u]), make_float2(t.x, t.y), o01);
+                                    o23 = __ffma2_rn(make_float2(gk[u], gk[u]), make_float2(t.z, t.w), o23);
+                                }
+                                *reinterpret_cast<float4 *>(dst + sj * p.plane_stride) = make_float4(o01.x, o01.y, o23.x, o23.y);
+                            }
                         }
                     }
+#endif
                     asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(TG) : "memory");
                     if (H2 > 0 && keep) {                        // (after the barrier: the readers of the old carry are done)
                         float *cr = carry + ((size_t)(si * S) * H2 + (er - (p.EH - H2))) * EXT_W + ec;
@@ -374,11 +432,14 @@ int launch_shift_table(const CUtensorMap &mapA, const CUtensorMap &mapB, const T
                        size_t smem, cudaStream_t st)
 {
     auto kern = shift_table_kernel<S, RowBlock<S>::SH, NWT>;
-    static size_t attr_set = 0;
-    if (smem > attr_set) {
+    static size_t attr_set[64] = {0};                // per device (function attributes belong to the device's context)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > attr_set[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) { umpa_set_error("cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e)); return UMPA_ERR_CUDA; }
-        attr_set = smem;
+        attr_set[dev & 63] = smem;
     }
     kern<<<grid, nt, smem, st>>>(mapA, mapB, p);
     UMPA_CUDA(cudaGetLastError());

@@ -589,7 +589,7 @@ int ctas_per_sm() { const char *e = getenv("UMPA_TAB_CTAS"); return e ? std::max
 
 // Geometry of one table kernel: chunk height, warp groups, frame ring, and how the table is cut into items (column
 // strips x row segments, shift_table.cuh).  Returns dynamic smem bytes (0 = unsupported) and the block size.
-size_t plan_tiles(TableParams &p, int S, bool filter, int *nt, int rows, int cols, int ctas)
+size_t plan_tiles(TableParams &p, int S, bool filter, int *nt, int rows, int cols, int ctas, int ctas_sm)
 {
     const int HS = (S - 1) / 2, halo = filter ? p.Nw : 0, H2 = 2 * halo;
     const int delta = (4 - HS % 4) % 4;
@@ -601,7 +601,8 @@ size_t plan_tiles(TableParams &p, int S, bool filter, int *nt, int rows, int col
     p.cols_p = p.nstrips * p.TW;
     p.AP = EXT_W - 4 + 4 * NA4;
     auto up32 = [](int floats) { return (floats + 31) & ~31; };      // 128 B
-    const size_t budget = SMEM_CAP - 2048;
+    const size_t budget = SMEM_CAP / ctas_sm - 2048;           // (shared memory per SM: 228 KB, 1 KB reserved per CTA)
+    const int max_nt = ctas_sm > 1 ? (MAX_NT / ctas_sm) & ~31 : MAX_NT;  // registers: 168 per thread for MAX_NT threads per SM
     // Candidates: chunk height EH (a tall chunk leaves room for fewer warp groups, i.e. more passes over the
     // frames) x streaming or not.  STREAMING keeps the last 2*halo row-filtered rows of every shift plane in shared
     // memory for the next chunk of the segment, so no chunk row is wasted on the window halo; without it every
@@ -612,14 +613,14 @@ size_t plan_tiles(TableParams &p, int S, bool filter, int *nt, int rows, int col
     TableParams bp = p;
     size_t best_smem = 0;
     const char *e_eh = getenv("UMPA_TAB_EH"), *e_st = getenv("UMPA_TAB_STREAM"), *e_fb = getenv("UMPA_TAB_FB"), *e_g = getenv("UMPA_TAB_G");
-    for (int eh : {16, 24, 32, 48})
+    for (int eh : {8, 16, 24, 32, 48})
         for (int stream = (filter && halo > 0) ? 1 : 0; stream >= 0; stream--) {
-            if (e_eh && atoi(e_eh) != eh) continue;
+            if (e_eh ? atoi(e_eh) != eh : (eh == 8) != (ctas_sm > 1)) continue;     // 8-row chunks: two CTAs per SM only
             if (e_st && filter && halo > 0 && atoi(e_st) != stream) continue;
             if (!stream && eh - H2 < 2) continue;
             TableParams q = p;
             q.EH = eh;
-            q.G = std::min(MAX_NT / (eh * 8), (S + SH - 1) / SH);
+            q.G = std::min(max_nt / (eh * 8), (S + SH - 1) / SH);
             if (e_g) q.G = std::max(1, std::min(q.G, atoi(e_g)));
             if (q.G < 1) continue;
             q.npass = (S + q.G * SH - 1) / (q.G * SH);
@@ -810,8 +811,8 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         if ((rc = scratch_reserve(m, m->tabX, (size_t)roi.N0 * roi.N1 * ktable_row_floats(m->max_shift) * sizeof(float)))) return rc;
     } else {
         const int ctas = m->sm_count * ctas_per_sm();
-        smx = plan_tiles(px, S, true, &ntx, rows, cols + dxX, ctas);
-        smm = df ? plan_tiles(pm, S, false, &ntm, rows, cols + dxM, ctas) : 1;
+        smx = plan_tiles(px, S, true, &ntx, rows, cols + dxX, ctas, ctas_per_sm());
+        smm = df ? plan_tiles(pm, S, false, &ntm, rows, cols + dxM, ctas, ctas_per_sm()) : 1;
         if (!smx || !smm) { umpa_set_error("table path: tile does not fit shared memory"); return UMPA_ERR_UNSUPPORTED; }
         const int rows_alloc = rows;
         int tpitch = px.cols_p;

@@ -177,24 +177,27 @@ __device__ inline int walk_search(Eval &eval, FitArgs &args, double &out, double
         idle = 0;
         if (se != UMPA_ST_OK) { st = se; break; }  // bound error: return at once (Optim.cpp:264,291,324,359)
 
-        // ---- file the result ----
-        if (req == R_FILL && v < dc) {             // 4x4 fill, lower value off-axis: hard restart there (Optim.cpp:364-377)
-            c0 += sr - 2; c1 += sc - 2;
-            sr = sc = 2;
-            known = 0;
-            args = keep;                           // (keep is NOT refreshed: see above)
-            settled0 = settled1 = 0;
-            skip_limit = true;
-            fill = false;
-            dc = v;
-        } else {
-            // keep = args after the centre, and after a minus / plus neighbour that is not higher than the centre
-            // (Optim.cpp:262, 294-296, 325-327; the two tests are not symmetric)
-            const bool take = req == R_CENTRE || ((req & (R_LO | R_HI)) && !(v > (req == R_LO ? dc + tol : dc - tol)));
-            keep.t = take ? args.t : keep.t;
-            keep.v = take ? args.v : keep.v;
-            dc = req == R_CENTRE ? v : dc;
-        }
+        // ---- file the result (selects, no branches: the lanes of a warp are at different points of their walks) ----
+        // 4x4 fill, lower value off-axis: hard restart at that shift (Optim.cpp:364-377) -- the walk continues as if it
+        // had started there, except that args / keep are NOT refreshed (see above) and the loop-head test is skipped
+        const bool restart = req == R_FILL && v < dc;
+        // keep = args after the centre, and after a minus / plus neighbour that is not higher than the centre
+        // (Optim.cpp:262, 294-296, 325-327; the two tests are not symmetric)
+        const bool take = req == R_CENTRE || ((req & (R_LO | R_HI)) && !(v > dc + (req == R_LO ? tol : -tol)));
+        keep.t = take ? args.t : keep.t;
+        keep.v = take ? args.v : keep.v;
+        args.t = restart ? keep.t : args.t;
+        args.v = restart ? keep.v : args.v;
+        c0 += restart ? sr - 2 : 0;
+        c1 += restart ? sc - 2 : 0;
+        sr = restart ? 2 : sr;
+        sc = restart ? 2 : sc;
+        known = restart ? 0u : known;
+        settled0 = restart ? 0 : settled0;
+        settled1 = restart ? 0 : settled1;
+        skip_limit = skip_limit || restart;
+        fill = fill && !restart;
+        dc = (restart || req == R_CENTRE) ? v : dc;
         d[walk_cell(b0, b1, sr, sc)] = v;
         known |= 1u << (5 * sr + sc);
 

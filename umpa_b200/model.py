@@ -20,6 +20,8 @@ Differences from the reference that a caller can see (documented, deliberate):
     state like the reference, except ``f`` which the reference leaves uninitialised.
 """
 import ctypes as C
+import os
+import threading
 
 import numpy as np
 import torch
@@ -37,6 +39,38 @@ def pool_trim():
     """Release the device blocks the library caches between models (umpa_pool_trim); returns the bytes freed.
     Call it when another allocator in the process (PyTorch's, ...) needs the memory."""
     return int(_capi.lib().umpa_pool_trim())
+
+
+# Pinning host memory is slow (~0.5 ms per MB the first time; torch caches the blocks afterwards).  The result maps of
+# the first match() of a shape therefore go to ordinary (pageable) arrays, while a helper thread puts pinned blocks of
+# the right sizes into torch's pinned-memory cache for the calls that follow: the first call of a process does not wait
+# ~100 ms for 200 MB of maps to be pinned (the reference's constructor and first call cost nothing of the kind).
+_pinned_shapes = {}
+_pinned_lock = threading.Lock()
+
+
+def _pinned_ready(npx, df, debug):
+    key = (int(npx), bool(df), bool(debug))
+    with _pinned_lock:
+        state = _pinned_shapes.get(key)
+        if state is None:
+            _pinned_shapes[key] = "warming"
+    if state == "ready" or os.environ.get("UMPA_STAGE_SYNC"):
+        return True
+    if state is None:
+        def warm():
+            try:
+                blocks = [torch.empty((npx,), dtype=torch.float64, pin_memory=True) for _ in range(5 if df else 4)]
+                blocks += [torch.empty((npx,), dtype=torch.int32, pin_memory=True) for _ in range(2)]
+                if debug:
+                    blocks += [torch.empty((npx * 25,), dtype=torch.float64, pin_memory=True),
+                               torch.empty((npx * 16,), dtype=torch.float64, pin_memory=True)]
+                del blocks                  # back to torch's pinned cache: the next match() of this shape takes them from there
+            finally:
+                with _pinned_lock:
+                    _pinned_shapes[key] = "ready"
+        threading.Thread(target=warm, daemon=True).start()
+    return False
 
 
 def _as_ptr_array(ptrs):
@@ -413,7 +447,7 @@ class UMPAModelBase:
         s0, s1 = self._convert_ROI_slice(ROI, step)
         self._set_ROI((s0, s1))                       # sticky, like the reference (model.pyx:406)
         N0, N1 = self._shape_of(s0, s1)
-        pin = torch.cuda.is_available()
+        pin = torch.cuda.is_available() and _pinned_ready(N0 * N1, self._kind == _capi.DF, bool(debug))
         f64 = dict(dtype=torch.float64, pin_memory=pin)
         out = {k: torch.empty((N0, N1), **f64) for k in ("f", "T", "dx", "dy")}
         if self._kind == _capi.DF:
