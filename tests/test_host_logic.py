@@ -151,4 +151,4 @@ def test_bench_algorithmic_flops_match_survey():
     e5 = bench.executed_fma_per_px_cross(bench.CONFIGS["cfg5"])
     assert abs(e5 - 49 * ((4 + 13) * 32 / 20. + 13)) < 1e-9
     e4 = bench.executed_fma_per_px_cross(bench.CONFIGS["cfg4"])
-    assert abs(e4 - 225 * (40 * 24 * 32 + 7 * 24 * 26 + 7 * 18 * 26) / (18. * 26)) < 1e-9
+    assert abs(e4 - 225 * ((40 + 7) * 24 * 32 + 7 * 18 * 24) / (18. * 24)) < 1e-9      # (Nw = 3: 24 of 32 columns are outputs)
