@@ -1,6 +1,7 @@
 """GPU: handle life cycle and threading, as INTEGRATION.md states them -- different handles are independent
 (they share the per-device streams, the block cache and the pinned staging), a model per projection does not
 grow device memory, and a handle can be matched again after its frames were replaced."""
+import os
 import threading
 
 import numpy as np
@@ -151,3 +152,73 @@ def test_float32_host_frames_masked_and_dfkernel():
     k64 = umpa_b200.UMPAModelDFKernel(list(s64), list(r64), max_shift=4)
     abc = umpa_b200.synth.blur_abc(*k32.sh)
     _same(k32.match(abc=abc, quiet=True), k64.match(abc=abc, quiet=True))
+
+
+def test_staging_is_built_in_the_background():
+    """Without UMPA_STAGE_SYNC the first pipelined match() of a process does not wait for ~0.8 GB of pinned staging: it
+    goes by plain DMA (host_threads == 0) while a builder thread pins the buffer; a later call converts on the host.
+    Every call returns the same bits."""
+    import subprocess
+    import sys
+    code = r"""
+import os, sys, time
+os.environ.pop("UMPA_STAGE_SYNC", None)
+sys.path.insert(0, %r)
+import numpy as np, torch
+from umpa_b200 import UMPAModelDF, synth
+d = synth.speckle_stack(6, 1024, 1024, seed=3, max_shift=5, dark_field=True, device="cuda", as_numpy=False)
+hs = torch.empty(d["sam"].shape, dtype=torch.float64, pin_memory=True); hr = torch.empty_like(hs, pin_memory=True)
+hs.copy_(d["sam"]); hr.copy_(d["ref"]); torch.cuda.synchronize()
+sam, ref = list(hs.numpy()), list(hr.numpy())
+first, infos = None, []
+for n in range(40):
+    m = UMPAModelDF(sam, ref, window_size=2, max_shift=5)
+    r = m.match(quiet=True, debug=False)
+    infos.append(m.last_stream_info["host_threads"])
+    if first is None:
+        first = r
+    else:
+        assert all(np.array_equal(first[k], r[k]) for k in first), n
+    if infos[-1] > 0:
+        break
+    time.sleep(.05)
+print("RESULT", infos[0], infos[-1], len(infos))
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    first, last, n = (int(v) for v in out.stdout.split("RESULT")[1].split())
+    assert first == 0, "the first call waited for the staging buffer"
+    if (os.cpu_count() or 1) >= 8:              # (with few cores the library does not convert on the host at all)
+        assert last > 0, "host conversion never started (%d calls)" % n
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("path", ["table", "lazy"])
+def test_non_finite_pixels_stay_local_and_do_not_hang(path):
+    """Non-finite input pixels (a dead pixel divided by its flat field) are outside the reference's domain: with a NaN
+    cost next to finite ones its walk (Optim.cpp:233-479) can step back and forth between two evaluated shifts for
+    ever -- MAX_CALLS only counts evaluations -- and a kernel doing the same never returns (it hung a B200 once).
+    walk.cuh gives up after 16 idle loop-head visits (err = 0).  The damage must stay local: pixels whose reach does
+    not touch a bad pixel keep the clean result."""
+    import umpa_b200
+    from umpa_b200 import synth
+    d = synth.speckle_stack(6, 200, 220, seed=31, max_shift=4, dark_field=True)
+    sam, ref = np.array(d["sam"]), np.array(d["ref"])
+    clean = umpa_b200.UMPAModelDF(list(sam), list(ref), max_shift=4)
+    clean.cuda_path = path
+    want = clean.match(quiet=True, debug=False)
+    sam[2, 66, 100] = np.nan                      # rows 0, 6, 12, ... are the sampled ones (H // 32 = 6)
+    ref[1, 120, 50] = np.inf
+    m = umpa_b200.UMPAModelDF(list(sam), list(ref), max_shift=4)
+    m.cuda_path = path
+    got = m.match(quiet=True, debug=False)        # (returns: the guard ends the walks that would loop)
+    pad = m.padding
+    yy, xx = np.mgrid[pad:200 - pad, pad:220 - pad]
+    far = np.ones(yy.shape, bool)
+    for (y, x) in ((66, 100), (120, 50)):
+        far &= (np.abs(yy - y) > pad) | (np.abs(xx - x) > pad)
+    same = (got["err"] == want["err"]) & (got["debug_Ncalls"] == want["debug_Ncalls"])
+    assert same[far].mean() > .999
+    ok = far & same & (want["err"] == 1)
+    for k in ("dx", "dy", "T", "df"):
+        assert np.abs(got[k][ok] - want[k][ok]).max() < 1e-4, k

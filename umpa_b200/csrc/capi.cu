@@ -530,9 +530,9 @@ int download_outputs(const umpa_outputs &host, const umpa_outputs &dev, size_t n
 // Pinned FP32 staging for the rows the host converts (grow-only, shared by all models of the process).
 // Pinning is slow (~0.3 ms per MB: config 2 needs ~0.8 GB), so it never happens inside a call: the first call that
 // wants a bigger buffer than there is starts a builder thread and goes by plain DMA itself (no host conversion);
-// the builder allocates page-aligned memory, touches it (no CUDA involved), registers it with CUDA in 64 MB pieces
-// (each piece holds the driver's lock only briefly, so the calls of the running match are not held up) and
-// publishes it for the calls that follow.  UMPA_STAGE_SYNC=1 pins inside the call instead (tests, benchmarks of
+// the builder allocates page-aligned memory, touches it (no CUDA involved: most of the cost of pinning is faulting the
+// pages in), registers it with CUDA in ONE piece (a 2-D copy must not span two registrations) and publishes it for the
+// calls that follow.  UMPA_STAGE_SYNC=1 pins inside the call instead (tests, benchmarks of
 // the steady state from the first call on).
 struct HostStage {
     std::mutex mu;                  // held by a pipelined match for its whole duration; the builder publishes under it
@@ -553,20 +553,13 @@ void stage_release_locked()
 void stage_builder(size_t bytes, int device)
 {
     cudaSetDevice(device);
-    const size_t piece = (size_t)64 << 20;
-    bytes = (bytes + piece - 1) / piece * piece;
+    bytes = (bytes + 4095) & ~(size_t)4095;
     char *q = (char *)aligned_alloc(4096, bytes);
     bool ok = q != nullptr;
     if (ok) {
         for (size_t o = 0; o < bytes; o += 4096) q[o] = 0;                // fault the pages in (first touch on this thread)
-        size_t done = 0;
-        for (; ok && done < bytes; done += piece)
-            ok = cudaHostRegister(q + done, piece, cudaHostRegisterPortable) == cudaSuccess;
-        if (!ok) {
-            cudaGetLastError();
-            for (size_t o = 0; o + piece <= done - piece; o += piece) cudaHostUnregister(q + o);
-            free(q);
-        }
+        ok = cudaHostRegister(q, bytes, cudaHostRegisterPortable) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); free(q); }
     }
     if (ok) {
         std::lock_guard<std::mutex> lk(g_stage.mu);                      // (waits for a match that is using the old buffer)
@@ -574,7 +567,7 @@ void stage_builder(size_t bytes, int device)
             stage_release_locked();
             g_stage.p = (float *)q; g_stage.bytes = bytes; g_stage.registered = true;
         } else {
-            for (size_t o = 0; o < bytes; o += piece) cudaHostUnregister(q + o);
+            cudaHostUnregister(q);
             free(q);
         }
     }

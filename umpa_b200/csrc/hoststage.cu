@@ -1,7 +1,12 @@
 // hoststage.cu -- host-side helpers of the pipelined upload (capi.cu, streamed_match): the centring
 // constants of a frame from its sampled rows, and the FP64 -> centred FP32 conversion that lets part
 // of a stack cross PCIe at half the bytes.  Plain host code (no device code in this unit).
+#if defined(__x86_64__)
 #include <immintrin.h>
+#define UMPA_HOST_AVX2 1         // x86-64 hosts: AVX2 path chosen at run time; other hosts (aarch64: Grace + Blackwell) scalar
+#else
+#define UMPA_HOST_AVX2 0
+#endif
 #include <stddef.h>
 #include <stdint.h>
 
@@ -43,6 +48,7 @@ void convert_scalar(float *dst, const double *src, size_t n, double c)
     for (size_t i = 0; i < n; i++) dst[i] = (float)(src[i] - c);
 }
 
+#if UMPA_HOST_AVX2
 __attribute__((target("avx2"))) void convert_avx2(float *dst, const double *src, size_t n, double c)
 {
     const __m256d vc = _mm256_set1_pd(c);
@@ -56,12 +62,14 @@ __attribute__((target("avx2"))) void convert_avx2(float *dst, const double *src,
     for (; i < n; i++) dst[i] = (float)(src[i] - c);
     _mm_sfence();
 }
+#endif
 
 void convert_scalar(float *dst, const float *src, size_t n, double c)
 {
     for (size_t i = 0; i < n; i++) dst[i] = (float)((double)src[i] - c);
 }
 
+#if UMPA_HOST_AVX2
 __attribute__((target("avx2"))) void convert_avx2(float *dst, const float *src, size_t n, double c)
 {
     const __m256d vc = _mm256_set1_pd(c);
@@ -76,11 +84,19 @@ __attribute__((target("avx2"))) void convert_avx2(float *dst, const float *src, 
     for (; i < n; i++) dst[i] = (float)((double)src[i] - c);
     _mm_sfence();
 }
+#else
+inline void convert_avx2(float *dst, const double *src, size_t n, double c) { convert_scalar(dst, src, n, c); }
+inline void convert_avx2(float *dst, const float *src, size_t n, double c) { convert_scalar(dst, src, n, c); }
+#endif
 
 template <typename T>
 void center_rows(float *dst, const T *src, int rows, int W, int pitch, double c)
 {
+#if UMPA_HOST_AVX2
     static const bool avx2 = __builtin_cpu_supports("avx2");
+#else
+    const bool avx2 = false;
+#endif
     if (pitch == W) {
         if (avx2) convert_avx2(dst, src, (size_t)rows * W, c); else convert_scalar(dst, src, (size_t)rows * W, c);
         return;

@@ -20,8 +20,6 @@ Differences from the reference that a caller can see (documented, deliberate):
     state like the reference, except ``f`` which the reference leaves uninitialised.
 """
 import ctypes as C
-import os
-import threading
 
 import numpy as np
 import torch
@@ -39,38 +37,6 @@ def pool_trim():
     """Release the device blocks the library caches between models (umpa_pool_trim); returns the bytes freed.
     Call it when another allocator in the process (PyTorch's, ...) needs the memory."""
     return int(_capi.lib().umpa_pool_trim())
-
-
-# Pinning host memory is slow (~0.5 ms per MB the first time; torch caches the blocks afterwards).  The result maps of
-# the first match() of a shape therefore go to ordinary (pageable) arrays, while a helper thread puts pinned blocks of
-# the right sizes into torch's pinned-memory cache for the calls that follow: the first call of a process does not wait
-# ~100 ms for 200 MB of maps to be pinned (the reference's constructor and first call cost nothing of the kind).
-_pinned_shapes = {}
-_pinned_lock = threading.Lock()
-
-
-def _pinned_ready(npx, df, debug):
-    key = (int(npx), bool(df), bool(debug))
-    with _pinned_lock:
-        state = _pinned_shapes.get(key)
-        if state is None:
-            _pinned_shapes[key] = "warming"
-    if state == "ready" or os.environ.get("UMPA_STAGE_SYNC"):
-        return True
-    if state is None:
-        def warm():
-            try:
-                blocks = [torch.empty((npx,), dtype=torch.float64, pin_memory=True) for _ in range(5 if df else 4)]
-                blocks += [torch.empty((npx,), dtype=torch.int32, pin_memory=True) for _ in range(2)]
-                if debug:
-                    blocks += [torch.empty((npx * 25,), dtype=torch.float64, pin_memory=True),
-                               torch.empty((npx * 16,), dtype=torch.float64, pin_memory=True)]
-                del blocks                  # back to torch's pinned cache: the next match() of this shape takes them from there
-            finally:
-                with _pinned_lock:
-                    _pinned_shapes[key] = "ready"
-        threading.Thread(target=warm, daemon=True).start()
-    return False
 
 
 def _as_ptr_array(ptrs):
@@ -341,9 +307,11 @@ class UMPAModelBase:
         return self._coverage_device(s0, s1).cpu().numpy()
 
     # ------------------------------------------------------------------ match (model.pyx:334-497)
-    def match_device(self, step=None, dxdy=None, ROI=None, abc=None, debug=False, input_values=None):
+    def match_device(self, step=None, dxdy=None, ROI=None, abc=None, debug=False, cover_max=None):
         """Like match() but leaves the result maps on the GPU (torch tensors) and does not
-        synchronise.  This is the call bench.py times as the device-resident metric."""
+        synchronise.  This is the call bench.py times as the device-resident metric.
+        cover_max: the coverage maximum the gate of model.pyx:431 uses instead of this model's own (a row band of
+        a sharded match passes the maximum over all bands)."""
         if (ROI is not None) and (step is not None):
             step = None
         s0, s1 = self._convert_ROI_slice(ROI, step)
@@ -369,7 +337,7 @@ class UMPAModelBase:
         cover_t, thr = None, 0.
         if self._masked or not self._uniform:
             cover_t = self._coverage_device(s0, s1)
-            thr = .1 * float(cover_t.max()) / self._Na               # model.pyx:431
+            thr = .1 * (float(cover_t.max()) if cover_max is None else float(cover_max)) / self._Na      # model.pyx:431
         uv0 = None
         if dxdy is not None:
             uv0 = (C.c_double * 2)(float(dxdy[0]), float(dxdy[1]))   # model.pyx:463-465
@@ -447,7 +415,7 @@ class UMPAModelBase:
         s0, s1 = self._convert_ROI_slice(ROI, step)
         self._set_ROI((s0, s1))                       # sticky, like the reference (model.pyx:406)
         N0, N1 = self._shape_of(s0, s1)
-        pin = torch.cuda.is_available() and _pinned_ready(N0 * N1, self._kind == _capi.DF, bool(debug))
+        pin = torch.cuda.is_available()
         f64 = dict(dtype=torch.float64, pin_memory=pin)
         out = {k: torch.empty((N0, N1), **f64) for k in ("f", "T", "dx", "dy")}
         if self._kind == _capi.DF:

@@ -35,6 +35,10 @@ class ShardedMatcher:
     def __init__(self, cls, sam, ref, rank, world, window_size=2, max_shift=4, mask=None, **kw):
         self.rank, self.world = int(rank), int(world)
         self.padding = int(max_shift) + int(window_size) + cls.safe_crop
+        if kw.get("pos_list") is not None or any(tuple(f.shape) != tuple(sam[0].shape) for f in sam):
+            raise NotImplementedError("ShardedMatcher: equal frames at position 0 only (a ragged / stepped stack has no "
+                                      "common row bands); match it on one GPU")
+        self.masked = mask is not None
         H = sam[0].shape[0]
         self.n_rows = H - 2 * self.padding
         self.n_cols = sam[0].shape[1] - 2 * self.padding
@@ -50,6 +54,20 @@ class ShardedMatcher:
                              window_size=window_size, max_shift=max_shift, **kw)
 
     def match_device(self, **kw):
+        """The local band's maps (torch CUDA tensors).  `step` / `ROI` are not supported (the bands are cut in
+        unstrided output rows); masked models take the coverage threshold of the WHOLE frame, as the unsharded
+        match does (model.pyx:431): the bands' coverage maxima are all-reduced (MAX) first."""
+        if kw.get("step") is not None or kw.get("ROI") is not None:
+            raise NotImplementedError("ShardedMatcher.match_device: step / ROI are not supported")
+        if self.masked:
+            import torch.distributed as dist
+            local = float(self.model.coverage().max()) if self.model is not None else 0.
+            if self.world > 1 and dist.is_available() and dist.is_initialized():
+                dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+                t = torch.tensor([local], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                local = float(t.item())
+            kw["cover_max"] = local
         if self.model is None:
             return {}
         if "abc" in kw and kw["abc"] is not None:
