@@ -167,13 +167,17 @@ constexpr int MO_TH = 16, MO_TW = 64, MO_NT = 256, MO_FB = 2;     // MO_FB: fram
 //   * both raw tiles (with their Nw halo) arrive by TMA into a two-stage ring (box start 16 B aligned:
 //     LPAD >= Nw columns are loaded left of the tile; zero fill outside the frame);
 //   * row pass: an item is 4 consecutive outputs of one extended row, float4 in / float4 out, result to
-//     a shared row buffer (the 8 lanes of a quarter warp cover one 128 B line: conflict free);
-//   * column pass: every thread owns ONE float4 of the output tile: K float4 loads per stack, the two
-//     filtered values a'_k, b'_k feed the five aux accumulators (registers) and go to the filtered stacks.
-// The per-pixel sums of squares are accumulated in registers (each thread owns three float4 of the raw
-// tiles) and filtered once at the end, as an extra "frame".
+//     a shared row buffer (the 8 lanes of a quarter warp cover one 128 B line: conflict free).  The raw
+//     float4s an item loads anyway also feed the per-pixel sums of squares (each raw float4 is owned by exactly
+//     one item: its first load, and for the items at the right edge their last one);
+//   * column pass: the first four warps own the reference stack, the last four the sample stack; a thread owns
+//     TWO vertically adjacent float4 of its stack's output tile, so the K+1 row-buffer lines they need are read
+//     once (3 LDS.128 per output float4 instead of 5 for Nw = 2).  Its filtered values a'_k (or b'_k) go to the
+//     filtered stacks and feed the aux accumulators of its own stack -- T3, P3, U, M2 belong to the reference,
+//     T1, P1, V to the sample, so no thread needs the other stack's values.
+// The sums of squares are filtered once at the end, as an extra "frame".
 template <int NW>
-__global__ void __launch_bounds__(MO_NT)
+__global__ void __launch_bounds__(MO_NT, 3)
 moments_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapS, MomentsParams p)
 {
     constexpr int K = 2 * NW + 1, ER = MO_TH + 2 * NW;
@@ -183,8 +187,10 @@ moments_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_constant__
     constexpr int FR = ER * BW;                         // floats per raw frame tile (dense inside a TMA box)
     constexpr int RAW = ((MO_FB * FR * 4 + 127) & ~127) / 4; // floats per stack and ring stage: MO_FB frames (128 B multiple)
     constexpr int S4 = MO_TW / 4;                       // output strips per row
-    constexpr int NROW = 2 * ER * S4, NSQ = 2 * ER * (BW / 4);
-    constexpr int RIT = (NROW + MO_NT - 1) / MO_NT, QIT = (NSQ + MO_NT - 1) / MO_NT;
+    constexpr int NROW = 2 * ER * S4;
+    constexpr int RIT = (NROW + MO_NT - 1) / MO_NT;
+    static_assert(S4 + NL4 - 1 == BW / 4, "the row-pass items of a row load every raw float4 of it");
+    static_assert(MO_NT == 2 * (MO_TH / 2) * S4, "one thread per stack, row pair and strip");
     extern __shared__ __align__(128) float sm[];
     float *raw = sm;                                    // [2 stages][2 stacks][RAW]
     float *rowbuf = sm + 4 * RAW;                       // [2 stacks][ER][MO_TW]
@@ -211,8 +217,18 @@ moments_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_constant__
     };
     if (tid == 0) { request(0); if (nbox > 1) request(1); }
 
-    // row pass of the two tiles at `in` (reference) and `in + RAW` (sample) -> rowbuf
-    auto row_pass = [&](const float *in) {
+    // sums of squares of the raw float4s this thread's row-pass items own: [item][first load | last load]
+    float sq[RIT][2][4];
+#pragma unroll
+    for (int n = 0; n < RIT; n++)
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int x = 0; x < 4; x++) sq[n][h][x] = 0.f;
+
+    // row pass of the two tiles at `in` (reference) and `in + RAW` (sample) -> rowbuf; SQ: also accumulate the squares
+    auto row_pass = [&](const float *in, auto accumulate) {
+        constexpr bool SQ = decltype(accumulate)::value;
 #pragma unroll
         for (int n = 0; n < RIT; n++) {
             const int it = tid + n * MO_NT;
@@ -226,6 +242,14 @@ moments_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_constant__
                     const float4 t = *reinterpret_cast<const float4 *>(src + 4 * v);
                     r[4 * v] = t.x; r[4 * v + 1] = t.y; r[4 * v + 2] = t.z; r[4 * v + 3] = t.w;
                 }
+                if (SQ) {
+#pragma unroll
+                    for (int x = 0; x < 4; x++) sq[n][0][x] = fmaf(r[x], r[x], sq[n][0][x]);
+                    if (NL4 > 1 && c4 >= S4 - (NL4 - 1)) {
+#pragma unroll
+                        for (int x = 0; x < 4; x++) sq[n][1][x] = fmaf(r[4 * (NL4 - 1) + x], r[4 * (NL4 - 1) + x], sq[n][1][x]);
+                    }
+                }
                 float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int v = 0; v < K; v++)
@@ -235,92 +259,100 @@ moments_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_constant__
             }
         }
     };
-    // column pass of this thread's float4 (output row orow, strip c4) of stack st
-    const int orow = tid / S4, oc4 = tid - orow * S4;
-    auto col_pass = [&](int st, float (&o)[4]) {
-        o[0] = o[1] = o[2] = o[3] = 0.f;
-        const float *src = rowbuf + (st * ER + orow) * MO_TW + 4 * oc4;
+    // column pass of this thread's two float4 (output rows 2 og, 2 og + 1, strip oc4) of its stack
+    const int ost = tid >> 7, og = (tid & 127) / S4, oc4 = tid & (S4 - 1);
+    auto col_pass = [&](float (&o)[2][4]) {
 #pragma unroll
-        for (int u = 0; u < K; u++) {
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int x = 0; x < 4; x++) o[i][x] = 0.f;
+        const float *src = rowbuf + (ost * ER + 2 * og) * MO_TW + 4 * oc4;
+#pragma unroll
+        for (int u = 0; u <= K; u++) {
             const float4 t = *reinterpret_cast<const float4 *>(src + u * MO_TW);
-            o[0] = fmaf(g[u], t.x, o[0]); o[1] = fmaf(g[u], t.y, o[1]);
-            o[2] = fmaf(g[u], t.z, o[2]); o[3] = fmaf(g[u], t.w, o[3]);
+            if (u < K) {
+                o[0][0] = fmaf(g[u], t.x, o[0][0]); o[0][1] = fmaf(g[u], t.y, o[0][1]);
+                o[0][2] = fmaf(g[u], t.z, o[0][2]); o[0][3] = fmaf(g[u], t.w, o[0][3]);
+            }
+            if (u > 0) {
+                o[1][0] = fmaf(g[u - 1], t.x, o[1][0]); o[1][1] = fmaf(g[u - 1], t.y, o[1][1]);
+                o[1][2] = fmaf(g[u - 1], t.z, o[1][2]); o[1][3] = fmaf(g[u - 1], t.w, o[1][3]);
+            }
         }
     };
 
-    float m2[4], p3[4], uu[4], p1[4], vv[4], sq[QIT][4];
+    // aux accumulators of this thread's stack: sum x^2 (M2), sum cA x (P3 | P1), sum cB x (U | V), with x = a'_k and
+    // (cA, cB) = (c_k, d_k) for the reference stack, x = b'_k and (cA, cB) = (d_k, c_k) for the sample stack
+    float a1[2][4], a2[2][4], a3[2][4];
 #pragma unroll
-    for (int x = 0; x < 4; x++) m2[x] = p3[x] = uu[x] = p1[x] = vv[x] = 0.f;
+    for (int i = 0; i < 2; i++)
 #pragma unroll
-    for (int n = 0; n < QIT; n++)
-#pragma unroll
-        for (int x = 0; x < 4; x++) sq[n][x] = 0.f;
-    const int oy = y0 + orow, ox = x0 + 4 * oc4;
-    const bool inside = oy < p.H && ox < p.pitch;
+        for (int x = 0; x < 4; x++) a1[i][x] = a2[i][x] = a3[i][x] = 0.f;
+    const int oy = y0 + 2 * og, ox = x0 + 4 * oc4;
+    const bool in0 = oy < p.H && ox < p.pitch, in1 = oy + 1 < p.H && ox < p.pitch;
     const size_t opix = (size_t)oy * p.pitch + ox;
+    float *fdst = ost ? p.fb : p.fa;
 
     for (int k = 0; k < p.Na; k++) {
         const int box = k / MO_FB, fr = k - box * MO_FB;
         if (fr == 0) mbar_wait(&full_bar[box & 1], (box >> 1) & 1);
         const float *in = raw + (box & 1) * 2 * RAW + fr * FR;
-        row_pass(in);
-#pragma unroll
-        for (int n = 0; n < QIT; n++) {                  // squares of the raw float4s this thread owns
-            const int it = tid + n * MO_NT;
-            if (it < NSQ) {
-                const int st = it / (ER * (BW / 4)), rem = it - st * (ER * (BW / 4));
-                const float4 t = *reinterpret_cast<const float4 *>(in + st * RAW + 4 * rem);
-                sq[n][0] = fmaf(t.x, t.x, sq[n][0]); sq[n][1] = fmaf(t.y, t.y, sq[n][1]);
-                sq[n][2] = fmaf(t.z, t.z, sq[n][2]); sq[n][3] = fmaf(t.w, t.w, sq[n][3]);
-            }
-        }
+        row_pass(in, std::true_type{});
         __syncthreads();                                 // row buffer complete; after a box's last frame its stage is consumed
         if (tid == 0 && (fr == MO_FB - 1 || k == p.Na - 1) && box + 2 < nbox) request(box + 2);
-        float a[4], b[4];
-        col_pass(0, a);
-        col_pass(1, b);
+        float o[2][4];
+        col_pass(o);
         const float ck = __ldg(p.mean_r + k), dk = __ldg(p.mean_s + k);
+        const float cA = ost ? dk : ck, cB = ost ? ck : dk;
 #pragma unroll
-        for (int x = 0; x < 4; x++) {
-            m2[x] = fmaf(a[x], a[x], m2[x]);
-            p3[x] = fmaf(ck, a[x], p3[x]);
-            uu[x] = fmaf(dk, a[x], uu[x]);
-            p1[x] = fmaf(dk, b[x], p1[x]);
-            vv[x] = fmaf(ck, b[x], vv[x]);
-        }
-        if (p.fa && inside) {
-            *reinterpret_cast<float4 *>(p.fa + k * fstride + opix) = make_float4(a[0], a[1], a[2], a[3]);
-            *reinterpret_cast<float4 *>(p.fb + k * fstride + opix) = make_float4(b[0], b[1], b[2], b[3]);
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                a1[i][x] = fmaf(o[i][x], o[i][x], a1[i][x]);
+                a2[i][x] = fmaf(cA, o[i][x], a2[i][x]);
+                a3[i][x] = fmaf(cB, o[i][x], a3[i][x]);
+            }
+        if (fdst) {
+            if (in0) *reinterpret_cast<float4 *>(fdst + k * fstride + opix) = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
+            if (in1) *reinterpret_cast<float4 *>(fdst + k * fstride + opix + p.pitch) = make_float4(o[1][0], o[1][1], o[1][2], o[1][3]);
         }
         __syncthreads();                                 // row buffer free for the next frame
     }
     // the sums of squares as one more frame: T3 = w (*) sum_k R'^2, T1 = w (*) sum_k S'^2
 #pragma unroll
-    for (int n = 0; n < QIT; n++) {
+    for (int n = 0; n < RIT; n++) {
         const int it = tid + n * MO_NT;
-        if (it < NSQ) {
-            const int st = it / (ER * (BW / 4)), rem = it - st * (ER * (BW / 4));
-            *reinterpret_cast<float4 *>(raw + st * RAW + 4 * rem) = make_float4(sq[n][0], sq[n][1], sq[n][2], sq[n][3]);
+        if (it < NROW) {
+            const int st = it / (ER * S4), rem = it - st * (ER * S4);
+            const int er = rem / S4, c4 = rem - er * S4;
+            float *dst = raw + st * RAW + er * BW + 4 * c4;
+            *reinterpret_cast<float4 *>(dst) = make_float4(sq[n][0][0], sq[n][0][1], sq[n][0][2], sq[n][0][3]);
+            if (NL4 > 1 && c4 >= S4 - (NL4 - 1))
+                *reinterpret_cast<float4 *>(dst + 4 * (NL4 - 1)) = make_float4(sq[n][1][0], sq[n][1][1], sq[n][1][2], sq[n][1][3]);
         }
     }
     __syncthreads();
-    row_pass(raw);
+    row_pass(raw, std::false_type{});
     __syncthreads();
-    float t3[4], t1[4];
-    col_pass(0, t3);
-    col_pass(1, t1);
-    if (inside) {
-        const double cd = __ldg(p.consts), cc = __ldg(p.consts + 1), dd = __ldg(p.consts + 2);
+    float q[2][4];
+    col_pass(q);
+    const double cd = __ldg(p.consts), cc = __ldg(p.consts + 1), dd = __ldg(p.consts + 2);
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        if (!(i ? in1 : in0)) continue;
 #pragma unroll
         for (int x = 0; x < 4; x++) {
-            AuxR r;
-            r.t3 = (double)t3[x] + 2. * (double)p3[x] + p.sw * cc;
-            r.t2 = (double)m2[x] * p.inv_sw2 + 2. * (double)p3[x] * p.inv_sw + cc;
-            const double t6 = p.sw * r.t2;
-            r.rden = 1. / (p.kind == UMPA_DF ? r.t2 * r.t3 - t6 * t6 : r.t3);
-            r.linq = (double)uu[x] + p.sw * cd;
-            p.auxR[opix + x] = r;
-            p.auxS[opix + x] = AuxS{(double)t1[x] + 2. * (double)p1[x] + p.sw * dd, (double)vv[x]};
+            if (ost == 0) {                              // reference: q = T3, a1 = M2, a2 = P3, a3 = U
+                AuxR r;
+                r.t3 = (double)q[i][x] + 2. * (double)a2[i][x] + p.sw * cc;
+                r.t2 = (double)a1[i][x] * p.inv_sw2 + 2. * (double)a2[i][x] * p.inv_sw + cc;
+                const double t6 = p.sw * r.t2;
+                r.rden = 1. / (p.kind == UMPA_DF ? r.t2 * r.t3 - t6 * t6 : r.t3);
+                r.linq = (double)a3[i][x] + p.sw * cd;
+                p.auxR[opix + i * p.pitch + x] = r;
+            } else {                                     // sample: q = T1, a2 = P1, a3 = V
+                p.auxS[opix + i * p.pitch + x] = AuxS{(double)q[i][x] + 2. * (double)a2[i][x] + p.sw * dd, (double)a3[i][x]};
+            }
         }
     }
 }

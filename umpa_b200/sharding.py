@@ -86,38 +86,39 @@ def gather_bands(local, bands, rank, keys=("f", "T", "dx", "dy", "df", "err"), d
     """The only inter-GPU traffic of a sharded match (north_star: "a final gather of the output maps"): rank r
     contributes maps of shape (bands[r][1]-bands[r][0], N1); rank `dst` receives their row-wise concatenation.
 
-    The float64 maps of a rank travel as ONE packed tensor and the int32 maps as another, so a gather is two
-    torch.distributed.gather calls whatever the number of maps (NCCL over NVLink for CUDA tensors, gloo for CPU
-    tensors); no Python objects are exchanged.  Every rank must pass the same `keys`; keys a model does not
-    produce (df for NoDF) are dropped by name on every rank alike.  n_cols: map width (needed by a rank whose
-    band is empty)."""
+    Point to point, one batch: every rank sends each of its maps straight into the row slice it occupies in the full
+    map on `dst` (torch.distributed.batch_isend_irecv -- one NCCL group over NVLink for CUDA tensors, gloo for CPU
+    tensors), so nothing is packed, padded or copied twice and no Python objects are exchanged.  Every rank must pass
+    the same `keys`; a key the model does not produce (df for NoDF) is skipped on every rank alike.  n_cols: map width
+    (needed by a `dst` whose own band is empty; it then expects every key)."""
     import torch.distributed as dist
-    world = len(bands)
-    rows = max(b[1] - b[0] for b in bands)                    # bands differ by at most one row: pad to the tallest
+    n_rows = bands[-1][1]
     mine = bands[rank][1] - bands[rank][0]
     some = next((local[k] for k in keys if local.get(k) is not None), None)
-    if some is not None:
-        n_cols = int(some.shape[1])
-        dev = some.device
-    else:
-        if n_cols is None:
-            raise ValueError("gather_bands: a rank with an empty band needs n_cols")
-        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-    out = {}
-    for group, dtype in ((tuple(k for k in keys if k not in _INT_KEYS), torch.float64),
-                         (tuple(k for k in keys if k in _INT_KEYS), torch.int32)):
-        if not group:
-            continue
-        send = torch.zeros((len(group), rows, n_cols), dtype=dtype, device=dev)
-        for n, k in enumerate(group):
+    ops, out = [], {}
+    if rank == dst:
+        if some is not None:
+            n_cols, dev = int(some.shape[1]), some.device
+        else:
+            if n_cols is None:
+                raise ValueError("gather_bands: a destination with an empty band needs n_cols")
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        for k in keys:
             t = local.get(k)
-            if t is not None and mine:
-                send[n, :mine] = t
-        parts = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
-        dist.gather(send, parts, dst=dst)
-        if rank == dst:
-            full = torch.cat([p_[:, :b[1] - b[0]] for p_, b in zip(parts, bands)], dim=1)
-            for n, k in enumerate(group):
-                if local.get(k) is not None or not mine:      # a map the model does not produce (df for NoDF) is dropped
-                    out[k] = full[n]
+            if t is None and mine:
+                continue
+            full = torch.empty((n_rows, n_cols), dtype=torch.int32 if k in _INT_KEYS else torch.float64, device=dev)
+            if mine:
+                full[bands[rank][0]:bands[rank][1]] = t
+            for r, (r0, r1) in enumerate(bands):
+                if r != dst and r1 > r0:
+                    ops.append(dist.P2POp(dist.irecv, full[r0:r1], r))
+            out[k] = full
+    elif mine:
+        for k in keys:
+            t = local.get(k)
+            if t is not None:
+                ops.append(dist.P2POp(dist.isend, t.contiguous(), dst))
+    for req in (dist.batch_isend_irecv(ops) if ops else []):
+        req.wait()
     return out if rank == dst else None
