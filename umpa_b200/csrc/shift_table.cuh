@@ -9,6 +9,9 @@
 
 #include "common.cuh"
 
+#ifndef UMPA_FFMA2_MAX_S
+#define UMPA_FFMA2_MAX_S 99      // packed FFMA2 in the main loop for S <= this (experiments: 0 = plain FFMA everywhere)
+#endif
 #ifndef UMPA_COLPASS4
 #define UMPA_COLPASS4 1          // 1: column pass of the filter epilogue on four output rows per thread (see the kernel)
 #endif
@@ -62,6 +65,7 @@ struct TableParams {
     int TW;                      // output columns per strip
     int EH;                      // chunk rows (chunk columns are EXT_W)
     int seg_rows, nseg, nstrips; // items: nstrips x nseg segments of seg_rows output rows (the last one may be shorter)
+    int nchunk_full, nchunk_last;// chunks of a full segment / of the last one (host: no integer division per item)
     int AH, AP;                  // A tile rows, pitch (= TMA box width)
     int G, npass, nstage;
     int a_stage_floats, stage_floats;   // per-stage layout: A tile then B tile (128 B aligned)
@@ -134,9 +138,14 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     const uint32_t stage_bytes = (uint32_t)(p.FB * (p.AH * p.AP + p.EH * EXT_W)) * sizeof(float);
     const int a_frame = p.AH * p.AP, b_frame = p.EH * EXT_W;             // one frame inside a stage
 
-    float gk[K];
+    // BIG: 120 accumulators per thread (S >= 11).  Registers that are live across the frame loop then cost the A rows in
+    // flight (see the producer state below), so the epilogue's per-chunk quantities and the window factors are
+    // derived after the frame loop; with 108 accumulators (S <= 9) deriving them early is what ptxas schedules best
+    // (measured both ways on both: config 2's cross table 0.87 vs 0.99 ms, config 4's 29.4 vs 24.3 ms).
+    constexpr bool BIG = SH * S * 4 > 112;
+    float gk_early[K];
 #pragma unroll
-    for (int v = 0; v < K; v++) gk[v] = FILTER ? __ldg(p.g + v) : 1.f;
+    for (int v = 0; v < K; v++) gk_early[v] = (FILTER && !BIG) ? __ldg(p.g + v) : 1.f;
     if (tid == 0) {
         for (int s = 0; s < p.nstage; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], nt / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -146,45 +155,76 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
     // ---- persistent CTA: items blockIdx.x, +gridDim.x, ... ; the frame ring runs across chunks and items ----
     // item -> (strip, segment); neighbouring CTAs work on neighbouring strips at the same time (shared x halos in L2)
+    // (segment, strip) of an item advance by gridDim.x items at a time: carried along instead of divided out
     const int nitems = p.nstrips * p.nseg;
-    auto seg_rows_of = [&](int item) { const int r0 = (item / p.nstrips) * p.seg_rows; return min(p.seg_rows, p.rows - r0); };
-    auto chunks_of = [&](int rows) { return (rows + H2 + p.EH - 1) / p.EH; };
+    const int step_seg = (int)gridDim.x / p.nstrips, step_strip = (int)gridDim.x - step_seg * p.nstrips;
+    auto advance = [&](int &seg, int &strip) {
+        seg += step_seg; strip += step_strip;
+        if (strip >= p.nstrips) { strip -= p.nstrips; seg++; }
+    };
+    auto chunks_of_seg = [&](int seg) { return seg == p.nseg - 1 ? p.nchunk_last : p.nchunk_full; };
+    const int seg_first = (int)blockIdx.x / p.nstrips, strip_first = (int)blockIdx.x - seg_first * p.nstrips;
     // A ring stage holds FB consecutive frames (one TMA box per stack): a box costs ~450-500 cycles of
     // TMA-unit time whatever its size (measured: A only, B only and both take the same time with the FMA
     // loop and the epilogue switched off), so one box per frame capped the kernel at ~515 cycles per frame.
     const int nbox = (p.Na + p.FB - 1) / p.FB;       // boxes per pass over the frames (the last one may run past Na: zero fill)
     const int per_chunk = p.npass * nbox;
 
-    // producer state (thread 0): next (item, chunk, frame) to request, and where
-    int total = 0, pr_issued = 0, pr_item = blockIdx.x, pr_chunks = 0, pr_left = per_chunk, pr_frame = 0, pr_stage = 0;
-    int pr_ax = 0, pr_ay = 0, pr_bx = 0, pr_by = 0;
-    auto pr_coords = [&]() {                         // first chunk of pr_item
-        if (pr_item >= nitems) return;
-        const int seg = pr_item / p.nstrips, strip = pr_item - seg * p.nstrips;
-        pr_by = p.oy + seg * p.seg_rows - HALO; pr_bx = p.ox + strip * p.TW - HALO;
-        pr_ay = pr_by - HS; pr_ax = pr_bx - HS - DELTA;
-        pr_chunks = chunks_of(seg_rows_of(pr_item));
+    // producer state (thread 0): next (item, chunk, frame) to request, and where.  Only one thread uses it, once per
+    // box, but as local variables it holds a dozen registers in EVERY thread across the frame loop.  With 120
+    // accumulators per thread (S >= 11) those registers are what the A rows in flight need: with the state in registers
+    // every A row load waited for the previous row's FMAs and config 4 (S = 15) lost 20 %, so there it lives in shared
+    // memory.  With 108 accumulators (S <= 9) there is room, and the serial shared-memory round trips of thread 0 would
+    // make warp 0 the straggler of every barrier (config 2: +6 %): registers.
+    struct Producer { int total, issued, item, chunks, left, frame, stage, ax, ay, bx, by, seg, strip; };
+    __shared__ Producer pr_shared;
+    Producer pr_local;
+    Producer &pr = BIG ? pr_shared : pr_local;
+    auto pr_coords = [&]() {                         // first chunk of pr.item = (pr.seg, pr.strip)
+        if (pr.item >= nitems) return;
+        pr.by = p.oy + pr.seg * p.seg_rows - HALO; pr.bx = p.ox + pr.strip * p.TW - HALO;
+        pr.ay = pr.by - HS; pr.ax = pr.bx - HS - DELTA;
+        pr.chunks = chunks_of_seg(pr.seg);
     };
     auto issue_next = [&]() {
-        float *As = sm + (size_t)pr_stage * p.stage_floats, *Bs = As + p.a_stage_floats;
-        mbar_expect_tx(&full_bar[pr_stage], stage_bytes);
-        tma_load_3d(As, &mapA, pr_ax, pr_ay, pr_frame, &full_bar[pr_stage]);
-        tma_load_3d(Bs, &mapB, pr_bx, pr_by, pr_frame, &full_bar[pr_stage]);
-        pr_issued++;
-        if (++pr_stage == p.nstage) pr_stage = 0;
-        pr_frame += p.FB;
-        if (pr_frame >= p.Na) pr_frame = 0;
-        if (--pr_left == 0) {                        // next chunk of the item, or the next item
-            pr_left = per_chunk;
-            if (--pr_chunks > 0) { pr_by += p.EH; pr_ay += p.EH; }
-            else { pr_item += gridDim.x; pr_coords(); }
+        const int st = pr.stage;
+        float *As = sm + (size_t)st * p.stage_floats, *Bs = As + p.a_stage_floats;
+        mbar_expect_tx(&full_bar[st], stage_bytes);
+        tma_load_3d(As, &mapA, pr.ax, pr.ay, pr.frame, &full_bar[st]);
+        tma_load_3d(Bs, &mapB, pr.bx, pr.by, pr.frame, &full_bar[st]);
+        pr.issued++;
+        pr.stage = st + 1 == p.nstage ? 0 : st + 1;
+        pr.frame = pr.frame + p.FB >= p.Na ? 0 : pr.frame + p.FB;
+        if (--pr.left == 0) {                        // next chunk of the item, or the next item
+            pr.left = per_chunk;
+            if (--pr.chunks > 0) { pr.by += p.EH; pr.ay += p.EH; }
+            else { pr.item += gridDim.x; advance(pr.seg, pr.strip); pr_coords(); }
         }
     };
     if (tid == 0) {
-        for (int it = blockIdx.x; it < nitems; it += gridDim.x) total += chunks_of(seg_rows_of(it)) * per_chunk;
+        int total = 0;
+        for (int it = blockIdx.x, sg = seg_first, sp = strip_first; it < nitems; it += gridDim.x, advance(sg, sp))
+            total += chunks_of_seg(sg) * per_chunk;
+        pr.total = total; pr.issued = 0; pr.item = blockIdx.x; pr.left = per_chunk; pr.frame = 0; pr.stage = 0;
+        pr.seg = seg_first; pr.strip = strip_first; pr.chunks = 0;
         pr_coords();
         for (int n = 0; n < p.nstage && n < total; n++) issue_next();
     }
+
+    // What the epilogue needs to know about a chunk.  Output row of this thread: the column pass ends at its own chunk
+    // row (taps er-H2 .. er); the four-row column pass works on groups of four chunk rows e4 .. e4+3 (output rows
+    // r_out4 .. r_out4+3, row_ok: which of them are stored).
+    struct Epi { int r_out, r_out4; unsigned row_ok; bool store; };
+    auto make_epi = [&](int chunk, int item_rows) {
+        Epi e;
+        e.r_out = chunk * p.EH + er - H2;
+        e.store = e.r_out >= 0 && e.r_out < item_rows && ec < p.TW;
+        e.r_out4 = chunk * p.EH + (er & ~3) - H2;
+        e.row_ok = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) e.row_ok |= (e.r_out4 + i >= 0 && e.r_out4 + i < item_rows && ec < p.TW) ? 1u << i : 0u;
+        return e;
+    };
 
     int stage = 0, phase = 0;                        // consumer ring position
     int prev_stage = 0, prev_phase = 0;
@@ -198,22 +238,12 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #define ACC(SH_, SJ_, PX_) (((PX_) & 1) ? ((SJ_) == S - 1 ? accs[SH_][(PX_) >> 1][1] : accp[SH_][(PX_) >> 1][(SJ_)].y) \
                                         : ((SJ_) == 0 ? accs[SH_][(PX_) >> 1][0] : accp[SH_][(PX_) >> 1][(SJ_) - 1].x))
 
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-      const int seg = item / p.nstrips, strip = item - seg * p.nstrips;
+    for (int item = blockIdx.x, seg = seg_first, strip = strip_first; item < nitems; item += gridDim.x, advance(seg, strip)) {
       const int row0 = seg * p.seg_rows, tx0 = strip * p.TW;             // table coords of the item
-      const int item_rows = min(p.seg_rows, p.rows - row0), nchunk = chunks_of(item_rows);
+      const int item_rows = min(p.seg_rows, p.rows - row0), nchunk = chunks_of_seg(seg);
       for (int chunk = 0; chunk < nchunk; chunk++) {
-        // output row of this thread in this chunk: the column pass ends at its own chunk row (taps er-H2 .. er)
-        const int r_out = chunk * p.EH + er - H2;
-        const bool store = r_out >= 0 && r_out < item_rows && ec < p.TW;
-#if UMPA_COLPASS4
-        // FILTER: the column pass works on groups of four chunk rows e4 .. e4+3 (output rows r_out4 .. r_out4+3)
-        const int e4 = er & ~3, qi = er & 3, r_out4 = chunk * p.EH + e4 - H2;
-        unsigned row_ok = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) row_ok |= (r_out4 + i >= 0 && r_out4 + i < item_rows && ec < p.TW) ? 1u << i : 0u;
-        const bool any_store = row_ok != 0;
-#endif
+        Epi epi_early{};
+        if (!BIG) epi_early = make_epi(chunk, item_rows);
         for (int pass = 0; pass < p.npass; pass++) {
             const int si0 = (pass * p.G + grp) * SH; // first shift row of this thread in this pass
             const bool work = si0 < S;
@@ -227,7 +257,7 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                 }
 
             for (int box = 0; box < nbox; box++) {
-                if (tid == 0 && !first && pr_issued < total) {           // refill the stage the previous box used
+                if (tid == 0 && !first && pr.issued < pr.total) {        // refill the stage the previous box used
                     mbar_wait(&empty_bar[prev_stage], prev_phase);
                     issue_next();
                 }
@@ -257,7 +287,12 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
                                 for (int t = 1; t < S; t++) {
                                     const float a = av[DELTA + t + 2 * xp];
-                                    accp[sh][xp][t - 1] = __ffma2_rn(make_float2(a, a), bp[xp], accp[sh][xp][t - 1]);
+                                    if (S <= UMPA_FFMA2_MAX_S)
+                                        accp[sh][xp][t - 1] = __ffma2_rn(make_float2(a, a), bp[xp], accp[sh][xp][t - 1]);
+                                    else {
+                                        accp[sh][xp][t - 1].x = fmaf(a, bp[xp].x, accp[sh][xp][t - 1].x);
+                                        accp[sh][xp][t - 1].y = fmaf(a, bp[xp].y, accp[sh][xp][t - 1].y);
+                                    }
                                 }
                                 accs[sh][xp][1] = fmaf(bp[xp].y, av[DELTA + S + 2 * xp], accs[sh][xp][1]);
                             }
@@ -271,6 +306,17 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             }
 
             // ---------------- epilogue of this pass ----------------
+            const Epi epi = BIG ? make_epi(chunk, item_rows) : epi_early;
+            const int r_out = epi.r_out;
+            const bool store = epi.store;
+#if UMPA_COLPASS4
+            const int e4 = er & ~3, qi = er & 3, r_out4 = epi.r_out4;
+            const unsigned row_ok = epi.row_ok;
+            const bool any_store = row_ok != 0;
+#endif
+            float gk[K];
+#pragma unroll
+            for (int v = 0; v < K; v++) gk[v] = (FILTER && BIG) ? __ldg(p.g + v) : gk_early[v];
             if (p.dbg & 1) {
                 if (work && tid == 0x7fffffff) p.table[0] = ACC(0, 0, 0);      // keeps the accumulators alive
             } else if (!FILTER) {
@@ -437,7 +483,6 @@ int launch_shift_table(const CUtensorMap &mapA, const CUtensorMap &mapB, const T
     cudaGetDevice(&dev);
     if (smem > attr_set[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) { umpa_set_error("cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e)); return UMPA_ERR_CUDA; }
         attr_set[dev & 63] = smem;
     }

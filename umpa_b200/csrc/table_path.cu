@@ -369,8 +369,8 @@ struct WalkParams {
     const float *tabX;              // the tables: entry (row, shift, col) of the cross table at
                                     // tabX[row * row_stride + shift * tpitch + col], of the mean table (DF) m_off floats
                                     // further (shift_table.cuh: TableParams)
-    size_t row_stride;
-    int tpitch, m_off;
+    size_t row_stride, m_off;
+    unsigned tpitch;                // floats between consecutive shifts of one pixel
     const AuxS *auxS;               // [H][pitch], raw coordinates
     const AuxR *auxR;
     int pitch;
@@ -432,7 +432,7 @@ struct TableEval {
             return UMPA_ST_OK;
         }
         // the gathers of one evaluation: one aux record + one entry per table, a fixed distance apart
-        const float *px = pX + sidx * (unsigned)w.tpitch;
+        const float *px = pX + (size_t)sidx * w.tpitch;
         const float x = __ldg(px);
         const float m = KIND == UMPA_DF ? __ldg(px + w.m_off) : 0.f;
         if (RS) {
@@ -699,6 +699,8 @@ size_t plan_tiles(TableParams &p, int S, bool filter, int *nt, int rows, int col
         p.seg_rows = (rows + best_n - 1) / best_n;
     }
     p.nseg = (rows + p.seg_rows - 1) / p.seg_rows;
+    p.nchunk_full = (p.seg_rows + H2 + p.EH - 1) / p.EH;
+    p.nchunk_last = (rows - (p.nseg - 1) * p.seg_rows + H2 + p.EH - 1) / p.EH;
     *nt = p.G * p.EH * 8;
     return best_smem;
 }
@@ -853,7 +855,12 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         // (2 S*S for DF) segments -- a few hundred KB -- instead of S*S planes of the image size
         px.plane_stride = pm.plane_stride = tpitch;
         px.row_stride = pm.row_stride = (size_t)(df ? 2 : 1) * S * S * tpitch;
-        if ((rc = scratch_reserve(m, m->tabX, (size_t)rows_alloc * px.row_stride * sizeof(float)))) return rc;
+        if (getenv("UMPA_TAB_PLANES")) {            // experiment: shift-major planes [table][shift][row][col]
+            px.plane_stride = pm.plane_stride = rows_alloc * tpitch;
+            px.row_stride = pm.row_stride = tpitch;
+        }
+        if ((rc = scratch_reserve(m, m->tabX, (size_t)(df ? 2 : 1) * S * S * rows_alloc * tpitch * sizeof(float)))) return rc;
+
     }
     const size_t img = (size_t)H * pitch;
     if ((rc = scratch_reserve(m, m->auxS, img * sizeof(AuxS)))) return rc;
@@ -914,7 +921,7 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         const float *fix = (const float *)(m->refshift ? m->filtA.p : m->filtB.p);
         if ((rc = make_stack_map(&ma, mov, Na, H, m->W, pitch, pm.AP, pm.AH, pm.FB))) return rc;
         if ((rc = make_stack_map(&mb, fix, Na, H, m->W, pitch, EXT_W, pm.EH, pm.FB))) return rc;
-        pm.table = (float *)m->tabX.p + (size_t)S * S * pm.plane_stride;
+        pm.table = (float *)m->tabX.p + (size_t)S * S * pm.plane_stride;     // (either layout: the mean table follows the S*S cross shifts)
         dim3 grid(std::min(pm.nstrips * pm.nseg, m->sm_count * ctas_per_sm()));
         if ((rc = dispatch_shift_table(false, S, ma, mb, pm, grid, ntm, smm, st))) return rc;
         m->last_launches++;
@@ -926,8 +933,8 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
     {
         WalkParams w{};
         w.tabX = (const float *)m->tabX.p;
-        w.row_stride = px.row_stride; w.tpitch = px.plane_stride;
-        w.m_off = S * S * px.plane_stride + dxM - dxX;
+        w.row_stride = px.row_stride; w.tpitch = (unsigned)px.plane_stride;
+        w.m_off = (size_t)S * S * px.plane_stride + dxM - dxX;
         if (dfk) {
             w.ktab = w.tabX; w.kstride = ktable_row_floats(m->max_shift);
             double swk = 0.;                           // exact sum of float(g_a) * float(g_b) as FP32 products
