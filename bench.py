@@ -60,24 +60,14 @@ def algorithmic_flops_per_px(cfg):
 
 
 def table_plan(cfg):
-    """(streaming, chunk rows) of the cross-table kernel for a configuration -- the choice plan_tiles (table_path.cu)
-    makes: streaming row segments when the carry (S^2 planes x 2 Nw rows x 128 B) fits shared memory next to the filter
-    buffer and a three-stage frame ring, else halo tiles whose height minimises rows computed per useful row at
-    +15 % per extra pass over the frames."""
-    S, Nw, Na = 2 * cfg["ms"] - 1, cfg["Nw"], cfg["Na"]
-    hs, sh = S // 2, (3 if S <= 9 else (2 if S <= 17 else 1))
-    delta = (4 - hs % 4) % 4
-    ap = 28 + 4 * ((delta + S + 6) // 4)
-
-    def groups(eh):
-        return min(384 // (eh * 8), -(-S // sh))
-    stage16 = min(4, Na) * ((16 + 2 * hs) * ap + 16 * 32) * 4      # (plan_tiles shortens the TMA boxes until three stages fit)
-    if S * S * 2 * Nw * 128 + groups(16) * S * 16 * 128 + 3 * stage16 <= 225 * 1024 and Nw > 0:
-        return True, 16
-
-    def cost(eh):
-        return eh / float(eh - 2 * Nw) * (1. + .15 * (-(-S // (groups(eh) * sh)) - 1))
-    return False, min((e for e in (16, 24, 32, 48) if e - 2 * Nw >= 2), key=lambda e: (cost(e), e))
+    """(streaming, chunk rows) of the cross-table kernel for a configuration: the plan the library itself makes
+    (umpa_table_plan -> plan_tiles, table_path.cu; host arithmetic, no device needed)."""
+    import ctypes
+    from umpa_b200 import _capi
+    out = (ctypes.c_int * 10)()
+    rows, cols = (cfg[k] - 2 * (cfg["Nw"] + cfg["ms"]) for k in ("H", "W"))
+    _capi.check(_capi.lib().umpa_table_plan(cfg["Na"], cfg["Nw"], cfg["ms"], rows, cols, 148, out))
+    return out[1] > 0, out[0]
 
 
 def executed_fma_per_px_cross(cfg):

@@ -205,6 +205,12 @@ UMPA_API double umpa_host_sampled_mean_f32(const float *frame, int H, int W, int
 UMPA_API void umpa_host_center_rows(float *dst, const double *src, int rows, int W, int pitch, double c);
 UMPA_API void umpa_host_center_rows_f32(float *dst, const float *src, int rows, int W, int pitch, double c);
 
+/* Geometry the table path chooses for the cross table of a match over rows x cols pixels (host arithmetic, no
+ * device needed): out = chunk rows EH, order (0 halo tiles, 1 streaming chunk-major, 2 streaming pass-major),
+ * warp groups G, passes over the frames, frames per TMA box, ring stages, output columns per strip TW, row
+ * segments, column strips, threads per CTA.  For bench.py's executed-work model and the tests. */
+UMPA_API int umpa_table_plan(int Na, int Nw, int max_shift, int rows, int cols, int sm_count, int out[10]);
+
 /* Measured FP32-FMA peak of the current device (dependent-free FFMA chains on all SMs, CUDA
  * events): the denominator of the FP32-FMA roofline that bench.py reports. */
 UMPA_API int umpa_fma_peak(double *tflops, int *sm_count);

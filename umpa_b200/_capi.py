@@ -13,7 +13,7 @@ PATH_NAMES = {0: "none", 1: "table", 2: "lazy", 3: "mixed"}
 
 EXPORTS = ("umpa_create", "umpa_destroy", "umpa_set_frames", "umpa_set_frames_f32", "umpa_set_window", "umpa_set_option",
            "umpa_get_option", "umpa_match", "umpa_match_host", "umpa_cost", "umpa_min", "umpa_coverage", "umpa_correct_bad_pixels",
-           "umpa_last_match_info", "umpa_last_stream_info", "umpa_set_profiling", "umpa_last_stage_ms", "umpa_device_bytes", "umpa_pool_trim",
+           "umpa_last_match_info", "umpa_last_stream_info", "umpa_set_profiling", "umpa_last_stage_ms", "umpa_device_bytes", "umpa_pool_trim", "umpa_table_plan",
            "umpa_fma_peak", "umpa_host_sampled_mean", "umpa_host_sampled_mean_f32", "umpa_host_center_rows", "umpa_host_center_rows_f32", "umpa_last_error", "umpa_version")
 
 
@@ -79,6 +79,8 @@ def lib():
     L.umpa_device_bytes.argtypes = [vp]
     L.umpa_pool_trim.restype = C.c_int64
     L.umpa_pool_trim.argtypes = []
+    L.umpa_table_plan.restype = C.c_int
+    L.umpa_table_plan.argtypes = [C.c_int] * 6 + [C.POINTER(C.c_int)]
     L.umpa_fma_peak.restype = C.c_int
     L.umpa_fma_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.umpa_host_sampled_mean.restype = C.c_double

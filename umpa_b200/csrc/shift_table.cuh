@@ -66,6 +66,10 @@ struct TableParams {
     int EH;                      // chunk rows (chunk columns are EXT_W)
     int seg_rows, nseg, nstrips; // items: nstrips x nseg segments of seg_rows output rows (the last one may be shorter)
     int nchunk_full, nchunk_last;// chunks of a full segment / of the last one (host: no integer division per item)
+    int stream;                  // (host) 0 halo tiles, 1 streaming chunk-major, 2 streaming pass-major
+    int pass_major;              // streaming when all S*S carry planes do not fit: the passes of an item become the outer
+                                 // loop (pass -> chunk instead of chunk -> pass), so that only the G*SH*S planes of the
+                                 // current pass need a carry (config 4: 60 of 225 planes, 46 KB)
     int AH, AP;                  // A tile rows, pitch (= TMA box width)
     int G, npass, nstage;
     int a_stage_floats, stage_floats;   // per-stage layout: A tile then B tile (128 B aligned)
@@ -143,6 +147,10 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     // derived after the frame loop; with 108 accumulators (S <= 9) deriving them early is what ptxas schedules best
     // (measured both ways on both: config 2's cross table 0.87 vs 0.99 ms, config 4's 29.4 vs 24.3 ms).
     constexpr bool BIG = SH * S * 4 > 112;
+    // pass-major order (TableParams::pass_major) exists where a table can need more than one pass at the streaming
+    // chunk height: S >= 11.  Compiled out below that -- the order selects cost the S = 9 kernel 10 % (config 2).
+    constexpr bool PMC = S >= 11;
+    const bool pass_major = PMC && p.pass_major;
     float gk_early[K];
 #pragma unroll
     for (int v = 0; v < K; v++) gk_early[v] = (FILTER && !BIG) ? __ldg(p.g + v) : 1.f;
@@ -176,7 +184,7 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     // every A row load waited for the previous row's FMAs and config 4 (S = 15) lost 20 %, so there it lives in shared
     // memory.  With 108 accumulators (S <= 9) there is room, and the serial shared-memory round trips of thread 0 would
     // make warp 0 the straggler of every barrier (config 2: +6 %): registers.
-    struct Producer { int total, issued, item, chunks, left, frame, stage, ax, ay, bx, by, seg, strip; };
+    struct Producer { int total, issued, item, chunks, left, frame, stage, ax, ay, bx, by, seg, strip, inner, outer; };
     __shared__ Producer pr_shared;
     Producer pr_local;
     Producer &pr = BIG ? pr_shared : pr_local;
@@ -195,18 +203,33 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         pr.issued++;
         pr.stage = st + 1 == p.nstage ? 0 : st + 1;
         pr.frame = pr.frame + p.FB >= p.Na ? 0 : pr.frame + p.FB;
-        if (--pr.left == 0) {                        // next chunk of the item, or the next item
-            pr.left = per_chunk;
-            if (--pr.chunks > 0) { pr.by += p.EH; pr.ay += p.EH; }
-            else { pr.item += gridDim.x; advance(pr.seg, pr.strip); pr_coords(); }
+        if (--pr.left == 0) {                        // next (chunk, pass) of the item in the consumers' order, or the next item
+            if constexpr (!PMC) {                    // chunk -> pass, counted as one run of boxes per chunk
+                pr.left = per_chunk;
+                if (--pr.chunks > 0) { pr.by += p.EH; pr.ay += p.EH; }
+                else { pr.item += gridDim.x; advance(pr.seg, pr.strip); pr_coords(); }
+            } else {
+                pr.left = nbox;
+                bool item_done = false;
+                if (!pass_major) {                   // chunk -> pass: the tile moves down after the last pass of a chunk
+                    if (++pr.inner == p.npass) { pr.inner = 0; pr.by += p.EH; pr.ay += p.EH; item_done = ++pr.outer == pr.chunks; }
+                } else {                             // pass -> chunk: down after every unit, back up after the last chunk
+                    pr.by += p.EH; pr.ay += p.EH;
+                    if (++pr.inner == pr.chunks) {
+                        pr.inner = 0; pr.by -= pr.chunks * p.EH; pr.ay -= pr.chunks * p.EH;
+                        item_done = ++pr.outer == p.npass;
+                    }
+                }
+                if (item_done) { pr.outer = 0; pr.item += gridDim.x; advance(pr.seg, pr.strip); pr_coords(); }
+            }
         }
     };
     if (tid == 0) {
         int total = 0;
         for (int it = blockIdx.x, sg = seg_first, sp = strip_first; it < nitems; it += gridDim.x, advance(sg, sp))
             total += chunks_of_seg(sg) * per_chunk;
-        pr.total = total; pr.issued = 0; pr.item = blockIdx.x; pr.left = per_chunk; pr.frame = 0; pr.stage = 0;
-        pr.seg = seg_first; pr.strip = strip_first; pr.chunks = 0;
+        pr.total = total; pr.issued = 0; pr.item = blockIdx.x; pr.left = PMC ? nbox : per_chunk; pr.frame = 0; pr.stage = 0;
+        pr.seg = seg_first; pr.strip = strip_first; pr.chunks = 0; pr.inner = 0; pr.outer = 0;
         pr_coords();
         for (int n = 0; n < p.nstage && n < total; n++) issue_next();
     }
@@ -241,10 +264,13 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     for (int item = blockIdx.x, seg = seg_first, strip = strip_first; item < nitems; item += gridDim.x, advance(seg, strip)) {
       const int row0 = seg * p.seg_rows, tx0 = strip * p.TW;             // table coords of the item
       const int item_rows = min(p.seg_rows, p.rows - row0), nchunk = chunks_of_seg(seg);
-      for (int chunk = 0; chunk < nchunk; chunk++) {
+      const int n_outer = pass_major ? p.npass : nchunk, n_inner = pass_major ? nchunk : p.npass;
+      for (int outer = 0; outer < n_outer; outer++) {
         Epi epi_early{};
-        if (!BIG) epi_early = make_epi(chunk, item_rows);
-        for (int pass = 0; pass < p.npass; pass++) {
+        if (!PMC) epi_early = make_epi(outer, item_rows);
+        for (int inner = 0; inner < n_inner; inner++) {
+            const int chunk = pass_major ? inner : outer, pass = pass_major ? outer : inner;
+            if (PMC && !BIG) epi_early = make_epi(chunk, item_rows);
             const int si0 = (pass * p.G + grp) * SH; // first shift row of this thread in this pass
             const bool work = si0 < S;
 #pragma unroll
@@ -351,6 +377,8 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                 for (int sh = 0; sh < SH; sh++) {
                     const int si = si0 + sh;
                     if (!work || si >= S) continue;              // uniform per group
+                    // first carry plane of this shift row: all S*S planes are kept, or only those of the current pass
+                    const int cplane0 = pass_major ? (grp * SH + sh) * S : si * S;
 #pragma unroll
                     for (int sj = 0; sj < S; sj++) {
                         float c[4 + 4 * NSH];
@@ -380,7 +408,7 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                     if (any_store) {
                         float *dq = p.table + (size_t)(row0 + r_out4) * p.row_stride + (size_t)(si * S + qi) * p.plane_stride + tx0 + ec;
                         const float *cb = cbuf + (size_t)(grp * S + qi) * plane + ec;             // chunk row 0 of plane qi
-                        const float *cr = carry + (size_t)((si * S + qi) * H2) * EXT_W + ec;      // carry row 0 of plane qi
+                        const float *cr = carry + (size_t)((cplane0 + qi) * H2) * EXT_W + ec;     // carry row 0 of plane qi
                         auto colpass = [&](auto e4c) {
                             constexpr int E4 = decltype(e4c)::value;
                             const float *base = E4 < 0 ? cb + (e4 - H2) * EXT_W : cb;
@@ -438,7 +466,7 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                             }
                         } else {                                 // taps er+u < 2Nw come from the previous chunk's last rows
                             const float *cw = cbuf + (size_t)grp * S * plane + ec;
-                            const float *cr = carry + (size_t)(si * S) * (H2 * EXT_W) + ec;
+                            const float *cr = carry + (size_t)cplane0 * (H2 * EXT_W) + ec;
 #pragma unroll
                             for (int sj = 0; sj < S; sj++) {
                                 float2 o01 = make_float2(0.f, 0.f), o23 = make_float2(0.f, 0.f);
@@ -457,7 +485,7 @@ shift_table_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #endif
                     asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(TG) : "memory");
                     if (H2 > 0 && keep) {                        // (after the barrier: the readers of the old carry are done)
-                        float *cr = carry + ((size_t)(si * S) * H2 + (er - (p.EH - H2))) * EXT_W + ec;
+                        float *cr = carry + ((size_t)cplane0 * H2 + (er - (p.EH - H2))) * EXT_W + ec;
 #pragma unroll
                         for (int sj = 0; sj < S; sj++)
                             *reinterpret_cast<float4 *>(cr + sj * (H2 * EXT_W)) = *reinterpret_cast<const float4 *>(cg + sj * plane);

@@ -636,17 +636,22 @@ size_t plan_tiles(TableParams &p, int S, bool filter, int *nt, int rows, int col
     const size_t budget = SMEM_CAP / ctas_sm - 2048;           // (shared memory per SM: 228 KB, 1 KB reserved per CTA)
     const int max_nt = ctas_sm > 1 ? (MAX_NT / ctas_sm) & ~31 : MAX_NT;  // registers: 168 per thread for MAX_NT threads per SM
     // Candidates: chunk height EH (a tall chunk leaves room for fewer warp groups, i.e. more passes over the
-    // frames) x streaming or not.  STREAMING keeps the last 2*halo row-filtered rows of every shift plane in shared
+    // frames) x streaming or not.  STREAMING keeps the last 2*halo row-filtered rows of the shift planes in shared
     // memory for the next chunk of the segment, so no chunk row is wasted on the window halo; without it every
-    // segment is one chunk and EH - 2*halo of its EH rows are outputs.  Cost model fitted to measurements: rows
-    // computed per useful row, +15 % per extra pass over the frames, and the TMA box cost (a box takes the same
-    // TMA time whatever its depth FB; config 2, FB 1 / 2 / 5 / 9 -> 1.51 / 1.22 / 1.08 / 1.04 ms ~ 1 + 0.5 / FB).
+    // segment is one chunk and EH - 2*halo of its EH rows are outputs.  Two streaming orders: chunk-major (1: all
+    // passes of a chunk before the next chunk, carry = all S*S planes) and pass-major (2: all chunks of the segment
+    // before the next pass, carry = the G*SH*S planes of one pass -- what fits when S = 15).  Cost model fitted to
+    // measurements: rows computed per useful row; shift rows covered per shift row of the table (S = 15: 3 passes
+    // of 3 groups cover 18, 4 passes of 2 groups 16 -- config 4 cross table 21.06 vs 20.49 ms); +5 % per extra pass
+    // over the frames; the TMA box cost (a box takes the same TMA time whatever its depth FB; config 2, FB 1 / 2 /
+    // 5 / 9 -> 1.51 / 1.22 / 1.08 / 1.04 ms ~ 1 + 0.5 / FB); pass-major +5 % (config 2, where both orders fit:
+    // 0.957 vs 0.872 ms).
     double best = 1e30;
     TableParams bp = p;
     size_t best_smem = 0;
     const char *e_eh = getenv("UMPA_TAB_EH"), *e_st = getenv("UMPA_TAB_STREAM"), *e_fb = getenv("UMPA_TAB_FB"), *e_g = getenv("UMPA_TAB_G");
     for (int eh : {8, 16, 24, 32, 48})
-        for (int stream = (filter && halo > 0) ? 1 : 0; stream >= 0; stream--) {
+        for (int stream = (filter && halo > 0) ? 2 : 0; stream >= 0; stream--) {     // 2: streaming, pass-major (see below)
             if (e_eh ? atoi(e_eh) != eh : (eh == 8) != (ctas_sm > 1)) continue;     // 8-row chunks: two CTAs per SM only
             if (e_st && filter && halo > 0 && atoi(e_st) != stream) continue;
             if (!stream && eh - H2 < 2) continue;
@@ -658,7 +663,10 @@ size_t plan_tiles(TableParams &p, int S, bool filter, int *nt, int rows, int col
             q.npass = (S + q.G * SH - 1) / (q.G * SH);
             q.AH = eh + 2 * HS;
             const size_t cbuf = filter ? (size_t)q.G * S * eh * EXT_W * sizeof(float) : 0;
-            const size_t carry = stream ? (size_t)S * S * H2 * EXT_W * sizeof(float) : 0;
+            // carry: all S*S planes, or (pass-major order, stream == 2) only the G*SH*S planes of one pass
+            if (stream == 2 && (q.npass == 1 || S < 11)) continue;       // (the S <= 9 kernels are compiled without it)
+            const size_t carry = stream == 1 ? (size_t)S * S * H2 * EXT_W * sizeof(float)
+                               : stream == 2 ? (size_t)q.G * SH * S * H2 * EXT_W * sizeof(float) : 0;
             if (cbuf + carry >= budget) continue;
             // frames per TMA box = per ring stage: the fewest boxes of at most 9 frames, as long as 3 stages fit (2 at least)
             const int nboxes = (p.Na + 8) / 9;
@@ -674,10 +682,15 @@ size_t plan_tiles(TableParams &p, int S, bool filter, int *nt, int rows, int col
             }
             if (ns < 2) continue;
             q.nstage = std::min(ns, q.FB >= 4 ? 4 : MAX_STAGES);
-            const double cost = (stream ? 1. : (double)eh / (eh - H2)) * (1. + .15 * (q.npass - 1)) * (1. + .5 / q.FB);
+            // shift rows the passes cover per shift row of the table (a pass takes the time of G full warp groups)
+            const double cover = (double)q.npass * q.G * SH / S;
+            const double cost = (stream ? 1. : (double)eh / (eh - H2)) * cover * (1. + .05 * (q.npass - 1)) * (1. + .5 / q.FB)
+                              * (stream == 2 ? 1.05 : 1.);
             if (cost < best - 1e-9) {
                 best = cost; bp = q;
                 bp.seg_rows = stream ? 0 : eh - H2;              // streaming: chosen below
+                bp.pass_major = stream == 2;
+                bp.stream = stream;
                 best_smem = (size_t)q.nstage * q.stage_floats * sizeof(float) + cbuf + carry;
             }
         }
@@ -706,6 +719,25 @@ size_t plan_tiles(TableParams &p, int S, bool filter, int *nt, int rows, int col
 }
 
 }  // namespace
+
+// The geometry plan_tiles chooses for the cross table of a match (host arithmetic only; bench.py and the tests
+// read the plan from here instead of restating it).  out: EH, streaming order (0 halo tiles, 1 chunk-major,
+// 2 pass-major), G, npass, FB, nstage, TW, nseg, nstrips, block size.
+extern "C" UMPA_API int umpa_table_plan(int Na, int Nw, int max_shift, int rows, int cols, int sm_count, int out[10])
+{
+    if (Na < 1 || Nw < 0 || Nw > 6 || max_shift < 1 || rows < 1 || cols < 1 || sm_count < 1 || !out) {
+        umpa_set_error("umpa_table_plan: bad arguments");
+        return UMPA_ERR_ARG;
+    }
+    TableParams p{};
+    p.Na = Na; p.Nw = Nw;
+    int nt = 0;
+    const size_t smem = plan_tiles(p, 2 * max_shift - 1, true, &nt, rows, cols, sm_count * ctas_per_sm(), ctas_per_sm());
+    if (!smem) { umpa_set_error("table path: tile does not fit shared memory"); return UMPA_ERR_UNSUPPORTED; }
+    const int v[10] = {p.EH, p.stream, p.G, p.npass, p.FB, p.nstage, p.TW, p.nseg, p.nstrips, nt};
+    for (int i = 0; i < 10; i++) out[i] = v[i];
+    return UMPA_OK;
+}
 
 // FP64 device stacks -> centring constants + centred FP32 stacks (pitch multiple of 4 floats)
 int table_row_step(int H) { return std::max(1, H / 32); }
@@ -855,10 +887,6 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         // (2 S*S for DF) segments -- a few hundred KB -- instead of S*S planes of the image size
         px.plane_stride = pm.plane_stride = tpitch;
         px.row_stride = pm.row_stride = (size_t)(df ? 2 : 1) * S * S * tpitch;
-        if (getenv("UMPA_TAB_PLANES")) {            // experiment: shift-major planes [table][shift][row][col]
-            px.plane_stride = pm.plane_stride = rows_alloc * tpitch;
-            px.row_stride = pm.row_stride = tpitch;
-        }
         if ((rc = scratch_reserve(m, m->tabX, (size_t)(df ? 2 : 1) * S * S * rows_alloc * tpitch * sizeof(float)))) return rc;
 
     }
