@@ -360,8 +360,9 @@ def ours(args, cfg):
         nbytes = sum_over_ranks(0. if rank == 0 else float(sum(out[k].numel() * out[k].element_size() for k in keys if k in out)))
         gather = {"gather_ms": g_ms, "bytes_to_rank0": int(nbytes), "gbs_into_rank0": nbytes / (g_ms * 1e-3) / 1e9,
                   "value_incl_gather": total_px / ((ms + g_ms) * 1e-3),
-                  "how": "two torch.distributed.gather calls (packed float64 maps, packed int32 maps) over NCCL / NVLink "
-                         "after the timed steps; rank 0 ends with the full (N0, N1) maps in its HBM"}
+                  "how": "point to point (sharding.gather_bands: one torch.distributed.batch_isend_irecv group over NCCL / "
+                         "NVLink, every rank sends each map straight into its row slice of the full map) after the timed "
+                         "steps; rank 0 ends with the full (N0, N1) maps in its HBM"}
         if rank == 0:
             out = full
     err_ok = None
@@ -427,6 +428,7 @@ def ours(args, cfg):
         torch.cuda.synchronize()
         t_e = (time.perf_counter() - t0) / steps_e
         barrier()
+        t_own = t_e
         t_e = max_over_ranks(t_e)
         e2e = {"value": total_px / t_e, "unit": "output pixels/s", "ms_per_step": 1e3 * t_e, "first_call_ms": first_ms,
                "h2d_bytes_per_step": int(sum_over_ranks(float(sam_np.nbytes + ref_np.nbytes))),
@@ -437,6 +439,21 @@ def ours(args, cfg):
                                 "convert the lower host_rows_per_frame rows of every frame to centred FP32 in pinned "
                                 "staging while the DMA engine uploads the upper rows as FP64 (UMPA_HOST_THREADS=0 "
                                 "disables the host part)")}
+        if world > 1:
+            # what every rank's pipeline did (all ranks of a box share one host memory system): its own time per call,
+            # host threads, rows per frame converted on the host, and the PCIe rate of its own link
+            mine = {"rank": rank, "ms_per_step": 1e3 * t_own, "host_threads": stream_info.get("host_threads", 0),
+                    "host_rows_per_frame": stream_info.get("host_rows_per_frame", 0), "rows": hi - lo}
+            hrows = mine["host_rows_per_frame"]
+            up = 2 * cfg["Na"] * cfg["W"] * (4 * hrows + 8 * (hi - lo - hrows))
+            mine["pcie_up_gbs"] = up / t_own / 1e9
+            mine["host_conversion_gbs"] = 2 * cfg["Na"] * cfg["W"] * 8 * hrows / t_own / 1e9
+            t = torch.tensor([mine[k] for k in ("rank", "ms_per_step", "host_threads", "host_rows_per_frame", "rows",
+                                                "pcie_up_gbs", "host_conversion_gbs")], dtype=torch.float64, device=dev)
+            allr = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(allr, t)
+            e2e["per_rank"] = [dict(zip(("rank", "ms_per_step", "host_threads", "host_rows_per_frame", "rows", "pcie_up_gbs",
+                                         "host_conversion_gbs"), (round(v, 3) for v in a.tolist()))) for a in allr]
         # the same call on float32 host frames (detector data; umpa_set_frames_f32): half the upload, no host
         # conversion.  Reported beside the headline, not instead of it: the reference's API is float64.
         hs32 = torch.empty(hs.shape, dtype=torch.float32, pin_memory=True)
