@@ -63,9 +63,14 @@ enum {
  *  AUTO:  TABLE when the model has equal frames at position 0 and no masks; with masks or ragged frames /
  *         positions the MIXED path: TABLE on every pixel for which it is exact (no mask value != 1 within reach;
  *         every frame either contains the pixel's reach or misses it), LAZY on the rest; LAZY when TABLE does
- *         not apply at all.  Requesting TABLE on a model that is not eligible is an error. */
+ *         not apply at all.  Requesting TABLE on a model that is not eligible is an error.
+ *  MASKED (reported only): the MIXED path of a model whose masks are 0 / 1 and the same in every frame (a dead-pixel
+ *         map): the pixels with a dead pixel within reach are matched from the same tables, their sums corrected
+ *         by the few window positions the mask removes (Model.cpp:461-499, 775-847), instead of going to LAZY.
+ *         UMPA_MASK_TABLES=0 in the environment turns it off. */
 enum { UMPA_PATH_AUTO = 0, UMPA_PATH_TABLE = 1, UMPA_PATH_LAZY = 2,
-       UMPA_PATH_MIXED = 3 /* reported by umpa_last_match_info only (see AUTO above) */ };
+       UMPA_PATH_MIXED = 3 /* reported by umpa_last_match_info only (see AUTO above) */,
+       UMPA_PATH_MASKED = 4 /* reported only */ };
 
 /* Output maps of umpa_match*, all row-major (N0, N1); any pointer may be NULL to
  * skip that map.  Replaces the `values`, `err`, `debug_*` arrays that

@@ -90,3 +90,48 @@ def test_dfkernel_blur_table_identities(refshift):
                 cost = (t1 - t5 * T) / len(ref)
                 assert abs(T - t) <= 1e-11 * abs(t)
                 assert abs(cost - f) <= 1e-11 * max(abs(f), t1 / len(ref) * 1e-3)
+
+
+@pytest.mark.parametrize("kind", ["NoDF", "DF"])
+def test_binary_shared_mask_is_the_unmasked_sums_minus_the_dead_window_positions(kind):
+    """What table_path.cu's masked_walk_kernel computes for a 0 / 1 mask shared by all frames: the UNMASKED sums of a
+    cost evaluation (Model.cpp:415-458 / 709-773; the tables hold them) minus the window positions at which either
+    window sees a dead pixel, with t2 and wt scaled by the live window weight -- against the oracle's masked branch
+    (Model.cpp:461-499, 775-847).  The frame's reference mean m_k stays unmasked, as in the reference."""
+    rng = np.random.default_rng(5)
+    Na, H, W, Nw, ms = 6, 40, 44, 2, 4
+    S = 1. + .3 * rng.standard_normal((Na, H, W))
+    R = 1. + .3 * rng.standard_normal((Na, H, W))
+    M = (rng.random((H, W)) > .05).astype(np.float64)
+    win = port.make_window(Nw)
+    sw = win.sum()
+    om = port.OracleModel(kind, list(S), list(R), mask_list=[M] * Na, window_size=Nw, max_shift=ms)
+    for _ in range(200):
+        i = int(rng.integers(om.padding, H - om.padding)); j = int(rng.integers(om.padding, W - om.padding))
+        si, sj = (int(v) for v in rng.integers(-ms + 1, ms, 2))
+        qi, qj = i + si, j + sj
+        ws = S[:, i - Nw:i + Nw + 1, j - Nw:j + Nw + 1]
+        wr = R[:, qi - Nw:qi + Nw + 1, qj - Nw:qj + Nw + 1]
+        mk = (win * wr).sum((1, 2)) / sw
+        t1, t3, t5 = (win * ws * ws).sum(), (win * wr * wr).sum(), (win * wr * ws).sum()
+        t2, t4, t6 = (mk ** 2).sum(), (mk * (win * ws).sum((1, 2))).sum(), (mk * (win * wr).sum((1, 2))).sum()
+        dead = (M[qi - Nw:qi + Nw + 1, qj - Nw:qj + Nw + 1] == 0) | (M[i - Nw:i + Nw + 1, j - Nw:j + Nw + 1] == 0)
+        cw = 0.
+        for a, b in np.argwhere(dead):
+            w, s, r = win[a, b], ws[:, a, b], wr[:, a, b]
+            cw += w
+            t1 -= w * (s * s).sum(); t3 -= w * (r * r).sum(); t5 -= w * (r * s).sum()
+            t4 -= w * (mk * s).sum(); t6 -= w * (mk * r).sum()
+        t2 *= sw - cw
+        wt = Na * (sw - cw)
+        if kind == "NoDF":
+            t = t5 / t3
+            f, v = (t1 - t5 * t) / wt, 0.
+        else:
+            den = t2 * t3 - t6 * t6
+            Kc, beta = (t2 * t5 - t4 * t6) / den, (t3 * t4 - t5 * t6) / den
+            t, v = beta + Kc, Kc / (beta + Kc)
+            f = (t1 - beta * t4 - Kc * t5) / wt
+        (fo, to, vo), st = om.cost(i, j, si, sj)
+        assert st == 1
+        assert abs(f - fo) <= 1e-11 * abs(fo) and abs(t - to) <= 1e-11 * abs(to) and abs(v - vo) <= 1e-10 * max(1., abs(vo))

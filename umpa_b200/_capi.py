@@ -9,7 +9,7 @@ LIB_PATH = os.environ.get("UMPA_LIB") or os.path.join(HERE, "csrc", "libumpa_b20
 NODF, DF, DFKERNEL = 0, 1, 2
 OPT_SUBPX_FUNC, OPT_REFERENCE_SHIFT, OPT_PATH = 1, 2, 3
 PATH_AUTO, PATH_TABLE, PATH_LAZY = 0, 1, 2
-PATH_NAMES = {0: "none", 1: "table", 2: "lazy", 3: "mixed"}
+PATH_NAMES = {0: "none", 1: "table", 2: "lazy", 3: "mixed", 4: "masked_table"}
 
 EXPORTS = ("umpa_create", "umpa_destroy", "umpa_set_frames", "umpa_set_frames_f32", "umpa_set_window", "umpa_set_option",
            "umpa_get_option", "umpa_match", "umpa_match_host", "umpa_cost", "umpa_min", "umpa_coverage", "umpa_correct_bad_pixels",

@@ -343,7 +343,7 @@ void free_frames(umpa_model *m)
     m->h_sam.clear(); m->h_ref.clear(); m->h_mask.clear();
     m->h_sam_f.clear(); m->h_ref_f.clear(); m->h_mask_f.clear();
     m->host_f32 = false;
-    m->maskbad_valid = false;
+    m->maskbad_valid = false; m->mask_mode = 0;
     m->host_pending = false; m->fp64_missing = false;
     m->d_sam64 = m->d_ref64 = m->d_mask64 = nullptr;
     m->d_sam32 = m->d_ref32 = nullptr;
@@ -1109,7 +1109,7 @@ void umpa_destroy(umpa_model *m)
     DeviceGuard dg(m);
     cudaDeviceSynchronize();      // (the model's device) blocks go back to the cache: nothing of this model may still be running
     free_frames(m);
-    for (Scratch *s : {&m->filtA, &m->filtB, &m->auxS, &m->auxR, &m->tabX, &m->outbuf, &m->maskbad, &m->dirty})
+    for (Scratch *s : {&m->filtA, &m->filtB, &m->auxS, &m->auxR, &m->tabX, &m->outbuf, &m->maskbad, &m->dirty, &m->maskbits, &m->maskflags, &m->maskwin, &m->fmImgS, &m->fmImgR, &m->fmS, &m->fmR, &m->fmA})
         if (s->p) pool_free(s->p, s->bytes);
     pinned_small_give(m->h_small, m->h_small_own);       // (the streams are shared per device and stay)
     if (m->win_own) { cudaFree(m->d_win); cudaFree(m->d_g); }

@@ -109,6 +109,13 @@ struct umpa_model {
     Scratch filtA, filtB, auxS, auxR, tabX;
     Scratch maskbad, dirty;                      // masked models: row-dilated "mask != 1" image [H][W], per-ROI dirty map
     bool maskbad_valid = false;
+    // masks that are 0 / 1 and the same in every frame take the corrected table walk (table_path.cu: masked_walk_kernel)
+    Scratch maskbits, maskflags;                 // dead-pixel bit image [H][W/32 + 2]; classification flags (device)
+    Scratch maskwin;                             // Nw <= 3: the dead pixels of every pixel's window, one 64-bit word per pixel
+    int maskwin_Nw = -1;
+    Scratch fmImgS, fmImgR;                      // per-pixel frame sums of the centred stacks (float4 images)
+    Scratch fmS, fmR, fmA;                       // frame-minor copies [H][pitch][4 ceil(Na/4)] of the FP32 stacks / filtA
+    int mask_mode = 0;                           // 0 not classified yet | 1 general (lazy evaluation) | 2 binary and shared
     bool moments_valid = false;
 
     // One device block for all the small per-model arrays (shapes, window, pointer tables, constants):

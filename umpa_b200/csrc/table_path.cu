@@ -36,6 +36,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "shift_table.cuh"
 #include "walk.cuh"
@@ -853,7 +854,15 @@ static int stage_check(const char *name, cudaStream_t st)
     return UMPA_OK;
 }
 
+static int table_match_impl(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st, WalkParams *keep);
+
 int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st)
+{
+    return table_match_impl(m, roi, out, st, nullptr);
+}
+
+// keep: where to leave the walk's view of the tables (mixed_match: the corrected walk of binary masks reads them too)
+static int table_match_impl(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st, WalkParams *keep)
 {
     const int S = 2 * m->max_shift - 1, HS = m->max_shift - 1;
     const bool df = m->kind == UMPA_DF;
@@ -977,6 +986,7 @@ int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         w.sw = m->win_sum; w.quad = m->d_quad;
         w.inv_sw = 1. / w.sw; w.inv_Na = 1. / (double)Na;
         w.consts = m->d_consts;
+        if (keep) *keep = w;
         dim3 grid((roi.N1 + WALK_NT - 1) / WALK_NT, roi.N0);
         if (m->refshift) launch_walk<true>(m->kind, grid, w, roi, out, st);
         else launch_walk<false>(m->kind, grid, w, roi, out, st);
@@ -1045,7 +1055,301 @@ __global__ void dirty_rect_kernel(const int *dim, const int *pos, int Na, int pa
     dirty[(size_t)xi * roi.N1 + xj] = b;
 }
 
+// ---- binary masks shared by all frames: the table walk with corrected sums
+//
+// For mask values in {0, 1} the weight m_r m_s / (m_r + m_s + 1e-8) is gamma = 1/(2+1e-8) where both are 1, else 0;
+// gamma cancels in T, df and the cost (every sum of Model.cpp:461-499 / 775-847 carries it, wt too).  With ONE mask
+// M = 1 - D for all frames a masked sum is the unmasked one minus the window positions u where D(p+s+u) or D(p+u):
+//     t1 = t1u - sum_E w(u) sum_k S_k(p+u)^2          t3 = t3u - sum_E w(u) sum_k R_k(p+s+u)^2
+//     t5 = t5u - sum_E w(u) sum_k R_k(p+s+u) S_k(p+u)
+//     t4 = t4u - sum_E w(u) sum_k m_k S_k(p+u)        t6 = t6u - sum_E w(u) sum_k m_k R_k(p+s+u)
+//     t2 = (sum_k m_k^2) (sw - sum_E w(u))            wt = Na (sw - sum_E w(u))
+// (m_k, the frame's window mean of the reference, is NOT masked in the reference: Model.cpp:789-806).  The unmasked
+// sums are what the tables and aux images hold; E is read off a bit image of D, K row words per window; a dead
+// position costs the Na frame values of either stack at that position (+ m_k from the filtered reference stack, DF),
+// read from frame-minor copies of the stacks and summed in FP32 like the tables.  Exact algebra
+// (tests/test_table_algebra.py); the FP32 rounding is that of the unmasked path.
+
+struct MaskedParams {
+    const unsigned *bits;           // D: bit (x & 31) of bits[y * wb + (x >> 5)]
+    int wb;
+    const unsigned long long *dwin; // Nw <= 3: per raw pixel [H][W], bit (a K + b) = D(y - Nw + a, x - Nw + b); else nullptr
+    int W;
+    // frame-minor copies [H][pitch][Nap] of the centred stacks and (DF) of the filtered reference stack w (*) R'_k:
+    // the Na values of one pixel are Nap = 4 ceil(Na / 4) consecutive floats (zero padded) -- a dead window
+    // position costs 7 x 16 B loads per stack instead of 25 sectors in 25 frames
+    const float *tS, *tR, *tA;
+    int Nap;
+    // what a dead position needs of ONE pixel, [H][pitch]: imgS = (sum S'^2, sum d_k S', sum c_k S', -),
+    // imgR = (sum R'^2, sum c_k R', sum d_k R', sum c_k a'_k) with the FP32 centring constants d_k (sample), c_k (reference)
+    const float4 *imgS, *imgR;
+    const double *win;              // K x K window (FP64, the reference's)
+    int Nw;
+};
+
+// [Na][H][pitch] -> [H][pitch][Nap], rows [y0, y1), and the frame sums that need ONE pixel only, as an image of
+// float4 [H][pitch]: mode 0 -> (sum v^2, sum k1 v, sum k2 v) into x, y, z; mode 1 -> sum k1 v into w.
+// grid (ceil(pitch / 32), y1 - y0), 256 threads
+__global__ void frame_minor_kernel(const float *src, int Na, int Nap, int H, int pitch, int y0, float *dst,
+                                   const float *k1, const float *k2, float *img, int mode)
+{
+    extern __shared__ float tile[];             // [Nap][33]
+    const int y = y0 + blockIdx.y, x0 = blockIdx.x * 32, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    for (int k = wrp; k < Nap; k += 8)
+        tile[k * 33 + lane] = (k < Na && x0 + lane < pitch) ? src[((size_t)k * H + y) * pitch + x0 + lane] : 0.f;
+    __syncthreads();
+    const int n = min(32, pitch - x0) * Nap;
+    float *out = dst + ((size_t)y * pitch + x0) * Nap;
+    for (int i = threadIdx.x; i < n; i += 256) out[i] = tile[(i % Nap) * 33 + i / Nap];
+    if (wrp == 0 && x0 + lane < pitch) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int k = 0; k < Na; k++) {
+            const float v = tile[k * 33 + lane];
+            a0 = fmaf(v, v, a0); a1 = fmaf(__ldg(k1 + k), v, a1);
+            if (mode == 0) a2 = fmaf(__ldg(k2 + k), v, a2);
+        }
+        float *o = img + 4 * ((size_t)y * pitch + x0 + lane);
+        if (mode == 0) { o[0] = a0; o[1] = a1; o[2] = a2; }
+        else o[3] = a1;
+    }
+}
+
+// flags[0] |= 1 where a mask value is neither 0 nor 1 or differs from frame 0; flags[1] / flags[2]: largest |centred
+// value| of either stack over the dead / the live pixels (bits of a non-negative float: they order like the values;
+// a NaN counts as larger than everything).  One warp per 32 columns: its ballot is the row's bit word.
+__global__ void mask_classify_kernel(const double *mask, const float *sam32, const float *ref32, int Na, int H, int W,
+                                     int pitch, unsigned *bits, int wb, unsigned *flags)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const bool in = x < W;
+    bool dead = false, odd = false;
+    unsigned mx = 0;
+    if (in) {
+        const size_t px = (size_t)y * W + x, img64 = (size_t)H * W, img32 = (size_t)H * pitch, p32 = (size_t)y * pitch + x;
+        const double v0 = mask[px];
+        dead = v0 == 0.;
+        odd = !(v0 == 0. || v0 == 1.);
+        for (int k = 0; k < Na; k++) {
+            if (k) odd |= mask[k * img64 + px] != v0;
+            mx = max(mx, __float_as_uint(fabsf(sam32[k * img32 + p32])));
+            mx = max(mx, __float_as_uint(fabsf(ref32[k * img32 + p32])));
+        }
+    }
+    const unsigned word = __ballot_sync(0xffffffffu, dead);
+    if ((threadIdx.x & 31) == 0 && (x >> 5) < wb) bits[(size_t)y * wb + (x >> 5)] = word;
+    if (__any_sync(0xffffffffu, odd) && (threadIdx.x & 31) == 0) atomicOr(flags, 1u);
+    unsigned md = dead ? mx : 0u, ml = (in && !dead) ? mx : 0u;
+    for (int o = 16; o > 0; o >>= 1) {
+        md = max(md, __shfl_xor_sync(0xffffffffu, md, o));
+        ml = max(ml, __shfl_xor_sync(0xffffffffu, ml, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (md) atomicMax(flags + 1, md);
+        if (ml) atomicMax(flags + 2, ml);
+    }
+}
+
+// the dead pixels of every pixel's window as one word (K*K <= 49 bits): one gather per cost evaluation
+__global__ void window_bits_kernel(const unsigned *bits, int wb, int H, int W, int Nw, unsigned long long *dwin)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const int K = 2 * Nw + 1;
+    unsigned long long e = 0;
+    for (int a = 0; a < K; a++) {
+        const int yy = y - Nw + a;
+        if (yy < 0 || yy >= H) continue;
+        // columns x - Nw ... x + Nw of row yy (bits beyond the row are 0; left of column 0: shift in zeros)
+        const int x0 = x - Nw;
+        unsigned r;
+        if (x0 >= 0) {
+            const unsigned *p = bits + (size_t)yy * wb + (x0 >> 5);
+            r = __funnelshift_r(p[0], p[1], x0 & 31);
+        } else {
+            r = bits[(size_t)yy * wb] << (-x0);
+        }
+        e |= (unsigned long long)(r & ((1u << K) - 1u)) << (a * K);
+    }
+    dwin[(size_t)y * W + x] = e;
+}
+
+template <int KIND>
+struct MaskedEval {
+    const WalkParams &w;
+    const MaskedParams &mp;
+    double cd, cc, dd;              // sum c_k d_k, sum c_k^2, sum d_k^2
+    AuxS ps;                        // the sample's record at the pixel
+    const AuxR *pR;
+    const float *pX;
+    int y0, x0;                     // raw coordinates of the pixel
+    unsigned long long epw;         // the dead pixels of the pixel's own window (dwin)
+
+    __device__ __forceinline__ unsigned row_bits(int y, int x, int K) const
+    {
+        const unsigned *r = mp.bits + (size_t)y * mp.wb + (x >> 5);
+        return __funnelshift_r(__ldg(r), __ldg(r + 1), x & 31) & ((1u << K) - 1u);
+    }
+
+    __device__ __forceinline__ int operator()(int si, int sj, double &cst, FitArgs &args)
+    {
+        const int ms = w.max_shift, S = 2 * ms - 1;
+        const unsigned a = (unsigned)(si + ms - 1), b = (unsigned)(sj + ms - 1);
+        if (a >= (unsigned)S || b >= (unsigned)S) return TableEval<false, KIND>::out_of_bounds(si, sj, ms);
+        const unsigned sidx = a * (unsigned)S + b;
+        const int q = si * w.pitch + sj;
+        const float *px = pX + (size_t)sidx * w.tpitch;
+        const float x = __ldg(px);
+        const float m = KIND == UMPA_DF ? __ldg(px + w.m_off) : 0.f;
+        const double2 v0 = __ldg(reinterpret_cast<const double2 *>(pR + q));
+        const double2 v1 = __ldg(reinterpret_cast<const double2 *>(pR + q) + 1);
+        const double lin = v1.y + ps.V;
+        double t1 = ps.t1, t3 = v0.x, t5 = (double)x + lin;
+        double t4 = (double)m * w.inv_sw + lin, t6 = w.sw * v0.y;
+        // the window positions with a dead pixel in either window
+        const int Nw = mp.Nw, K = 2 * Nw + 1, n4 = mp.Nap >> 2;
+        const int qy = y0 + si, qx = x0 + sj;
+        const double U = v1.y - w.sw * cd;           // sum_k d_k a'_k(q)  (AuxR::linq = U + sw sum c_k d_k)
+        double cw = 0.;
+        const int rows = mp.dwin ? 1 : K;            // one word for the whole window, or a word per window row (Nw > 3)
+        const unsigned rk = 65536u / (unsigned)K + 1u;      // (bit * rk) >> 16 == bit / K for bit < K*K <= 49
+        const size_t qpix = (size_t)qy * w.pitch + qx;
+        for (int row = 0; row < rows; row++) {
+            unsigned long long e = mp.dwin ? (epw | __ldg(mp.dwin + (size_t)qy * mp.W + qx))
+                                           : (unsigned long long)(row_bits(y0 - Nw + row, x0 - Nw, K) | row_bits(qy - Nw + row, qx - Nw, K));
+            while (e) {
+                const int bit = __ffsll((long long)e) - 1;
+                e &= e - 1;
+                const int wa = mp.dwin ? (int)(((unsigned)bit * rk) >> 16) : row;
+                const int wb = mp.dwin ? bit - wa * K : bit;
+                const double wgt = __ldg(mp.win + wa * K + wb);
+                const size_t spix = (size_t)(y0 - Nw + wa) * w.pitch + (x0 - Nw + wb);
+                const size_t rpix = (size_t)(qy - Nw + wa) * w.pitch + (qx - Nw + wb);
+                const float4 iS = __ldg(mp.imgS + spix), iR = __ldg(mp.imgR + rpix);
+                const float4 *S4 = reinterpret_cast<const float4 *>(mp.tS + spix * mp.Nap);
+                const float4 *R4 = reinterpret_cast<const float4 *>(mp.tR + rpix * mp.Nap);
+                const float4 *A4 = reinterpret_cast<const float4 *>(mp.tA + qpix * mp.Nap);
+                // the sums over the frames that need both pixels, in FP32 on the centred values (the precision class
+                // of the tables themselves).  (Two positions per trip, sharing the A4 loads, measured slower: 12.5 vs
+                // 11.9 ms -- the second set of operands spills.)
+                float rs = 0.f, as = 0.f, ar = 0.f;
+#pragma unroll 4
+                for (int k = 0; k < n4; k++) {
+                    const float4 s = __ldg(S4 + k), r = __ldg(R4 + k);
+                    rs = fmaf(r.x, s.x, rs); rs = fmaf(r.y, s.y, rs); rs = fmaf(r.z, s.z, rs); rs = fmaf(r.w, s.w, rs);
+                    if (KIND == UMPA_DF) {
+                        const float4 av = __ldg(A4 + k);
+                        as = fmaf(av.x, s.x, as); as = fmaf(av.y, s.y, as); as = fmaf(av.z, s.z, as); as = fmaf(av.w, s.w, as);
+                        ar = fmaf(av.x, r.x, ar); ar = fmaf(av.y, r.y, ar); ar = fmaf(av.z, r.z, ar); ar = fmaf(av.w, r.w, ar);
+                    }
+                }
+                // uncentred: S = S' + d_k, R = R' + c_k, m_k = a'_k / sw + c_k
+                cw += wgt;
+                t1 -= wgt * ((double)iS.x + 2. * (double)iS.y + dd);
+                t3 -= wgt * ((double)iR.x + 2. * (double)iR.y + cc);
+                t5 -= wgt * ((double)rs + (double)iS.z + (double)iR.z + cd);
+                if (KIND == UMPA_DF) {
+                    const double ca = (double)__ldg(reinterpret_cast<const float *>(mp.imgR + qpix) + 3);
+                    t4 -= wgt * (((double)as + U) * w.inv_sw + (double)iS.z + cd);
+                    t6 -= wgt * (((double)ar + ca) * w.inv_sw + (double)iR.y + cc);
+                }
+            }
+        }
+        const double swm = w.sw - cw, wt = (double)w.Na * swm;
+        if (KIND == UMPA_DF) {
+            const double t2 = v0.y * swm;
+            const double rden = 1. / (t2 * t3 - t6 * t6);
+            const double Kc = (t2 * t5 - t4 * t6) * rden;
+            const double beta = (t3 * t4 - t5 * t6) * rden;
+            args.t = beta + Kc;
+            args.v = Kc;
+            cst = (t1 - beta * t4 - Kc * t5) / wt;
+            return UMPA_ST_OK;
+        }
+        args.t = t5 / t3;
+        cst = (t1 - t5 * args.t) / wt;
+        return UMPA_ST_OK;
+    }
+};
+
+#ifndef MASKED_MINB
+#define MASKED_MINB 5
+#endif
+
+template <int KIND>
+__global__ void __launch_bounds__(WALK_NT, MASKED_MINB) masked_walk_kernel(WalkParams w, MaskedParams mp, RoiView roi, umpa_outputs out)
+{
+    __shared__ double d_sm[25][WALK_NT];
+    const int xj = blockIdx.x * blockDim.x + threadIdx.x;
+    const int xi = blockIdx.y;
+    if (xj >= roi.N1 || xi >= roi.N0) return;
+    const size_t n = (size_t)xi * roi.N1 + xj;
+    if (roi.cover && roi.cover[n] < roi.cover_threshold) return;
+    if (roi.dirty && (roi.dirty[n] != 0) != (roi.dirty_want != 0)) return;
+    const int ty = roi.step0 * xi, tx = roi.step1 * xj;
+    const size_t pix = (size_t)(w.oy + ty) * w.pitch + (w.ox + tx);
+    MaskedEval<KIND> eval{w, mp};
+    eval.cd = __ldg(w.consts); eval.cc = __ldg(w.consts + 1); eval.dd = __ldg(w.consts + 2);
+    const double2 v = __ldg(reinterpret_cast<const double2 *>(w.auxS + pix));
+    eval.ps = AuxS{v.x, v.y};
+    eval.pR = w.auxR + pix;
+    eval.pX = w.tabX + (size_t)ty * w.row_stride + tx + w.dxX;
+    eval.y0 = w.oy + ty; eval.x0 = w.ox + tx;
+    eval.epw = mp.dwin ? __ldg(mp.dwin + (size_t)eval.y0 * mp.W + eval.x0) : 0ull;
+    FitArgs args{0., 0.};
+    SharedGrid d{&d_sm[0][threadIdx.x]};
+    double uv[2] = {roi.uv0[0], roi.uv0[1]}, f = 0.;
+    int ncalls;
+    WalkState ws;
+    const int st = walk_search(eval, args, f, uv, d, ncalls, ws);
+    store_debug(out, n, d, ws);
+    if (ws.finished) walk_refine(w.subpx, w.quad, d, ws, f, uv);
+    if (KIND == UMPA_DF && args.t != 0.) args.v = args.v / args.t;
+    store_pixel(out, n, KIND, st, f, args, uv, ncalls);
+}
+
 }  // namespace
+
+// Classifies the mask stack once per set of frames: 2 = values 0 / 1, the same in every frame, and no dead pixel
+// holds a value far outside the live range (the corrections subtract what the unmasked tables summed: a hot pixel
+// of 1e4 times the signal would cost the FP32 tables their precision) -> corrected table walk; else 1 (lazy).
+static int classify_mask(umpa_model *m, cudaStream_t st)
+{
+    if (m->mask_mode) return UMPA_OK;
+    m->mask_mode = 1;
+    const char *e = getenv("UMPA_MASK_TABLES");
+    if ((e && atoi(e) == 0) || !m->uniform || m->refshift || !m->d_sam32) return UMPA_OK;
+    const int H = m->H, W = m->W, wb = W / 32 + 2;
+    int rc;
+    if ((rc = scratch_reserve(m, m->maskbits, (size_t)H * wb * sizeof(unsigned)))) return rc;
+    if ((rc = scratch_reserve(m, m->maskflags, 4 * sizeof(unsigned)))) return rc;
+    UMPA_CUDA(cudaMemsetAsync(m->maskbits.p, 0, (size_t)H * wb * sizeof(unsigned), st));
+    UMPA_CUDA(cudaMemsetAsync(m->maskflags.p, 0, 4 * sizeof(unsigned), st));
+    mask_classify_kernel<<<dim3((W + 127) / 128, H), 128, 0, st>>>(m->d_mask64, m->d_sam32, m->d_ref32, m->Na, H, W, m->pitch,
+                                                                  (unsigned *)m->maskbits.p, wb, (unsigned *)m->maskflags.p);
+    UMPA_CUDA(cudaGetLastError());
+    unsigned fl[4];
+    UMPA_CUDA(cudaMemcpyAsync(fl, m->maskflags.p, sizeof(fl), cudaMemcpyDeviceToHost, st));
+    UMPA_CUDA(cudaStreamSynchronize(st));
+    float dead_max, live_max;
+    memcpy(&dead_max, fl + 1, 4); memcpy(&live_max, fl + 2, 4);
+    if (!(fl[0] & 1u) && dead_max <= 4.f * live_max) m->mask_mode = 2;      // (a NaN fails the comparison)
+    m->maskwin_Nw = -1;
+    return UMPA_OK;
+}
+
+// the per-pixel window words of the current window size (rebuilt when the window changes)
+static int ensure_window_bits(umpa_model *m, cudaStream_t st)
+{
+    if (m->Nw > 3 || m->maskwin_Nw == m->Nw) return UMPA_OK;
+    const int H = m->H, W = m->W, wb = W / 32 + 2;
+    int rc;
+    if ((rc = scratch_reserve(m, m->maskwin, (size_t)H * W * sizeof(unsigned long long)))) return rc;
+    window_bits_kernel<<<dim3((W + 127) / 128, H), 128, 0, st>>>((const unsigned *)m->maskbits.p, wb, H, W, m->Nw,
+                                                                 (unsigned long long *)m->maskwin.p);
+    UMPA_CUDA(cudaGetLastError());
+    m->maskwin_Nw = m->Nw;
+    return UMPA_OK;
+}
 
 int mixed_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st)
 {
@@ -1078,6 +1382,45 @@ int mixed_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
     RoiView v = roi;
     v.dirty = (const unsigned char *)m->dirty.p;
     v.dirty_want = 0;
+    if ((rc = classify_mask(m, st))) return rc;
+    if (m->mask_mode == 2 && m->Nw <= 6) {
+        WalkParams w{};
+        if ((rc = table_match_impl(m, v, out, st, &w))) return rc;
+        v.dirty_want = 1;
+        // frame-minor copies of what a dead window position reads, over the rows the walk can reach
+        const bool df = m->kind == UMPA_DF;
+        const int Na = m->Na, Nap = (Na + 3) & ~3, pitch = m->pitch, reach = m->max_shift - 1 + m->Nw;
+        const int y0 = std::max(0, v.off0 - reach), y1 = std::min(H, v.off0 + (v.N0 - 1) * v.step0 + reach + 1);
+        const size_t fm = (size_t)H * pitch * Nap * sizeof(float);
+        if ((rc = scratch_reserve(m, m->fmS, fm)) || (rc = scratch_reserve(m, m->fmR, fm))) return rc;
+        if (df && (rc = scratch_reserve(m, m->fmA, fm))) return rc;
+        const size_t im = (size_t)H * pitch * sizeof(float4);
+        if ((rc = scratch_reserve(m, m->fmImgS, im)) || (rc = scratch_reserve(m, m->fmImgR, im))) return rc;
+        const dim3 tg((pitch + 31) / 32, y1 - y0);
+        const size_t tsm = (size_t)Nap * 33 * sizeof(float);
+        frame_minor_kernel<<<tg, 256, tsm, st>>>(m->d_sam32, Na, Nap, H, pitch, y0, (float *)m->fmS.p, m->d_mean_s, m->d_mean_r,
+                                                 (float *)m->fmImgS.p, 0);
+        frame_minor_kernel<<<tg, 256, tsm, st>>>(m->d_ref32, Na, Nap, H, pitch, y0, (float *)m->fmR.p, m->d_mean_r, m->d_mean_s,
+                                                 (float *)m->fmImgR.p, 0);
+        if (df) frame_minor_kernel<<<tg, 256, tsm, st>>>((const float *)m->filtA.p, Na, Nap, H, pitch, y0, (float *)m->fmA.p,
+                                                         m->d_mean_r, nullptr, (float *)m->fmImgR.p, 1);
+        UMPA_CUDA(cudaGetLastError());
+        MaskedParams mp{};
+        mp.bits = (const unsigned *)m->maskbits.p; mp.wb = W / 32 + 2;
+        if ((rc = ensure_window_bits(m, st))) return rc;
+        mp.dwin = m->Nw <= 3 ? (const unsigned long long *)m->maskwin.p : nullptr;
+        mp.W = W;
+        mp.tS = (const float *)m->fmS.p; mp.tR = (const float *)m->fmR.p; mp.tA = df ? (const float *)m->fmA.p : mp.tR;
+        mp.Nap = Nap; mp.imgS = (const float4 *)m->fmImgS.p; mp.imgR = (const float4 *)m->fmImgR.p;
+        mp.win = m->d_win; mp.Nw = m->Nw;
+        dim3 grid((v.N1 + WALK_NT - 1) / WALK_NT, v.N0);
+        if (df) masked_walk_kernel<UMPA_DF><<<grid, WALK_NT, 0, st>>>(w, mp, v, out);
+        else masked_walk_kernel<UMPA_NODF><<<grid, WALK_NT, 0, st>>>(w, mp, v, out);
+        UMPA_CUDA(cudaGetLastError());
+        m->last_launches += 6 + (df ? 1 : 0);
+        m->last_path = UMPA_PATH_MASKED;
+        return UMPA_OK;
+    }
     if ((rc = table_match(m, v, out, st))) return rc;
     v.dirty_want = 1;
     if ((rc = lazy_match(m, v, out, st))) return rc;
