@@ -99,6 +99,43 @@ def test_what_does_not_qualify_stays_on_the_lazy_evaluation():
     compare_fp32(got, exp, tol=1e-4, label="hot dead pixel")
 
 
+def test_options_changed_after_the_first_match():
+    """The classification of the mask stack is cached per set of frames; window size and assign_coordinates may
+    change afterwards: a new window size rebuilds the window words, assign_coordinates='ref' goes back to the lazy
+    evaluation (the corrected walk is written for the moving reference window)."""
+    H, W, Na, ms = 84, 90, 5, 4
+    sam, ref = _stacks(Na, H, W, seed=6, ms=ms, dark_field=True)
+    masks = [_dead_map(H, W, .03, seed=4)] * Na
+    m = _product("DF", sam, ref, masks, 2, ms)
+    m.match(quiet=True)
+    assert m.last_match_info["path"] == "masked_table", m.last_match_info
+    m.Nw = 3
+    got = m.match(quiet=True)
+    assert m.last_match_info["path"] == "masked_table", m.last_match_info
+    exp = port.OracleModel("DF", sam, ref, mask_list=masks, window_size=3, max_shift=ms).match()
+    compare_fp32(got, exp, tol=1e-4, label="Nw 2 -> 3")
+    m.assign_coordinates = "ref"
+    got = m.match(quiet=True)
+    assert m.last_match_info["path"] == "mixed", m.last_match_info
+    om = port.OracleModel("DF", sam, ref, mask_list=masks, window_size=3, max_shift=ms)
+    om.set_options(reference_shift=1)
+    compare_fp32(got, om.match(), tol=1e-4, label="assign_coordinates = ref")
+
+
+def test_dfkernel_keeps_the_lazy_evaluation():
+    import umpa_b200
+    from umpa_b200 import synth
+    H, W, Na, ms = 80, 86, 5, 4
+    sam, ref = _stacks(Na, H, W, seed=7, ms=ms, dark_field=True)
+    masks = [_dead_map(H, W, .02, seed=3)] * Na
+    m = umpa_b200.UMPAModelDFKernel(sam, ref, mask_list=masks, window_size=2, max_shift=ms)
+    abc = synth.blur_abc(*m.sh)
+    got = m.match(abc=abc, quiet=True)
+    assert m.last_match_info["path"] == "mixed", m.last_match_info
+    exp = port.OracleModel("DFKernel", sam, ref, mask_list=masks, window_size=2, max_shift=ms).match(abc=abc)
+    compare_fp32(got, exp, tol=1e-4, label="DFKernel with a dead-pixel map")
+
+
 def test_env_switch_off(monkeypatch):
     H, W, Na, Nw, ms = 70, 72, 4, 2, 3
     sam, ref = _stacks(Na, H, W, seed=5, ms=ms, dark_field=False)

@@ -1317,7 +1317,9 @@ static int classify_mask(umpa_model *m, cudaStream_t st)
     if (m->mask_mode) return UMPA_OK;
     m->mask_mode = 1;
     const char *e = getenv("UMPA_MASK_TABLES");
-    if ((e && atoi(e) == 0) || !m->uniform || m->refshift || !m->d_sam32) return UMPA_OK;
+    if ((e && atoi(e) == 0) || !m->uniform || !m->d_sam32) return UMPA_OK;
+    if (m->kind != UMPA_DF && m->kind != UMPA_NODF) return UMPA_OK;      // (DFKernel: the blur couples the windows once more)
+    if ((size_t)m->H * m->pitch * ((m->Na + 3) & ~3) >= ((size_t)1 << 40)) return UMPA_OK;
     const int H = m->H, W = m->W, wb = W / 32 + 2;
     int rc;
     if ((rc = scratch_reserve(m, m->maskbits, (size_t)H * wb * sizeof(unsigned)))) return rc;
@@ -1383,7 +1385,7 @@ int mixed_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
     v.dirty = (const unsigned char *)m->dirty.p;
     v.dirty_want = 0;
     if ((rc = classify_mask(m, st))) return rc;
-    if (m->mask_mode == 2 && m->Nw <= 6) {
+    if (m->mask_mode == 2 && !m->refshift && m->Nw <= 6) {      // (the options may change between matches)
         WalkParams w{};
         if ((rc = table_match_impl(m, v, out, st, &w))) return rc;
         v.dirty_want = 1;
