@@ -147,11 +147,14 @@ def fp32_parity_stats(got, exp, tol=1e-4, eps=3e-6, noise_floor=3e-6, max_probe=
     def near_tie(i, j):
         # every comparison the walk makes is between two entries of its cache: the centre against a neighbour
         # (Optim.cpp:294, 325), the two neighbours of an axis against each other (337, 344-345), a 4x4 entry against
-        # the centre (364).  A "tie": two such entries agree to FP32 noise in the reference's own (final) cache.
+        # the centre (364) -- at the final centre AND at the centres it passed on the way, whose entries are still in
+        # the cache.  A "tie": two evaluated entries of the reference's own (final) cache agree to FP32 noise.  (With
+        # 25 entries spread over ~0.5 cost scales a random pixel has such a pair with probability ~0.2 %; all three
+        # pixels of config 2's 4.1 M whose walk differs from the FP64 evaluation have one, at 1e-7 ... 1.4e-6 of the
+        # cost scale, and end at the same minimum: tools/diag_walk_mismatch.py.)
         d5 = exp["debug_d"][i, j]
-        vals = [abs(d5[n] - d5[12]) for n in range(25) if n != 12 and d5[n] > -.5]
-        vals += [abs(d5[a] - d5[b]) for a, b in ((7, 17), (11, 13)) if d5[a] > -.5 and d5[b] > -.5]
-        return bool(vals) and min(vals) <= 1e-5 * cost_scale
+        known = np.sort(d5[d5 > -.5])
+        return known.size > 1 and float(np.diff(known).min()) <= 1e-5 * cost_scale
 
     nc = ok & (np.asarray(got["debug_Ncalls"]) != exp["debug_Ncalls"])
     st["ncalls_mismatch"] = int(nc.sum())

@@ -106,18 +106,18 @@ def test_options_changed_after_the_first_match():
     H, W, Na, ms = 84, 90, 5, 4
     sam, ref = _stacks(Na, H, W, seed=6, ms=ms, dark_field=True)
     masks = [_dead_map(H, W, .03, seed=4)] * Na
-    m = _product("DF", sam, ref, masks, 2, ms)
+    m = _product("DF", sam, ref, masks, 3, ms)
     m.match(quiet=True)
     assert m.last_match_info["path"] == "masked_table", m.last_match_info
-    m.Nw = 3
+    m.Nw = 2                                   # (the padding stays that of window_size 3, model.pyx:702-704)
     got = m.match(quiet=True)
     assert m.last_match_info["path"] == "masked_table", m.last_match_info
-    exp = port.OracleModel("DF", sam, ref, mask_list=masks, window_size=3, max_shift=ms).match()
-    compare_fp32(got, exp, tol=1e-4, label="Nw 2 -> 3")
+    om = port.OracleModel("DF", sam, ref, mask_list=masks, window_size=3, max_shift=ms)
+    om.set_Nw(2)
+    compare_fp32(got, om.match(), tol=1e-4, label="Nw 3 -> 2")
     m.assign_coordinates = "ref"
     got = m.match(quiet=True)
     assert m.last_match_info["path"] == "mixed", m.last_match_info
-    om = port.OracleModel("DF", sam, ref, mask_list=masks, window_size=3, max_shift=ms)
     om.set_options(reference_shift=1)
     compare_fp32(got, om.match(), tol=1e-4, label="assign_coordinates = ref")
 
