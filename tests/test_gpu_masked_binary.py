@@ -184,7 +184,8 @@ def test_full_size_block_against_the_reference():
     os.environ["UMPA_MASK_TABLES"] = "0"
     try:
         ml = umpa_b200.UMPAModelDF(list(sam), list(ref), mask_list=masks, window_size=Nw, max_shift=ms)
-        ml.match(ROI=roi, quiet=True, debug=False)
+        ml.match(quiet=True, debug=False)             # (full frame: a ROI would stick, model.pyx:406)
+        assert ml.last_match_info["path"] == "mixed", ml.last_match_info
         t0 = time.perf_counter()
         ml.match(quiet=True, debug=False)
         rec["match_ms_lazy_evaluation"] = 1e3 * (time.perf_counter() - t0)
