@@ -1212,7 +1212,14 @@ struct MaskedEval {
         double cw = 0.;
         const int rows = mp.dwin ? 1 : K;            // one word for the whole window, or a word per window row (Nw > 3)
         const unsigned rk = 65536u / (unsigned)K + 1u;      // (bit * rk) >> 16 == bit / K for bit < K*K <= 49
-        const size_t qpix = (size_t)qy * w.pitch + qx;
+        // 32-bit pixel / float4 indices (classify_mask keeps models whose frame-minor copies exceed 2^32 float4s off
+        // this path): the address arithmetic is a third of the kernel's instructions
+        const unsigned upitch = (unsigned)w.pitch, un4 = (unsigned)n4;
+        const unsigned qpix = (unsigned)qy * upitch + (unsigned)qx;
+        const unsigned sbase = (unsigned)(y0 - Nw) * upitch + (unsigned)(x0 - Nw);
+        const unsigned rbase = (unsigned)(qy - Nw) * upitch + (unsigned)(qx - Nw);
+        const float4 *tS4 = reinterpret_cast<const float4 *>(mp.tS), *tR4 = reinterpret_cast<const float4 *>(mp.tR);
+        const float4 *A4 = reinterpret_cast<const float4 *>(mp.tA) + qpix * un4;
         for (int row = 0; row < rows; row++) {
             unsigned long long e = mp.dwin ? (epw | __ldg(mp.dwin + (size_t)qy * mp.W + qx))
                                            : (unsigned long long)(row_bits(y0 - Nw + row, x0 - Nw, K) | row_bits(qy - Nw + row, qx - Nw, K));
@@ -1222,12 +1229,9 @@ struct MaskedEval {
                 const int wa = mp.dwin ? (int)(((unsigned)bit * rk) >> 16) : row;
                 const int wb = mp.dwin ? bit - wa * K : bit;
                 const double wgt = __ldg(mp.win + wa * K + wb);
-                const size_t spix = (size_t)(y0 - Nw + wa) * w.pitch + (x0 - Nw + wb);
-                const size_t rpix = (size_t)(qy - Nw + wa) * w.pitch + (qx - Nw + wb);
+                const unsigned off = (unsigned)wa * upitch + (unsigned)wb, spix = sbase + off, rpix = rbase + off;
                 const float4 iS = __ldg(mp.imgS + spix), iR = __ldg(mp.imgR + rpix);
-                const float4 *S4 = reinterpret_cast<const float4 *>(mp.tS + spix * mp.Nap);
-                const float4 *R4 = reinterpret_cast<const float4 *>(mp.tR + rpix * mp.Nap);
-                const float4 *A4 = reinterpret_cast<const float4 *>(mp.tA + qpix * mp.Nap);
+                const float4 *S4 = tS4 + spix * un4, *R4 = tR4 + rpix * un4;
                 // the sums over the frames that need both pixels, in FP32 on the centred values (the precision class
                 // of the tables themselves).  (Two positions per trip, sharing the A4 loads, measured slower: 12.5 vs
                 // 11.9 ms -- the second set of operands spills.)
@@ -1319,7 +1323,7 @@ static int classify_mask(umpa_model *m, cudaStream_t st)
     const char *e = getenv("UMPA_MASK_TABLES");
     if ((e && atoi(e) == 0) || !m->uniform || !m->d_sam32) return UMPA_OK;
     if (m->kind != UMPA_DF && m->kind != UMPA_NODF) return UMPA_OK;      // (DFKernel: the blur couples the windows once more)
-    if ((size_t)m->H * m->pitch * ((m->Na + 3) & ~3) >= ((size_t)1 << 40)) return UMPA_OK;
+    if ((size_t)m->H * m->pitch * ((m->Na + 3) / 4) >= ((size_t)1 << 32)) return UMPA_OK;     // (32-bit float4 indices in the walk)
     const int H = m->H, W = m->W, wb = W / 32 + 2;
     int rc;
     if ((rc = scratch_reserve(m, m->maskbits, (size_t)H * wb * sizeof(unsigned)))) return rc;
