@@ -361,8 +361,9 @@ def ours(args, cfg):
         gather = {"gather_ms": g_ms, "bytes_to_rank0": int(nbytes), "gbs_into_rank0": nbytes / (g_ms * 1e-3) / 1e9,
                   "value_incl_gather": total_px / ((ms + g_ms) * 1e-3),
                   "how": "point to point (sharding.gather_bands: one torch.distributed.batch_isend_irecv group over NCCL / "
-                         "NVLink, every rank sends each map straight into its row slice of the full map) after the timed "
-                         "steps; rank 0 ends with the full (N0, N1) maps in its HBM"}
+                         "NVLink; four ranks and more: every rank sends each map straight into its row slice of the full "
+                         "map; fewer: two packed messages per rank) after the timed steps; rank 0 ends with the full "
+                         "(N0, N1) maps in its HBM"}
         if rank == 0:
             out = full
     err_ok = None

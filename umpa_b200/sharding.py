@@ -86,10 +86,16 @@ def gather_bands(local, bands, rank, keys=("f", "T", "dx", "dy", "df", "err"), d
     """The only inter-GPU traffic of a sharded match (north_star: "a final gather of the output maps"): rank r
     contributes maps of shape (bands[r][1]-bands[r][0], N1); rank `dst` receives their row-wise concatenation.
 
-    Point to point, one batch: every rank sends each of its maps straight into the row slice it occupies in the full
-    map on `dst` (torch.distributed.batch_isend_irecv -- one NCCL group over NVLink for CUDA tensors, gloo for CPU
-    tensors), so nothing is packed, padded or copied twice and no Python objects are exchanged.  Every rank must pass
-    the same `keys`; a key the model does not produce (df for NoDF) is skipped on every rank alike.  n_cols: map width
+    Point to point, one batch (torch.distributed.batch_isend_irecv -- one NCCL group over NVLink for CUDA tensors, gloo
+    for CPU tensors), no Python objects exchanged: every rank sends each of its maps straight into the row slice it
+    occupies in the full map on `dst`, nothing packed or copied twice.  With fewer than four ranks on NCCL a rank's
+    float64 maps travel stacked as one message and its int32 maps as another (_gather_bands_packed): NCCL runs the
+    messages to ONE peer one after the other, and seven 16 MB messages are slower than one of 100 MB (config 2 on two
+    B200: 0.96 -> 0.59 ms on one box, 2.4 -> 1.05 ms on another), while with seven peers the per-map messages already
+    run side by side (eight B200: 0.82 ms per map against 0.98 ms packed; config 4: 1.19 against 1.59 ms).  An
+    all-gather of everything to everybody is not faster at either size (tools/diag_gather.py).  UMPA_GATHER=maps |
+    packed | allgather forces a variant.  Every rank must pass the same `keys`; a key the model does not produce (df
+    for NoDF) is skipped on every rank alike.  n_cols: map width
     (needed by a `dst` whose own band is empty; it then expects every key)."""
     import os
     import torch.distributed as dist
