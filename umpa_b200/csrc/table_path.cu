@@ -1076,8 +1076,8 @@ struct MaskedParams {
     const unsigned long long *dwin; // Nw <= 3: per raw pixel [H][W], bit (a K + b) = D(y - Nw + a, x - Nw + b); else nullptr
     int W;
     // frame-minor copies [H][pitch][Nap] of the centred stacks and (DF) of the filtered reference stack w (*) R'_k:
-    // the Na values of one pixel are Nap = 4 ceil(Na / 4) consecutive floats (zero padded) -- a dead window
-    // position costs 7 x 16 B loads per stack instead of 25 sectors in 25 frames
+    // the Na values of one pixel are Nap = 8 ceil(Na / 8) consecutive floats (zero padded; 25 frames: exactly one
+    // 128 B line) -- a dead window position costs four 256-bit loads per stack instead of 25 sectors in 25 frames
     const float *tS, *tR, *tA;
     int Nap;
     // what a dead position needs of ONE pixel, [H][pitch]: imgS = (sum S'^2, sum d_k S', sum c_k S', -),
@@ -1173,6 +1173,18 @@ __global__ void window_bits_kernel(const unsigned *bits, int wb, int H, int W, i
     dwin[(size_t)y * W + x] = e;
 }
 
+// eight consecutive floats, 32 B aligned, as ONE 256-bit load (sm_100: LDG.E.256): the walk below is bound by the
+// number of load wavefronts its scattered lanes generate, not by bytes
+struct Float8 { float v[8]; };
+__device__ __forceinline__ Float8 ldg256(const float *p)
+{
+    Float8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+
 template <int KIND>
 struct MaskedEval {
     const WalkParams &w;
@@ -1206,7 +1218,7 @@ struct MaskedEval {
         double t1 = ps.t1, t3 = v0.x, t5 = (double)x + lin;
         double t4 = (double)m * w.inv_sw + lin, t6 = w.sw * v0.y;
         // the window positions with a dead pixel in either window
-        const int Nw = mp.Nw, K = 2 * Nw + 1, n4 = mp.Nap >> 2;
+        const int Nw = mp.Nw, K = 2 * Nw + 1, n8 = mp.Nap >> 3;
         const int qy = y0 + si, qx = x0 + sj;
         const double U = v1.y - w.sw * cd;           // sum_k d_k a'_k(q)  (AuxR::linq = U + sw sum c_k d_k)
         double cw = 0.;
@@ -1214,15 +1226,27 @@ struct MaskedEval {
         const unsigned rk = 65536u / (unsigned)K + 1u;      // (bit * rk) >> 16 == bit / K for bit < K*K <= 49
         // 32-bit pixel / float4 indices (classify_mask keeps models whose frame-minor copies exceed 2^32 float4s off
         // this path): the address arithmetic is a third of the kernel's instructions
-        const unsigned upitch = (unsigned)w.pitch, un4 = (unsigned)n4;
+        const unsigned upitch = (unsigned)w.pitch, unap = (unsigned)mp.Nap;
         const unsigned qpix = (unsigned)qy * upitch + (unsigned)qx;
         const unsigned sbase = (unsigned)(y0 - Nw) * upitch + (unsigned)(x0 - Nw);
         const unsigned rbase = (unsigned)(qy - Nw) * upitch + (unsigned)(qx - Nw);
-        const float4 *tS4 = reinterpret_cast<const float4 *>(mp.tS), *tR4 = reinterpret_cast<const float4 *>(mp.tR);
-        const float4 *A4 = reinterpret_cast<const float4 *>(mp.tA) + qpix * un4;
+        const float *A8 = mp.tA + (size_t)(qpix * unap);
         for (int row = 0; row < rows; row++) {
             unsigned long long e = mp.dwin ? (epw | __ldg(mp.dwin + (size_t)qy * mp.W + qx))
                                            : (unsigned long long)(row_bits(y0 - Nw + row, x0 - Nw, K) | row_bits(qy - Nw + row, qx - Nw, K));
+#ifdef UMPA_MASK_PREFETCH
+            // every position's lines are requested before the first is consumed: the positions of a lane are
+            // otherwise one memory round trip after the other
+            for (unsigned long long t = e & (e - 1); t; ) {      // (all but the first, which is loaded right away)
+                const int bit = __ffsll((long long)t) - 1;
+                t &= t - 1;
+                const int wa = mp.dwin ? (int)(((unsigned)bit * rk) >> 16) : row;
+                const int wb = mp.dwin ? bit - wa * K : bit;
+                const unsigned off = (unsigned)wa * upitch + (unsigned)wb;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(mp.tS + (size_t)((sbase + off) * unap)));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(mp.tR + (size_t)((rbase + off) * unap)));
+            }
+#endif
             while (e) {
                 const int bit = __ffsll((long long)e) - 1;
                 e &= e - 1;
@@ -1231,19 +1255,20 @@ struct MaskedEval {
                 const double wgt = __ldg(mp.win + wa * K + wb);
                 const unsigned off = (unsigned)wa * upitch + (unsigned)wb, spix = sbase + off, rpix = rbase + off;
                 const float4 iS = __ldg(mp.imgS + spix), iR = __ldg(mp.imgR + rpix);
-                const float4 *S4 = tS4 + spix * un4, *R4 = tR4 + rpix * un4;
+                const float *S8 = mp.tS + (size_t)(spix * unap), *R8 = mp.tR + (size_t)(rpix * unap);
                 // the sums over the frames that need both pixels, in FP32 on the centred values (the precision class
                 // of the tables themselves).  (Two positions per trip, sharing the A4 loads, measured slower: 12.5 vs
                 // 11.9 ms -- the second set of operands spills.)
                 float rs = 0.f, as = 0.f, ar = 0.f;
-#pragma unroll 4
-                for (int k = 0; k < n4; k++) {
-                    const float4 s = __ldg(S4 + k), r = __ldg(R4 + k);
-                    rs = fmaf(r.x, s.x, rs); rs = fmaf(r.y, s.y, rs); rs = fmaf(r.z, s.z, rs); rs = fmaf(r.w, s.w, rs);
+#pragma unroll 2
+                for (int k = 0; k < n8; k++) {
+                    const Float8 s = ldg256(S8 + 8 * k), r = ldg256(R8 + 8 * k);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) rs = fmaf(r.v[u], s.v[u], rs);
                     if (KIND == UMPA_DF) {
-                        const float4 av = __ldg(A4 + k);
-                        as = fmaf(av.x, s.x, as); as = fmaf(av.y, s.y, as); as = fmaf(av.z, s.z, as); as = fmaf(av.w, s.w, as);
-                        ar = fmaf(av.x, r.x, ar); ar = fmaf(av.y, r.y, ar); ar = fmaf(av.z, r.z, ar); ar = fmaf(av.w, r.w, ar);
+                        const Float8 av = ldg256(A8 + 8 * k);
+#pragma unroll
+                        for (int u = 0; u < 8; u++) { as = fmaf(av.v[u], s.v[u], as); ar = fmaf(av.v[u], r.v[u], ar); }
                     }
                 }
                 // uncentred: S = S' + d_k, R = R' + c_k, m_k = a'_k / sw + c_k
@@ -1323,7 +1348,7 @@ static int classify_mask(umpa_model *m, cudaStream_t st)
     const char *e = getenv("UMPA_MASK_TABLES");
     if ((e && atoi(e) == 0) || !m->uniform || !m->d_sam32) return UMPA_OK;
     if (m->kind != UMPA_DF && m->kind != UMPA_NODF) return UMPA_OK;      // (DFKernel: the blur couples the windows once more)
-    if ((size_t)m->H * m->pitch * ((m->Na + 3) / 4) >= ((size_t)1 << 32)) return UMPA_OK;     // (32-bit float4 indices in the walk)
+    if ((size_t)m->H * m->pitch * ((m->Na + 7) & ~7) >= ((size_t)1 << 32)) return UMPA_OK;    // (32-bit element indices in the walk)
     const int H = m->H, W = m->W, wb = W / 32 + 2;
     int rc;
     if ((rc = scratch_reserve(m, m->maskbits, (size_t)H * wb * sizeof(unsigned)))) return rc;
@@ -1395,7 +1420,7 @@ int mixed_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         v.dirty_want = 1;
         // frame-minor copies of what a dead window position reads, over the rows the walk can reach
         const bool df = m->kind == UMPA_DF;
-        const int Na = m->Na, Nap = (Na + 3) & ~3, pitch = m->pitch, reach = m->max_shift - 1 + m->Nw;
+        const int Na = m->Na, Nap = (Na + 7) & ~7, pitch = m->pitch, reach = m->max_shift - 1 + m->Nw;
         const int y0 = std::max(0, v.off0 - reach), y1 = std::min(H, v.off0 + (v.N0 - 1) * v.step0 + reach + 1);
         const size_t fm = (size_t)H * pitch * Nap * sizeof(float);
         if ((rc = scratch_reserve(m, m->fmS, fm)) || (rc = scratch_reserve(m, m->fmR, fm))) return rc;
