@@ -1234,19 +1234,6 @@ struct MaskedEval {
         for (int row = 0; row < rows; row++) {
             unsigned long long e = mp.dwin ? (epw | __ldg(mp.dwin + (size_t)qy * mp.W + qx))
                                            : (unsigned long long)(row_bits(y0 - Nw + row, x0 - Nw, K) | row_bits(qy - Nw + row, qx - Nw, K));
-#ifdef UMPA_MASK_PREFETCH
-            // every position's lines are requested before the first is consumed: the positions of a lane are
-            // otherwise one memory round trip after the other
-            for (unsigned long long t = e & (e - 1); t; ) {      // (all but the first, which is loaded right away)
-                const int bit = __ffsll((long long)t) - 1;
-                t &= t - 1;
-                const int wa = mp.dwin ? (int)(((unsigned)bit * rk) >> 16) : row;
-                const int wb = mp.dwin ? bit - wa * K : bit;
-                const unsigned off = (unsigned)wa * upitch + (unsigned)wb;
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(mp.tS + (size_t)((sbase + off) * unap)));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(mp.tR + (size_t)((rbase + off) * unap)));
-            }
-#endif
             while (e) {
                 const int bit = __ffsll((long long)e) - 1;
                 e &= e - 1;
