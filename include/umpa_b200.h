@@ -66,7 +66,8 @@ enum {
  *         not apply at all.  Requesting TABLE on a model that is not eligible is an error.
  *  MASKED (reported only): the MIXED path of a model whose masks are 0 / 1 and the same in every frame (a dead-pixel
  *         map): the pixels with a dead pixel within reach are matched from the same tables, their sums corrected
- *         by the few window positions the mask removes (Model.cpp:461-499, 775-847), instead of going to LAZY.
+ *         by the few window positions the mask removes (Model.cpp:461-499, 775-847), instead of going to LAZY (NoDF /
+ *         DF, either assign_coordinates).
  *         UMPA_MASK_TABLES=0 in the environment turns it off. */
 enum { UMPA_PATH_AUTO = 0, UMPA_PATH_TABLE = 1, UMPA_PATH_LAZY = 2,
        UMPA_PATH_MIXED = 3 /* reported by umpa_last_match_info only (see AUTO above) */,

@@ -101,8 +101,8 @@ def test_what_does_not_qualify_stays_on_the_lazy_evaluation():
 
 def test_options_changed_after_the_first_match():
     """The classification of the mask stack is cached per set of frames; window size and assign_coordinates may
-    change afterwards: a new window size rebuilds the window words, assign_coordinates='ref' goes back to the lazy
-    evaluation (the corrected walk is written for the moving reference window)."""
+    change afterwards: a new window size rebuilds the window words, assign_coordinates='ref' takes the role-swapped
+    corrected walk."""
     H, W, Na, ms = 84, 90, 5, 4
     sam, ref = _stacks(Na, H, W, seed=6, ms=ms, dark_field=True)
     masks = [_dead_map(H, W, .03, seed=4)] * Na
@@ -115,11 +115,26 @@ def test_options_changed_after_the_first_match():
     om = port.OracleModel("DF", sam, ref, mask_list=masks, window_size=3, max_shift=ms)
     om.set_Nw(2)
     compare_fp32(got, om.match(), tol=1e-4, label="Nw 3 -> 2")
-    m.assign_coordinates = "ref"
+    m.assign_coordinates = "ref"               # (the sample window moves: Model.cpp:686-692)
     got = m.match(quiet=True)
-    assert m.last_match_info["path"] == "mixed", m.last_match_info
+    assert m.last_match_info["path"] == "masked_table", m.last_match_info
     om.set_options(reference_shift=1)
     compare_fp32(got, om.match(), tol=1e-4, label="assign_coordinates = ref")
+
+
+@pytest.mark.parametrize("kind,Nw", [("NoDF", 4), ("DF", 2)])
+def test_assign_coordinates_ref(kind, Nw):
+    """assign_coordinates='ref' with a dead-pixel map, also with the window-row words of Nw > 3."""
+    H, W, Na, ms = 88, 93, 5, 4
+    sam, ref = _stacks(Na, H, W, seed=8, ms=ms, dark_field=kind == "DF")
+    masks = [_dead_map(H, W, .02, seed=7)] * Na
+    m = _product(kind, sam, ref, masks, Nw, ms)
+    m.assign_coordinates = "ref"
+    got = m.match(quiet=True)
+    assert m.last_match_info["path"] == "masked_table", m.last_match_info
+    om = port.OracleModel(kind, sam, ref, mask_list=masks, window_size=Nw, max_shift=ms)
+    om.set_options(reference_shift=1)
+    compare_fp32(got, om.match(), tol=1e-4, label="%s ref Nw=%d" % (kind, Nw))
 
 
 def test_dfkernel_keeps_the_lazy_evaluation():

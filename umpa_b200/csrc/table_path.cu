@@ -1185,12 +1185,16 @@ __device__ __forceinline__ Float8 ldg256(const float *p)
     return r;
 }
 
-template <int KIND>
+// RS = reference_shift (assign_coordinates = 'ref', Model.cpp:686-692): the reference window stays at the pixel and
+// the SAMPLE window moves by -s; the tables hold the same sums with the roles of the stacks swapped (TableEval<RS>).
+template <bool RS, int KIND>
 struct MaskedEval {
     const WalkParams &w;
     const MaskedParams &mp;
     double cd, cc, dd;              // sum c_k d_k, sum c_k^2, sum d_k^2
-    AuxS ps;                        // the sample's record at the pixel
+    AuxS ps;                        // the sample's record at the pixel (!RS)
+    AuxR pr;                        // the reference's record at the pixel (RS)
+    const AuxS *pS;
     const AuxR *pR;
     const float *pX;
     int y0, x0;                     // raw coordinates of the pixel
@@ -1205,21 +1209,34 @@ struct MaskedEval {
     __device__ __forceinline__ int operator()(int si, int sj, double &cst, FitArgs &args)
     {
         const int ms = w.max_shift, S = 2 * ms - 1;
-        const unsigned a = (unsigned)(si + ms - 1), b = (unsigned)(sj + ms - 1);
-        if (a >= (unsigned)S || b >= (unsigned)S) return TableEval<false, KIND>::out_of_bounds(si, sj, ms);
+        const int ti = RS ? -si : si, tj = RS ? -sj : sj;
+        const unsigned a = (unsigned)(ti + ms - 1), b = (unsigned)(tj + ms - 1);
+        if (a >= (unsigned)S || b >= (unsigned)S) return TableEval<RS, KIND>::out_of_bounds(si, sj, ms);
         const unsigned sidx = a * (unsigned)S + b;
-        const int q = si * w.pitch + sj;
+        const int q = ti * w.pitch + tj;           // the moving window's pixel relative to this one
         const float *px = pX + (size_t)sidx * w.tpitch;
         const float x = __ldg(px);
         const float m = KIND == UMPA_DF ? __ldg(px + w.m_off) : 0.f;
-        const double2 v0 = __ldg(reinterpret_cast<const double2 *>(pR + q));
-        const double2 v1 = __ldg(reinterpret_cast<const double2 *>(pR + q) + 1);
-        const double lin = v1.y + ps.V;
-        double t1 = ps.t1, t3 = v0.x, t5 = (double)x + lin;
+        double2 v0, v1;                            // the reference's record {t3, t2}, {rden, linq}
+        double st1, sV;                            // the sample's record
+        if (RS) {
+            const double2 v = __ldg(reinterpret_cast<const double2 *>(pS + q));
+            st1 = v.x; sV = v.y;
+            v0 = make_double2(pr.t3, pr.t2); v1 = make_double2(pr.rden, pr.linq);
+        } else {
+            v0 = __ldg(reinterpret_cast<const double2 *>(pR + q));
+            v1 = __ldg(reinterpret_cast<const double2 *>(pR + q) + 1);
+            st1 = ps.t1; sV = ps.V;
+        }
+        const double lin = v1.y + sV;
+        double t1 = st1, t3 = v0.x, t5 = (double)x + lin;
         double t4 = (double)m * w.inv_sw + lin, t6 = w.sw * v0.y;
-        // the window positions with a dead pixel in either window
+        // the window positions with a dead pixel in either window: the reference window at (qy, qx), the sample
+        // window at (py, px_); (my, mx) is the one that moves
         const int Nw = mp.Nw, K = 2 * Nw + 1, n8 = mp.Nap >> 3;
-        const int qy = y0 + si, qx = x0 + sj;
+        const int qy = RS ? y0 : y0 + si, qx = RS ? x0 : x0 + sj;
+        const int py = RS ? y0 - si : y0, px_ = RS ? x0 - sj : x0;
+        const int my = RS ? py : qy, mx = RS ? px_ : qx;
         const double U = v1.y - w.sw * cd;           // sum_k d_k a'_k(q)  (AuxR::linq = U + sw sum c_k d_k)
         double cw = 0.;
         const int rows = mp.dwin ? 1 : K;            // one word for the whole window, or a word per window row (Nw > 3)
@@ -1228,12 +1245,12 @@ struct MaskedEval {
         // this path): the address arithmetic is a third of the kernel's instructions
         const unsigned upitch = (unsigned)w.pitch, unap = (unsigned)mp.Nap;
         const unsigned qpix = (unsigned)qy * upitch + (unsigned)qx;
-        const unsigned sbase = (unsigned)(y0 - Nw) * upitch + (unsigned)(x0 - Nw);
+        const unsigned sbase = (unsigned)(py - Nw) * upitch + (unsigned)(px_ - Nw);
         const unsigned rbase = (unsigned)(qy - Nw) * upitch + (unsigned)(qx - Nw);
         const float *A8 = mp.tA + (size_t)(qpix * unap);
         for (int row = 0; row < rows; row++) {
-            unsigned long long e = mp.dwin ? (epw | __ldg(mp.dwin + (size_t)qy * mp.W + qx))
-                                           : (unsigned long long)(row_bits(y0 - Nw + row, x0 - Nw, K) | row_bits(qy - Nw + row, qx - Nw, K));
+            unsigned long long e = mp.dwin ? (epw | __ldg(mp.dwin + (size_t)my * mp.W + mx))
+                                           : (unsigned long long)(row_bits(y0 - Nw + row, x0 - Nw, K) | row_bits(my - Nw + row, mx - Nw, K));
             while (e) {
                 const int bit = __ffsll((long long)e) - 1;
                 e &= e - 1;
@@ -1291,7 +1308,7 @@ struct MaskedEval {
 #define MASKED_MINB 5
 #endif
 
-template <int KIND>
+template <bool RS, int KIND>
 __global__ void __launch_bounds__(WALK_NT, MASKED_MINB) masked_walk_kernel(WalkParams w, MaskedParams mp, RoiView roi, umpa_outputs out)
 {
     __shared__ double d_sm[25][WALK_NT];
@@ -1303,11 +1320,19 @@ __global__ void __launch_bounds__(WALK_NT, MASKED_MINB) masked_walk_kernel(WalkP
     if (roi.dirty && (roi.dirty[n] != 0) != (roi.dirty_want != 0)) return;
     const int ty = roi.step0 * xi, tx = roi.step1 * xj;
     const size_t pix = (size_t)(w.oy + ty) * w.pitch + (w.ox + tx);
-    MaskedEval<KIND> eval{w, mp};
+    MaskedEval<RS, KIND> eval{w, mp};
     eval.cd = __ldg(w.consts); eval.cc = __ldg(w.consts + 1); eval.dd = __ldg(w.consts + 2);
-    const double2 v = __ldg(reinterpret_cast<const double2 *>(w.auxS + pix));
-    eval.ps = AuxS{v.x, v.y};
-    eval.pR = w.auxR + pix;
+    eval.pS = w.auxS + pix; eval.pR = w.auxR + pix;
+    if (RS) {
+        const double2 v0 = __ldg(reinterpret_cast<const double2 *>(eval.pR));
+        const double2 v1 = __ldg(reinterpret_cast<const double2 *>(eval.pR) + 1);
+        eval.pr = AuxR{v0.x, v0.y, v1.x, v1.y};
+        eval.ps = AuxS{0., 0.};
+    } else {
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(eval.pS));
+        eval.ps = AuxS{v.x, v.y};
+        eval.pr = AuxR{0., 0., 0., 0.};
+    }
     eval.pX = w.tabX + (size_t)ty * w.row_stride + tx + w.dxX;
     eval.y0 = w.oy + ty; eval.x0 = w.ox + tx;
     eval.epw = mp.dwin ? __ldg(mp.dwin + (size_t)eval.y0 * mp.W + eval.x0) : 0ull;
@@ -1401,7 +1426,7 @@ int mixed_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
     v.dirty = (const unsigned char *)m->dirty.p;
     v.dirty_want = 0;
     if ((rc = classify_mask(m, st))) return rc;
-    if (m->mask_mode == 2 && !m->refshift && m->Nw <= 6) {      // (the options may change between matches)
+    if (m->mask_mode == 2 && m->Nw <= 6) {      // (the window may change between matches)
         WalkParams w{};
         if ((rc = table_match_impl(m, v, out, st, &w))) return rc;
         v.dirty_want = 1;
@@ -1432,8 +1457,13 @@ int mixed_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cuda
         mp.Nap = Nap; mp.imgS = (const float4 *)m->fmImgS.p; mp.imgR = (const float4 *)m->fmImgR.p;
         mp.win = m->d_win; mp.Nw = m->Nw;
         dim3 grid((v.N1 + WALK_NT - 1) / WALK_NT, v.N0);
-        if (df) masked_walk_kernel<UMPA_DF><<<grid, WALK_NT, 0, st>>>(w, mp, v, out);
-        else masked_walk_kernel<UMPA_NODF><<<grid, WALK_NT, 0, st>>>(w, mp, v, out);
+        if (m->refshift) {
+            if (df) masked_walk_kernel<true, UMPA_DF><<<grid, WALK_NT, 0, st>>>(w, mp, v, out);
+            else masked_walk_kernel<true, UMPA_NODF><<<grid, WALK_NT, 0, st>>>(w, mp, v, out);
+        } else {
+            if (df) masked_walk_kernel<false, UMPA_DF><<<grid, WALK_NT, 0, st>>>(w, mp, v, out);
+            else masked_walk_kernel<false, UMPA_NODF><<<grid, WALK_NT, 0, st>>>(w, mp, v, out);
+        }
         UMPA_CUDA(cudaGetLastError());
         m->last_launches += 6 + (df ? 1 : 0);
         m->last_path = UMPA_PATH_MASKED;
