@@ -1065,7 +1065,8 @@ __global__ void dirty_rect_kernel(const int *dim, const int *pos, int Na, int pa
 //     t4 = t4u - sum_E w(u) sum_k m_k S_k(p+u)        t6 = t6u - sum_E w(u) sum_k m_k R_k(p+s+u)
 //     t2 = (sum_k m_k^2) (sw - sum_E w(u))            wt = Na (sw - sum_E w(u))
 // (m_k, the frame's window mean of the reference, is NOT masked in the reference: Model.cpp:789-806).  The unmasked
-// sums are what the tables and aux images hold; E is read off a bit image of D, K row words per window; a dead
+// sums are what the tables and aux images hold; E is read off the window's dead-pixel bits (one 64-bit word per
+// pixel for Nw <= 3, else K row words of the bit image of D); a dead
 // position costs the Na frame values of either stack at that position (+ m_k from the filtered reference stack, DF),
 // read from frame-minor copies of the stacks and summed in FP32 like the tables.  Exact algebra
 // (tests/test_table_algebra.py); the FP32 rounding is that of the unmasked path.
@@ -1241,7 +1242,7 @@ struct MaskedEval {
         double cw = 0.;
         const int rows = mp.dwin ? 1 : K;            // one word for the whole window, or a word per window row (Nw > 3)
         const unsigned rk = 65536u / (unsigned)K + 1u;      // (bit * rk) >> 16 == bit / K for bit < K*K <= 49
-        // 32-bit pixel / float4 indices (classify_mask keeps models whose frame-minor copies exceed 2^32 float4s off
+        // 32-bit pixel / element indices (classify_mask keeps models whose frame-minor copies exceed 2^32 floats off
         // this path): the address arithmetic is a third of the kernel's instructions
         const unsigned upitch = (unsigned)w.pitch, unap = (unsigned)mp.Nap;
         const unsigned qpix = (unsigned)qy * upitch + (unsigned)qx;
@@ -1261,7 +1262,7 @@ struct MaskedEval {
                 const float4 iS = __ldg(mp.imgS + spix), iR = __ldg(mp.imgR + rpix);
                 const float *S8 = mp.tS + (size_t)(spix * unap), *R8 = mp.tR + (size_t)(rpix * unap);
                 // the sums over the frames that need both pixels, in FP32 on the centred values (the precision class
-                // of the tables themselves).  (Two positions per trip, sharing the A4 loads, measured slower: 12.5 vs
+                // of the tables themselves).  (Two positions per trip, sharing the m_k loads, measured slower: 12.5 vs
                 // 11.9 ms -- the second set of operands spills.)
                 float rs = 0.f, as = 0.f, ar = 0.f;
 #pragma unroll 2
