@@ -856,42 +856,8 @@ static int stage_check(const char *name, cudaStream_t st)
 
 static int table_match_impl(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st, WalkParams *keep);
 
-static umpa_outputs band_outputs(const umpa_outputs &o, size_t px)
-{
-    umpa_outputs r = o;
-    if (r.f) r.f += px;
-    if (r.T) r.T += px;
-    if (r.dx) r.dx += px;
-    if (r.dy) r.dy += px;
-    if (r.df) r.df += px;
-    if (r.err) r.err += px;
-    if (r.ncalls) r.ncalls += px;
-    if (r.debug_d) r.debug_d += 25 * px;
-    if (r.debug_a) r.debug_a += 16 * px;
-    return r;
-}
-
 int table_match(umpa_model *m, const RoiView &roi, const umpa_outputs &out, cudaStream_t st)
 {
-    // experiment (UMPA_TAB_BANDROWS=n): the match in bands of n output rows, so that a band's tables are still in L2
-    // when its walk reads them
-    static const int band = getenv("UMPA_TAB_BANDROWS") ? atoi(getenv("UMPA_TAB_BANDROWS")) : 0;
-    if (band > 0 && roi.N0 > band && m->kind != UMPA_DFKERNEL) {
-        int launches = 0, rc;
-        for (int r0 = 0; r0 < roi.N0; r0 += band) {
-            RoiView vb = roi;
-            vb.off0 = roi.off0 + roi.step0 * r0; vb.N0 = std::min(band, roi.N0 - r0);
-            const size_t px0 = (size_t)r0 * roi.N1;
-            if (roi.abc) vb.abc = roi.abc + 3 * px0;
-            if (roi.cover) vb.cover = roi.cover + px0;
-            if (roi.dirty) vb.dirty = roi.dirty + px0;
-            m->last_launches = 0;
-            if ((rc = table_match_impl(m, vb, band_outputs(out, px0), st, nullptr))) return rc;
-            launches += m->last_launches;
-        }
-        m->last_launches = launches;
-        return UMPA_OK;
-    }
     return table_match_impl(m, roi, out, st, nullptr);
 }
 
