@@ -258,6 +258,8 @@ def kernel_roofline(cfg_name, world, stage_ms, fma_peak, hbm_gbs, sm_mhz, sms):
             continue
         name, k = pick[st]
         scale = k["ncu_duration_ns"] * 1e-6 / ms                 # same work, profiled duration vs live duration
+        if k.get("captured_before"):                             # the kernel issues less work than when it was profiled:
+            scale = 1.                                           # its pipe utilisations are reported as profiled
         dram = k["dram_read_bytes"] + k["dram_write_bytes"]
         fr = {"fma_pipe": k["fma_pipe_pct"] / 100. * scale,
               "hbm": dram / (ms * 1e-3) / 1e9 / hbm_gbs,
@@ -267,6 +269,8 @@ def kernel_roofline(cfg_name, world, stage_ms, fma_peak, hbm_gbs, sm_mhz, sms):
         out[st] = {"kernel": name, "ms": ms, "ncu_ms": k["ncu_duration_ns"] * 1e-6, "dram_bytes": dram,
                    "warp_inst": k["warp_inst"], "smem_wavefronts": k["smem_wavefronts"],
                    "fractions": fr, "bound": bound, "frac": fr[bound]}
+        if k.get("captured_before"):
+            out[st]["note"] = k["captured_before"]
     return out, "profiles/%s (%s; ncu --set full of `%s`)" % (os.path.basename(NCU_KERNELS), ncu.get("source"), ncu.get("command"))
 
 

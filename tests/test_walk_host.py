@@ -59,7 +59,12 @@ extern "C" int walk_host(cost_fn fn, const void *m, int i, int j, const double *
     double f = 0., uv[2] = {uv0[0], uv0[1]};
     double cells[25];                                     // the ring storage; d receives the cache in the reference's order
     WalkState ws;
-    const int st = walk_search(ev, args, f, uv, cells, *ncalls, ws);
+#ifndef WALK_PEEL
+#define WALK_PEEL true
+#endif
+    // WALK_PEEL: the centre evaluated in front of the loop (what the table kernels compile) or through the loop's own
+    // evaluation site (the lazy kernels) -- both have to replay the oracle
+    const int st = walk_search<WALK_PEEL>(ev, args, f, uv, cells, *ncalls, ws);
     for (int t = 0; t < 25; t++) d[t] = walk_cache_get(cells, ws, t);
     for (int t = 0; t < 16; t++) a[t] = ws.finished ? walk_block_get(cells, ws, t >> 2, t & 3) : 0.;
     if (ws.finished) walk_refine(subpx, quad, cells, ws, f, uv);
@@ -96,9 +101,11 @@ def _build(tmp, tag, extra=()):
     return L
 
 
-@pytest.fixture(scope="module")
-def walk_lib(tmp_path_factory):
-    return _build(str(tmp_path_factory.mktemp("walk")), "guard")
+@pytest.fixture(scope="module", params=["peeled", "single_site"])
+def walk_lib(request, tmp_path_factory):
+    """walk.cuh as the table kernels compile it (centre evaluation peeled off the loop) and as the lazy kernels do"""
+    extra = ("-DWALK_PEEL=true",) if request.param == "peeled" else ("-DWALK_PEEL=false",)
+    return _build(str(tmp_path_factory.mktemp("walk_" + request.param)), "guard", extra=extra)
 
 
 def _quad():

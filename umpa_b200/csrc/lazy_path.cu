@@ -263,7 +263,7 @@ lazy_match_kernel(LazyView m, RoiView roi, umpa_outputs out, double *kern_ws, in
     double d[25], uv[2] = {roi.uv0[0], roi.uv0[1]}, f = 0.;
     int ncalls;
     WalkState ws;
-    const int st = walk_search(eval, args, f, uv, d, ncalls, ws);
+    const int st = walk_search<false>(eval, args, f, uv, d, ncalls, ws);
     store_debug(out, n, d, ws);                    // (before the fit: it reuses the cache's cells)
     if (ws.finished) walk_refine(m.subpx, m.quad, d, ws, f, uv);
     store_pixel(out, n, m.kind, st, f, args, uv, ncalls);
@@ -289,7 +289,7 @@ __global__ void lazy_min_kernel(LazyView m, int i, int j, double *io, double *ke
     double d[25], uv[2] = {io[7], io[8]}, f = 0.;
     int ncalls;
     WalkState ws;
-    const int st = walk_search(eval, args, f, uv, d, ncalls, ws);
+    const int st = walk_search<false>(eval, args, f, uv, d, ncalls, ws);
     for (int t = 0; t < 25; t++) io[9 + t] = walk_cache_get(d, ws, t);
     for (int t = 0; t < 16; t++) io[34 + t] = ws.finished ? walk_block_get(d, ws, t >> 2, t & 3) : 0.;
     if (ws.finished) walk_refine(m.subpx, m.quad, d, ws, f, uv);

@@ -146,17 +146,21 @@ __device__ inline double subpixel_quadratic(const double *__restrict__ c_quad, G
 //
 // The reference calls the cost function from four places (centre, minus neighbour, plus
 // neighbour, 4x4 fill).  On a GPU that would serialise the lanes of a warp that happen to be
-// at different call sites, so the same control flow is written as a state machine with ONE
+// at different call sites, so the same control flow is written as a state machine whose loop has ONE
 // evaluation site: each lane advances its state until it knows which shift it needs next,
-// all lanes evaluate together, then each lane files the result.  The sequence of
+// all lanes evaluate together, then each lane files the result (the centre, which every lane evaluates
+// first and exactly once, may sit in front of the loop: PEEL).  The sequence of
 // evaluations per pixel -- and therefore Ncalls, d, the 4x4 block and every tie decision --
 // is exactly the reference's.
 // Eval: int operator()(int si, int sj, double &cost, FitArgs &args) -> error_status bits.
 // Returns the error_status bits; on UMPA_ST_OK with ws.finished the caller runs walk_refine().
-template <class Eval, class Grid>
+// PEEL: the centre evaluation gets its own copy of the cost function in front of the loop (the table evaluators: a few
+// dozen instructions, and the loop's filing code no longer knows the centre); PEEL = false sends it through the loop's
+// evaluation site (the lazy evaluator, whose code is long and whose bookkeeping does not matter).
+template <bool PEEL = true, class Eval, class Grid>
 __device__ inline int walk_search(Eval &eval, FitArgs &args, double &out, double *uv, Grid d, int &ncalls, WalkState &ws)
 {
-    enum { R_CENTRE = 1, R_LO = 2, R_HI = 4, R_FILL = 8 };    // what the pending evaluation is for
+    enum { R_LO = 2, R_HI = 4, R_FILL = 8 };       // what the pending evaluation is for
     const double tol = 1e-8;                       // absolute, Optim.cpp:243
     constexpr unsigned COL0 = 0x108421u, COL4 = 0x1084210u, ALL = 0x1ffffffu;
     int settled0 = 0, settled1 = 0, axis = 0, st = UMPA_ST_OK;
@@ -166,93 +170,115 @@ __device__ inline int walk_search(Eval &eval, FitArgs &args, double &out, double
     FitArgs keep = args;
     ncalls = 0;
     int c0 = (int)round(uv[0]), c1 = (int)round(uv[1]);
-    int req = R_CENTRE, sr = 2, sc = 2;            // the pending evaluation: logical cell (sr, sc) = shift (c0 + sr - 2, c1 + sc - 2)
+    int req = R_LO, sr = 2, sc = 2;                // the pending evaluation: logical cell (sr, sc) = shift (c0 + sr - 2, c1 + sc - 2)
     double dc = 0.;                                // d[12], the cost at the current centre
+    bool done = false;
+    bool centre = !PEEL;                           // (!PEEL) the loop's first evaluation is the centre's
 
-    while (true) {
-        // ---- the one evaluation site ----
+    // The centre (Optim.cpp:262) is evaluated exactly once -- a restart takes its new centre's cost from the fill
+    // evaluation that triggered it -- and by all lanes at the same time, so it sits before the loop: the loop's
+    // filing code then only knows neighbours and fill entries.
+    if (PEEL) {
+        double v;
+        const int se = eval(c0, c1, v, args);
+        ncalls = 1;
+        if (se != UMPA_ST_OK) { st = se; done = true; }      // bound error: return at once (Optim.cpp:264)
+        else {
+            keep = args;
+            dc = v;
+            d[walk_cell(b0, b1, 2, 2)] = v;
+            known = 1u << 12;
+        }
+    }
+
+    while (!done) {
+        if (PEEL || !centre) {
+            // ---- advance this lane until it needs the next cost value (or is done) ----
+            while (true) {
+                if (fill) {                            // next missing entry of the 4x4 block (row-major)
+                    const unsigned pending = (0x7bdefu << (5 * ip + jp)) & ~known;    // 4 rows of 4 bits, 5 apart
+                    if (!pending) { finished = true; done = true; break; }
+                    const int slot = __ffs(pending) - 1;
+                    sr = (slot * 13) >> 6;             // slot / 5 for slot < 64
+                    sc = slot - 5 * sr;
+                    req = R_FILL;
+                    break;
+                }
+                // head of the reference's loop (Optim.cpp:267); a restart jumps past the test (goto start)
+                if (!skip_limit && ncalls >= UMPA_MAX_CALLS) { st = 0; done = true; break; }   // Optim.cpp:267,477
+                // Not in the reference: with a NaN cost next to finite ones (a non-finite input pixel) its loop can step
+                // back and forth between two evaluated shifts for ever -- MAX_CALLS only counts evaluations.  Finite
+                // costs never revisit (a few visits here between two evaluations at most), so this changes no result;
+                // it turns a hung GPU into a failed pixel (err = 0).
+                if (++idle > 16) { st = 0; done = true; break; }
+                skip_limit = false;
+                // minus / plus neighbour along the axis: logical cells (2, 1) / (2, 3) or (1, 2) / (3, 2)
+                const int lo = axis ? 7 : 11, hi = axis ? 17 : 13;
+                if (!((known >> lo) & 1u)) { sr = 2 - axis; sc = 1 + axis; req = R_LO; break; }
+                if (!((known >> hi) & 1u)) { sr = 2 + axis; sc = 3 - axis; req = R_HI; break; }
+                const double dl = d[walk_cell(b0, b1, 2 - axis, 1 + axis)], dh = d[walk_cell(b0, b1, 2 + axis, 3 - axis)];
+                const bool up_m = dl > dc + tol, up_p = dh > dc - tol;
+                if (up_m && up_p) {                    // bracketed on this axis
+                    const int dir = dl < dh ? -1 : 1;
+                    if (axis) settled1 = dir; else settled0 = dir;
+                    if ((axis ? settled0 : settled1) == 0) { axis = 1 - axis; continue; }
+                    ip = d[walk_cell(b0, b1, 3, 2)] < d[walk_cell(b0, b1, 1, 2)] ? 1 : 0;
+                    jp = d[walk_cell(b0, b1, 2, 3)] < d[walk_cell(b0, b1, 2, 1)] ? 1 : 0;
+                    fill = true;
+                    continue;
+                }
+                uv[0] = c0; uv[1] = c1;                // best so far, Optim.cpp:421-423
+                out = dc;
+                bool plus = up_m;
+                if (!up_p && !up_m) plus = dh < dl;    // local maximum: go downhill
+                // one step along the axis (Optim.cpp:431-474): the cache moves with the centre
+                if (plus) {
+                    dc = dh;
+                    if (axis) { c0 += 1; b0 = b0 == 4 ? 0 : b0 + 1; known >>= 5; }
+                    else { c1 += 1; b1 = b1 == 4 ? 0 : b1 + 1; known = (known >> 1) & ~COL4; }
+                } else {
+                    dc = dl;
+                    if (axis) { c0 -= 1; b0 = b0 == 0 ? 4 : b0 - 1; known = (known << 5) & ALL; }
+                    else { c1 -= 1; b1 = b1 == 0 ? 4 : b1 - 1; known = (known << 1) & ~COL0 & ALL; }
+                }
+                if (axis) settled0 = 0; else settled1 = 0;
+            }
+            if (done) break;
+        }
+
+        // ---- the one evaluation site of the loop ----
         double v;
         const int se = eval(c0 + sr - 2, c1 + sc - 2, v, args);
         ncalls++;
         idle = 0;
-        if (se != UMPA_ST_OK) { st = se; break; }  // bound error: return at once (Optim.cpp:264,291,324,359)
+        if (se != UMPA_ST_OK) { st = se; break; }  // bound error: return at once (Optim.cpp:291,324,359)
 
-        // ---- file the result (selects, no branches: the lanes of a warp are at different points of their walks) ----
-        // 4x4 fill, lower value off-axis: hard restart at that shift (Optim.cpp:364-377) -- the walk continues as if it
-        // had started there, except that args / keep are NOT refreshed (see above) and the loop-head test is skipped
-        const bool restart = req == R_FILL && v < dc;
-        // keep = args after the centre, and after a minus / plus neighbour that is not higher than the centre
-        // (Optim.cpp:262, 294-296, 325-327; the two tests are not symmetric)
-        const bool take = req == R_CENTRE || ((req & (R_LO | R_HI)) && !(v > dc + (req == R_LO ? tol : -tol)));
-        keep.t = take ? args.t : keep.t;
-        keep.v = take ? args.v : keep.v;
-        args.t = restart ? keep.t : args.t;
-        args.v = restart ? keep.v : args.v;
-        c0 += restart ? sr - 2 : 0;
-        c1 += restart ? sc - 2 : 0;
-        sr = restart ? 2 : sr;
-        sc = restart ? 2 : sc;
-        known = restart ? 0u : known;
-        settled0 = restart ? 0 : settled0;
-        settled1 = restart ? 0 : settled1;
-        skip_limit = skip_limit || restart;
-        fill = fill && !restart;
-        dc = (restart || req == R_CENTRE) ? v : dc;
+        // ---- file the result ----
+        if (!PEEL && centre) {
+            centre = false;
+            keep = args;                           // Optim.cpp:262
+            dc = v;
+        } else if (req == R_FILL) {
+            // 4x4 fill, lower value off-axis: hard restart at that shift (Optim.cpp:364-377) -- the walk continues as if
+            // it had started there, except that args / keep are NOT refreshed (see above) and the loop-head test is
+            // skipped.  Rare, so it sits behind a branch: the eleven fill evaluations of a pixel pay one compare for it.
+            if (v < dc) {
+                args = keep;
+                c0 += sr - 2; c1 += sc - 2;
+                sr = 2; sc = 2;
+                known = 0u;
+                settled0 = 0; settled1 = 0;
+                skip_limit = true;
+                fill = false;
+                dc = v;
+            }
+        } else if (!(v > dc + (req == R_LO ? tol : -tol))) {
+            // a minus / plus neighbour that is not higher than the centre (Optim.cpp:294-296, 325-327; the two tests
+            // are not symmetric)
+            keep = args;
+        }
         d[walk_cell(b0, b1, sr, sc)] = v;
         known |= 1u << (5 * sr + sc);
-
-        // ---- advance this lane until it needs the next cost value (or is done) ----
-        bool done = false;
-        while (true) {
-            if (fill) {                            // next missing entry of the 4x4 block (row-major)
-                const unsigned pending = (0x7bdefu << (5 * ip + jp)) & ~known;    // 4 rows of 4 bits, 5 apart
-                if (!pending) { finished = true; done = true; break; }
-                const int slot = __ffs(pending) - 1;
-                sr = (slot * 13) >> 6;             // slot / 5 for slot < 64
-                sc = slot - 5 * sr;
-                req = R_FILL;
-                break;
-            }
-            // head of the reference's loop (Optim.cpp:267); a restart jumps past the test (goto start)
-            if (!skip_limit && ncalls >= UMPA_MAX_CALLS) { st = 0; done = true; break; }   // Optim.cpp:267,477
-            // Not in the reference: with a NaN cost next to finite ones (a non-finite input pixel) its loop can step
-            // back and forth between two evaluated shifts for ever -- MAX_CALLS only counts evaluations.  Finite
-            // costs never revisit (a few visits here between two evaluations at most), so this changes no result;
-            // it turns a hung GPU into a failed pixel (err = 0).
-            if (++idle > 16) { st = 0; done = true; break; }
-            skip_limit = false;
-            // minus / plus neighbour along the axis: logical cells (2, 1) / (2, 3) or (1, 2) / (3, 2)
-            const int lo = axis ? 7 : 11, hi = axis ? 17 : 13;
-            if (!((known >> lo) & 1u)) { sr = 2 - axis; sc = 1 + axis; req = R_LO; break; }
-            if (!((known >> hi) & 1u)) { sr = 2 + axis; sc = 3 - axis; req = R_HI; break; }
-            const double dl = d[walk_cell(b0, b1, 2 - axis, 1 + axis)], dh = d[walk_cell(b0, b1, 2 + axis, 3 - axis)];
-            const bool up_m = dl > dc + tol, up_p = dh > dc - tol;
-            if (up_m && up_p) {                    // bracketed on this axis
-                const int dir = dl < dh ? -1 : 1;
-                if (axis) settled1 = dir; else settled0 = dir;
-                if ((axis ? settled0 : settled1) == 0) { axis = 1 - axis; continue; }
-                ip = d[walk_cell(b0, b1, 3, 2)] < d[walk_cell(b0, b1, 1, 2)] ? 1 : 0;
-                jp = d[walk_cell(b0, b1, 2, 3)] < d[walk_cell(b0, b1, 2, 1)] ? 1 : 0;
-                fill = true;
-                continue;
-            }
-            uv[0] = c0; uv[1] = c1;                // best so far, Optim.cpp:421-423
-            out = dc;
-            bool plus = up_m;
-            if (!up_p && !up_m) plus = dh < dl;    // local maximum: go downhill
-            // one step along the axis (Optim.cpp:431-474): the cache moves with the centre
-            if (plus) {
-                dc = dh;
-                if (axis) { c0 += 1; b0 = b0 == 4 ? 0 : b0 + 1; known >>= 5; }
-                else { c1 += 1; b1 = b1 == 4 ? 0 : b1 + 1; known = (known >> 1) & ~COL4; }
-            } else {
-                dc = dl;
-                if (axis) { c0 -= 1; b0 = b0 == 0 ? 4 : b0 - 1; known = (known << 5) & ALL; }
-                else { c1 -= 1; b1 = b1 == 0 ? 4 : b1 - 1; known = (known << 1) & ~COL0 & ALL; }
-            }
-            if (axis) settled0 = 0; else settled1 = 0;
-        }
-        if (done) break;
     }
     ws.known = known; ws.b0 = b0; ws.b1 = b1; ws.c0 = c0; ws.c1 = c1; ws.ip = ip; ws.jp = jp;
     ws.finished = finished;
