@@ -130,7 +130,8 @@ def _run(L, o, i, j, abc=None, poison=None, subpx=-1, uv=(0., 0.)):
     return st, res, d, a, n.value
 
 
-@pytest.mark.parametrize("name", ["df_noisy", "nodf_noisy", "df_clean", "df_subpx0", "df_subpx1", "df_dxdy", "df_assign_ref", "dfk_clean"])
+@pytest.mark.parametrize("name", ["df_noisy", "nodf_noisy", "df_clean", "df_subpx0", "df_subpx1", "df_dxdy", "df_assign_ref", "dfk_clean",
+                                  "nodf_nw1", "df_nw3_ms6", "df_lowcontrast"])
 def test_walk_header_reproduces_the_oracle_walk(walk_lib, name):
     c = load_case(name)
     o = port.OracleModel(c["kind"], c["sam"], c["ref"], window_size=c["Nw"], max_shift=c["max_shift"])
